@@ -1,0 +1,528 @@
+// Warp-per-token ("row") kernels of the Transfusion hot path: adaptive LayerNorm (FiLM / text select),
+// branch-output gating backward, depth-wise AttentionResidual, final RMSNorm, token assemble,
+// qk-RMSNorm+RoPE backward.  All HBM-bound: one contiguous 512 B run per warp access, fp32 math,
+// warp-shuffle reductions, no shared memory.  Reference math: /root/reference/transfusion_pytorch/
+// transfusion.py:640-775 (AdaptiveWrapper), 779-829 (RMSNorm, AttentionResidual), 946-965 (qk norm, RoPE),
+// 3173-3184 (token select).
+#include "common.cuh"
+#include "../../include/tfx_b200.h"
+
+namespace tfx {
+
+struct PtrList { float* p[32]; };
+
+// ------------------------------------------------------------------------------------ adaLN forward
+// u = isM ? LN(x)*(gamma_c+1)+beta_c : LN(x)*(g+1)      (T.py:747-755; text-only 677-679)
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) adaln_fwd_k(const float* __restrict__ x, const int* __restrict__ cond_row,
+                                                          const float* __restrict__ film, long long film_ld,
+                                                          const float* __restrict__ g, __nv_bfloat16* __restrict__ u,
+                                                          float* __restrict__ stats, int M) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  float gv[NCH * 4];
+  load_row_f32<NCH>(g, lane, gv);
+  for (int row = warp0; row < M; row += nwarps) {
+    float v[NCH * 4];
+    load_row_f32<NCH>(x + (long long)row * D, lane, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+    const int cr = cond_row ? cond_row[row] : -1;
+    if (cr >= 0) {
+      float gm[NCH * 4], bt[NCH * 4];
+      load_row_f32<NCH>(film + cr * film_ld, lane, gm);
+      load_row_f32<NCH>(film + cr * film_ld + D, lane, bt);
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) v[i] = v[i] * rstd * (gm[i] + 1.f) + bt[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) v[i] = v[i] * rstd * (gv[i] + 1.f);
+    }
+    store_row_bf16<NCH>(u + (long long)row * D, lane, v);
+    if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+  }
+}
+
+// ------------------------------------------------------------------------------------ adaLN backward
+// dx += LN'(du * scale);  d(gamma_c) += du*xhat, d(beta_c) += du   (per cond row)   d(g) += du*xhat (text)
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) adaln_bwd_k(const float* __restrict__ du, const float* __restrict__ x,
+                                                          const float* __restrict__ stats, const int* __restrict__ cond_row,
+                                                          const float* __restrict__ film, long long film_ld, const float* __restrict__ g,
+                                                          float* __restrict__ dx, float* __restrict__ dfilm, long long dfilm_ld,
+                                                          float* __restrict__ dg, int M, int tpw) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
+  if (r0 >= M) return;
+  float gv[NCH * 4];
+  load_row_f32<NCH>(g, lane, gv);
+  float accA[NCH * 4], accB[NCH * 4];
+  int cur = -2;
+  auto flush = [&]() {
+    if (cur == -2) return;
+    if (cur >= 0) { red_row_f32<NCH>(dfilm + cur * dfilm_ld, lane, accA); red_row_f32<NCH>(dfilm + cur * dfilm_ld + D, lane, accB); }
+    else red_row_f32<NCH>(dg, lane, accA);
+  };
+  for (int row = r0; row < r1; ++row) {
+    const int cr = cond_row ? cond_row[row] : -1;
+    if (cr != cur) {
+      flush(); cur = cr;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) { accA[i] = 0.f; accB[i] = 0.f; }
+    }
+    float d[NCH * 4], xh[NCH * 4], sc[NCH * 4];
+    load_row_f32<NCH>(du + (long long)row * D, lane, d);
+    load_row_f32<NCH>(x + (long long)row * D, lane, xh);
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    if (cr >= 0) {
+      load_row_f32<NCH>(film + cr * film_ld, lane, sc);
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) sc[i] += 1.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) sc[i] = gv[i] + 1.f;
+    }
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) {
+      xh[i] = (xh[i] - mean) * rstd;
+      accA[i] += d[i] * xh[i];
+      accB[i] += d[i];
+      d[i] *= sc[i];
+      m1 += d[i]; m2 += d[i] * xh[i];
+    }
+    m1 = warp_sum(m1) * (1.f / D); m2 = warp_sum(m2) * (1.f / D);
+    float o[NCH * 4];
+    load_row_f32<NCH>(dx + (long long)row * D, lane, o);
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) o[i] += rstd * (d[i] - m1 - xh[i] * m2);
+    store_row_f32<NCH>(dx + (long long)row * D, lane, o);
+  }
+  flush();
+}
+
+// ------------------------------------------------------------------------------------ branch-output gate backward
+// forward was x_out = x_res + y * s,  s = isM ? sigmoid(z_c) : (layerscale+1)       (T.py:765-769)
+// dy = dx*s (bf16, feeds the dgrad / wgrad GEMMs);  d s accumulated per cond row / for layerscale.
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y,
+                                                          const int* __restrict__ cond_row, const float* __restrict__ zgate, long long zgate_ld,
+                                                          const float* __restrict__ ls, __nv_bfloat16* __restrict__ dy,
+                                                          float* __restrict__ dzgate, long long dzgate_ld, float* __restrict__ dls, int M, int tpw) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
+  if (r0 >= M) return;
+  const bool has_scale = ls != nullptr;
+  float lsv[NCH * 4];
+  if (has_scale) load_row_f32<NCH>(ls, lane, lsv);
+  float acc[NCH * 4];
+  int cur = -2;
+  auto flush = [&]() {
+    if (cur == -2 || !has_scale) return;
+    if (cur >= 0) red_row_f32<NCH>(dzgate + cur * dzgate_ld, lane, acc); else red_row_f32<NCH>(dls, lane, acc);
+  };
+  for (int row = r0; row < r1; ++row) {
+    const int cr = (cond_row && zgate) ? cond_row[row] : -1;
+    if (cr != cur) {
+      flush(); cur = cr;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) acc[i] = 0.f;
+    }
+    float d[NCH * 4];
+    load_row_f32<NCH>(dx + (long long)row * D, lane, d);
+    if (has_scale) {
+      float yv[NCH * 4], sc[NCH * 4];
+      load_row_bf16<NCH>(y + (long long)row * D, lane, yv);
+      if (cr >= 0) load_row_f32<NCH>(zgate + cr * zgate_ld, lane, sc);
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) {
+        const float s = cr >= 0 ? sc[i] : lsv[i] + 1.f;
+        acc[i] += d[i] * yv[i];
+        d[i] *= s;
+      }
+    }
+    store_row_bf16<NCH>(dy + (long long)row * D, lane, d);
+  }
+  flush();
+}
+
+// ------------------------------------------------------------------------------------ AttentionResidual forward
+// sim_l = <h_l, (gamma+1)*pq> / max(|h_l|, eps)   (sqrt(D) of the RMSNorm cancels the D^-1/2 scale)
+// x = sum_l softmax_l(sim) h_l           (T.py:803-829)   single pass, online softmax over depth.
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
+                                                             float* __restrict__ xo, __nv_bfloat16* __restrict__ xb, int M) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  float w[NCH * 4], t[NCH * 4];
+  load_row_f32<NCH>(gamma, lane, w);
+  load_row_f32<NCH>(pq, lane, t);
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) w[i] = (w[i] + 1.f) * t[i];
+  for (int row = warp0; row < M; row += nwarps) {
+    float acc[NCH * 4];
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) acc[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int k = 0; k < L1; ++k) {
+      float h[NCH * 4];
+      load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
+      float ss = 0.f, dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; }
+      ss = warp_sum(ss); dot = warp_sum(dot);
+      const float sim = dot / fmaxf(sqrtf(ss), 1e-12f);
+      const float mn = fmaxf(m, sim);
+      const float a = __expf(m - mn), b = __expf(sim - mn);
+      l = l * a + b; m = mn;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) acc[i] = acc[i] * a + h[i] * b;
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) acc[i] *= inv;
+    store_row_f32<NCH>(xo + (long long)row * D, lane, acc);
+    if (xb) store_row_bf16<NCH>(xb + (long long)row * D, lane, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------ AttentionResidual backward
+// dh_l += alpha_l*dx + dsim_l*(w/|h| - <h,w> h/|h|^3);   dw += dsim_l*h/|h|   (dw -> d gamma, d pq)
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) attn_res_bwd_k(PtrList hid, PtrList dhid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
+                                                             const float* __restrict__ dxo, float* __restrict__ dgamma, float* __restrict__ dpq, int M, int tpw) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
+  if (r0 >= M) return;
+  float w[NCH * 4], gv[NCH * 4], pv[NCH * 4], accw[NCH * 4];
+  load_row_f32<NCH>(gamma, lane, gv);
+  load_row_f32<NCH>(pq, lane, pv);
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) { w[i] = (gv[i] + 1.f) * pv[i]; accw[i] = 0.f; }
+  for (int row = r0; row < r1; ++row) {
+    float dxv[NCH * 4];
+    load_row_f32<NCH>(dxo + (long long)row * D, lane, dxv);
+    // pass 1: lane k keeps the scalars of hidden k
+    float my_sim = -INFINITY, my_da = 0.f, my_nrm = 1.f, my_dot = 0.f;
+    for (int k = 0; k < L1; ++k) {
+      float h[NCH * 4];
+      load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
+      float ss = 0.f, dot = 0.f, da = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; da += h[i] * dxv[i]; }
+      ss = warp_sum(ss); dot = warp_sum(dot); da = warp_sum(da);
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      if (lane == k) { my_sim = dot / nrm; my_da = da; my_nrm = nrm; my_dot = dot; }
+    }
+    const float mx = warp_max(my_sim);
+    const float e = lane < L1 ? __expf(my_sim - mx) : 0.f;
+    const float alpha = e / warp_sum(e);
+    const float mean_da = warp_sum(alpha * my_da);
+    const float dsim = alpha * (my_da - mean_da);
+    // pass 2
+    for (int k = 0; k < L1; ++k) {
+      const float a = __shfl_sync(0xffffffffu, alpha, k), ds = __shfl_sync(0xffffffffu, dsim, k);
+      const float nrm = __shfl_sync(0xffffffffu, my_nrm, k), dot = __shfl_sync(0xffffffffu, my_dot, k);
+      const float rn = 1.f / nrm, c2 = ds * dot * rn * rn * rn, c1 = ds * rn;
+      float h[NCH * 4], g[NCH * 4];
+      load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
+      load_row_f32<NCH>(dhid.p[k] + (long long)row * D, lane, g);
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) {
+        g[i] += a * dxv[i] + c1 * w[i] - c2 * h[i];
+        accw[i] += c1 * h[i];
+      }
+      store_row_f32<NCH>(dhid.p[k] + (long long)row * D, lane, g);
+    }
+  }
+  float t[NCH * 4];
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) t[i] = accw[i] * pv[i];
+  red_row_f32<NCH>(dgamma, lane, t);
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) t[i] = accw[i] * (gv[i] + 1.f);
+  red_row_f32<NCH>(dpq, lane, t);
+}
+
+// ------------------------------------------------------------------------------------ final RMSNorm
+// out = x / max(|x|,eps) * sqrt(D) * (gamma+1)      (T.py:779-786, 1250); optional compaction of modality rows
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) rmsnorm_fwd_k(const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ of,
+                                                            __nv_bfloat16* __restrict__ ob, const int* __restrict__ slot, __nv_bfloat16* __restrict__ omod, int M) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  float gv[NCH * 4];
+  load_row_f32<NCH>(gamma, lane, gv);
+  const float c = sqrtf((float)D);
+  for (int row = warp0; row < M; row += nwarps) {
+    float v[NCH * 4];
+    load_row_f32<NCH>(x + (long long)row * D, lane, v);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) ss += v[i] * v[i];
+    const float r = c / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) v[i] = v[i] * r * (gv[i] + 1.f);
+    if (of) store_row_f32<NCH>(of + (long long)row * D, lane, v);
+    if (ob) store_row_bf16<NCH>(ob + (long long)row * D, lane, v);
+    if (slot && omod) { const int s = slot[row]; if (s >= 0) store_row_bf16<NCH>(omod + (long long)s * D, lane, v); }
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) rmsnorm_bwd_k(const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            float* __restrict__ dx, float* __restrict__ dgamma, int M, int tpw) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
+  if (r0 >= M) return;
+  float gv[NCH * 4], acc[NCH * 4];
+  load_row_f32<NCH>(gamma, lane, gv);
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) acc[i] = 0.f;
+  const float c = sqrtf((float)D);
+  for (int row = r0; row < r1; ++row) {
+    float v[NCH * 4], d[NCH * 4];
+    load_row_f32<NCH>(x + (long long)row * D, lane, v);
+    load_row_f32<NCH>(dout + (long long)row * D, lane, d);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) ss += v[i] * v[i];
+    const float rn = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) {
+      v[i] *= rn;                              // xhat
+      acc[i] += d[i] * v[i] * c;
+      d[i] *= c * (gv[i] + 1.f);               // d xhat
+      dot += d[i] * v[i];
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) d[i] = rn * (d[i] - v[i] * dot);
+    store_row_f32<NCH>(dx + (long long)row * D, lane, d);
+  }
+  red_row_f32<NCH>(dgamma, lane, acc);
+}
+
+// ------------------------------------------------------------------------------------ token assemble (+ backward)
+// x0 = isM ? modality_token[slot] : text_embed[max(id,0)]         (T.py:3173-3184)
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) embed_assemble_k(const int* __restrict__ text_id, const float* __restrict__ emb, const float* __restrict__ modtok,
+                                                               const int* __restrict__ slot, float* __restrict__ x0, __nv_bfloat16* __restrict__ x0b, int M) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp0; row < M; row += nwarps) {
+    const int s = slot ? slot[row] : -1;
+    float v[NCH * 4];
+    if (s >= 0) load_row_f32<NCH>(modtok + (long long)s * D, lane, v);
+    else { int id = text_id[row]; if (id < 0) id = 0; load_row_f32<NCH>(emb + (long long)id * D, lane, v); }
+    store_row_f32<NCH>(x0 + (long long)row * D, lane, v);
+    if (x0b) store_row_bf16<NCH>(x0b + (long long)row * D, lane, v);
+  }
+}
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) embed_bwd_k(const float* __restrict__ dx0, const int* __restrict__ text_id, const int* __restrict__ slot,
+                                                          float* __restrict__ demb, __nv_bfloat16* __restrict__ dmodtok, int M) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp0; row < M; row += nwarps) {
+    const int s = slot ? slot[row] : -1;
+    float v[NCH * 4];
+    load_row_f32<NCH>(dx0 + (long long)row * D, lane, v);
+    if (s >= 0) { if (dmodtok) store_row_bf16<NCH>(dmodtok + (long long)s * D, lane, v); }
+    else { int id = text_id[row]; if (id < 0) id = 0; red_row_f32<NCH>(demb + (long long)id * D, lane, v); }
+  }
+}
+
+// dst[row_map[s]] += src[s]   (modality rows of d(final-norm output) receive the flow-head gradient)
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) scatter_add_rows_k(float* __restrict__ dst, const float* __restrict__ src, const int* __restrict__ row_map, int S) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = warp0; s < S; s += nwarps) {
+    const int r = row_map[s];
+    if (r < 0) continue;
+    float a[NCH * 4], b[NCH * 4];
+    load_row_f32<NCH>(src + (long long)s * D, lane, a);
+    load_row_f32<NCH>(dst + (long long)r * D, lane, b);
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) b[i] += a[i];
+    store_row_f32<NCH>(dst + (long long)r * D, lane, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------ qk RMSNorm + RoPE backward, packs d[q|k|.|gates]
+// forward (GEMM epilogue): xhat = x*inv;  y = xhat*8*(gamma+1);  q = R(pos) y (interleaved pairs)   (T.py:950-965)
+// One warp per token, lane i owns the rope pair (2i, 2i+1) of every head.
+__global__ void __launch_bounds__(ROW_THREADS) qk_bwd_pack_k(const float* __restrict__ dq, const float* __restrict__ dk, const __nv_bfloat16* __restrict__ q,
+                                                            const __nv_bfloat16* __restrict__ k, const float* __restrict__ qk_inv, const float* __restrict__ gq,
+                                                            const float* __restrict__ gk, const int* __restrict__ rope_pos, const float2* __restrict__ rope_cs,
+                                                            const float* __restrict__ gates, const float* __restrict__ dsum, __nv_bfloat16* __restrict__ out,
+                                                            long long out_ld, float* __restrict__ dgq, float* __restrict__ dgk, int M, int H, int tpw) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
+  if (r0 >= M) return;
+  const int HI = H * 64;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const float g1[2][2] = {{gq[2 * lane] + 1.f, gq[2 * lane + 1] + 1.f}, {gk[2 * lane] + 1.f, gk[2 * lane + 1] + 1.f}};
+  for (int row = r0; row < r1; ++row) {
+    const float2 cs = rope_cs[(long long)rope_pos[row] * 32 + lane];
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const float* dsrc = which == 0 ? dq : dk;
+      const __nv_bfloat16* src = which == 0 ? q : k;
+      for (int h = 0; h < H; ++h) {
+        const long long off = (long long)row * HI + h * 64 + 2 * lane;
+        const float2 dr = *reinterpret_cast<const float2*>(dsrc + off);
+        const float2 r = unpack2_bf16(*reinterpret_cast<const uint32_t*>(src + off));
+        const float inv = qk_inv[(long long)row * 2 * H + which * H + h];
+        // un-rotate (R^T)
+        const float y0 = r.x * cs.x + r.y * cs.y, y1 = r.y * cs.x - r.x * cs.y;
+        const float dy0 = dr.x * cs.x + dr.y * cs.y, dy1 = dr.y * cs.x - dr.x * cs.y;
+        const float ga = g1[which][0], gb = g1[which][1];
+        const float xh0 = fabsf(ga) > 1e-12f ? y0 / (8.f * ga) : 0.f, xh1 = fabsf(gb) > 1e-12f ? y1 / (8.f * gb) : 0.f;
+        acc[which][0] += dy0 * xh0 * 8.f; acc[which][1] += dy1 * xh1 * 8.f;
+        const float dxh0 = dy0 * 8.f * ga, dxh1 = dy1 * 8.f * gb;
+        const float dot = warp_sum(xh0 * dxh0 + xh1 * dxh1);
+        const float o0 = inv * (dxh0 - xh0 * dot), o1 = inv * (dxh1 - xh1 * dot);
+        *reinterpret_cast<uint32_t*>(out + (long long)row * out_ld + which * HI + h * 64 + 2 * lane) = pack2_bf16(o0, o1);
+      }
+    }
+    // gate logits: d g = (1 - sigmoid(g)) * sum_d dO_gated * O_gated
+    if (lane < H) {
+      const float gl = gates[(long long)row * H + lane];
+      const float sg = 1.f / (1.f + __expf(-gl));
+      out[(long long)row * out_ld + 3 * HI + lane] = __float2bfloat16((1.f - sg) * dsum[(long long)row * H + lane]);
+    }
+  }
+  atomicAdd(dgq + 2 * lane, acc[0][0]); atomicAdd(dgq + 2 * lane + 1, acc[0][1]);
+  atomicAdd(dgk + 2 * lane, acc[1][0]); atomicAdd(dgk + 2 * lane + 1, acc[1][1]);
+}
+
+static inline int row_grid(int M, int sms) {
+  long long blocks = ((long long)M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  long long cap = (long long)sms * 8;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+static inline int chunk_grid(int M, int tpw) {
+  long long warps = ((long long)M + tpw - 1) / tpw;
+  return (int)((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+}
+int num_sms();
+
+}  // namespace tfx
+
+using namespace tfx;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int tfx_adaln_fwd(const float* x, const int* cond_row, const float* film, long long film_ld, const float* ln_gamma,
+                  void* u_bf16, float* stats, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  TFX_DISPATCH_NCH(D, (adaln_fwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(x, cond_row, film, film_ld, ln_gamma, (__nv_bfloat16*)u_bf16, stats, M)));
+  return check_launch("adaln_fwd");
+}
+
+int tfx_adaln_bwd(const float* du, const float* x, const float* stats, const int* cond_row, const float* film, long long film_ld,
+                  const float* ln_gamma, float* dx_accum, float* dfilm, long long dfilm_ld, float* dln_gamma, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  const int tpw = 16;
+  TFX_DISPATCH_NCH(D, (adaln_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(du, x, stats, cond_row, film, film_ld, ln_gamma, dx_accum, dfilm, dfilm_ld, dln_gamma, M, tpw)));
+  return check_launch("adaln_bwd");
+}
+
+int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, const float* zgate, long long zgate_ld, const float* layerscale,
+                  void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  const int tpw = 16;
+  TFX_DISPATCH_NCH(D, (resid_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(dx, (const __nv_bfloat16*)y_bf16, cond_row, zgate, zgate_ld, layerscale,
+                                                                                              (__nv_bfloat16*)dy_bf16, dzgate, dzgate_ld, dlayerscale, M, tpw)));
+  return check_launch("resid_bwd");
+}
+
+int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                          float* x_out, void* x_out_bf16, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
+  PtrList pl;
+  for (int i = 0; i < n_hiddens; ++i) pl.p[i] = const_cast<float*>(hiddens[i]);
+  TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, M)));
+  return check_launch("attn_residual_fwd");
+}
+
+int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                          const float* dx_out, float* dgamma, float* dpseudo_query, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
+  PtrList pl, dl;
+  for (int i = 0; i < n_hiddens; ++i) { pl.p[i] = const_cast<float*>(hiddens[i]); dl.p[i] = dhiddens[i]; }
+  const int tpw = 8;
+  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, dgamma, dpseudo_query, M, tpw)));
+  return check_launch("attn_residual_bwd");
+}
+
+int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  TFX_DISPATCH_NCH(D, (rmsnorm_fwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(x, gamma, out_f32, (__nv_bfloat16*)out_bf16, slot, (__nv_bfloat16*)out_mod_bf16, M)));
+  return check_launch("rmsnorm_fwd");
+}
+
+int tfx_rmsnorm_bwd(const float* dout, const float* x, const float* gamma, float* dx, float* dgamma, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  const int tpw = 16;
+  TFX_DISPATCH_NCH(D, (rmsnorm_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(dout, x, gamma, dx, dgamma, M, tpw)));
+  return check_launch("rmsnorm_bwd");
+}
+
+int tfx_embed_assemble(const int* text_id, const float* emb, const float* modtok, const int* slot, float* x0, void* x0_bf16, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  TFX_DISPATCH_NCH(D, (embed_assemble_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(text_id, emb, modtok, slot, x0, (__nv_bfloat16*)x0_bf16, M)));
+  return check_launch("embed_assemble");
+}
+
+int tfx_embed_bwd(const float* dx0, const int* text_id, const int* slot, float* demb, void* dmodtok_bf16, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  TFX_DISPATCH_NCH(D, (embed_bwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(dx0, text_id, slot, demb, (__nv_bfloat16*)dmodtok_bf16, M)));
+  return check_launch("embed_bwd");
+}
+
+int tfx_scatter_add_rows(float* dst, const float* src, const int* row_map, int S, int D, void* stream) {
+  if (S <= 0) return 0;
+  TFX_DISPATCH_NCH(D, (scatter_add_rows_k<NCH><<<row_grid(S, num_sms()), ROW_THREADS, 0, ST(stream)>>>(dst, src, row_map, S)));
+  return check_launch("scatter_add_rows");
+}
+
+int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const void* k_bf16, const float* qk_inv, const float* q_gamma, const float* k_gamma,
+                    const int* rope_pos, const float* rope_cs, const float* gates, const float* dsum, void* dqkvg_bf16, long long out_ld,
+                    float* dq_gamma, float* dk_gamma, int M, int H, void* stream) {
+  if (M <= 0) return 0;
+  TFX_REQUIRE(H >= 1 && H <= 32, "qk_bwd_pack: heads %d out of range", H);
+  const int tpw = 16;
+  qk_bwd_pack_k<<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(dq, dk, (const __nv_bfloat16*)q_bf16, (const __nv_bfloat16*)k_bf16, qk_inv, q_gamma, k_gamma, rope_pos,
+                                                                     (const float2*)rope_cs, gates, dsum, (__nv_bfloat16*)dqkvg_bf16, out_ld, dq_gamma, dk_gamma, M, H, tpw);
+  return check_launch("qk_bwd_pack");
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+/* tfx_b200.h - C ABI of the B200-native Transfusion hot path (libtfx_b200.so, sm_100a only).
+ *
+ * The reference (lucidrains/transfusion-pytorch) has no FFI: its hot path is ATen calls inside
+ * transfusion_pytorch/transfusion.py ("T.py") and modality_processing.py ("MP.py").  Each entry
+ * point below replaces the ATen call sites cited beside it; the Python host in
+ * transfusion_pytorch_b200/ binds them with ctypes (see INTEGRATION.md for the stub a maintainer of
+ * the reference would add).
+ *
+ * Conventions: plain device pointers (no torch types), explicit sizes and row pitches in ELEMENTS,
+ * `stream` is a cudaStream_t passed as void*, every call is asynchronous on that stream, allocates
+ * nothing, and returns 0 or a negative code with the message in tfx_last_error() (thread-local).
+ * bf16 buffers are passed as void*.  "M" is the number of packed tokens of the ragged batch.
+ */
+#ifndef TFX_B200_H
+#define TFX_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFX_B200_VERSION 100
+
+const char* tfx_last_error(void);
+int tfx_version(void);
+int tfx_init(int device);                       /* checks the device is sm_10x */
+
+/* ---------------------------------------------------------------- tcgen05 GEMM family
+ * D[m][n] = sum_k A(m,k) B(n,k); operands bf16, fp32 accumulation in TMEM.
+ * x_mn_major = 0: operand stored [MN][K] (row pitch ld); 1: stored [K][MN].                      */
+
+/* generic: out = alpha*acc + bias[n]  -> fp32 (store / atomic accumulate, optional per-row offsets) and/or bf16.
+ * Replaces nn.Linear call sites with no fused tail: to_time_cond Linear (T.py:1070,1132), to_film /
+ * to_ada_ln_zero evaluated per distinct time (T.py:700,712,749,767), to_text_logits (T.py:3280,2640),
+ * model_to_latent (T.py:3302), latent_to_model (MP.py:667), and every dgrad / wgrad product of autograd. */
+int tfx_gemm_store(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M, int N, int K,
+                   float* out_f32, long long ld_f32, void* out_bf16, long long ld_bf16, const float* bias, const long long* row_off,
+                   float alpha, int accumulate, int k_splits, void* stream);
+
+/* to_qk | to_v | to_gates in one GEMM (W packed [3*H*64 + 128][D]: q rows, k rows, v rows, gate rows, zero pad) with the
+ * per-head qk-RMSNorm and interleaved-pair RoPE applied in the epilogue.  T.py:946 (to_qk, to_v), 950-952
+ * (q_norm, k_norm), 964-965 (apply_rotary_emb), 1027 (to_gates).  Outputs q,k (post-RoPE), v: bf16 [M][H*64];
+ * gates fp32 [M][H] (logits); qk_inv fp32 [M][2H] (saved 1/|x| for backward).                     */
+int tfx_gemm_qkvg(const void* u, long long ldu, const void* W, long long ldw, int M, int H, int D, void* q, void* k, void* v, float* gates, float* qk_inv,
+                  const float* q_gamma, const float* k_gamma, const int* rope_pos, const float* rope_cs, void* stream);
+
+/* branch output projection + AdaptiveWrapper output gate + residual:
+ *   y = [A | A2] W^T + bias ;  x_out = x_res + y * (cond_row[m] >= 0 ? zgate[cond_row[m]] : layerscale + 1)
+ * to_out (T.py:1031) / FeedForward net.3 (T.py:849) with T.py:765-769 and the residual adds T.py:1238,1242;
+ * with A2 != NULL and no gate it is skip_proj on cat(x, skip) (T.py:1217-1219) without materialising the concat. */
+int tfx_gemm_resid(const void* A, long long lda, const void* A2, long long lda2, int K1, const void* W, long long ldw, int M, int N, int K, const float* bias,
+                   const float* x_res, float* x_out, void* x_out_bf16, void* y_bf16, const int* cond_row, const float* zgate, long long zgate_ld,
+                   const float* layerscale, void* stream);
+
+/* FeedForward net.0 + GEGLU (T.py:833-834, 846-847): W1 packed so every 128-column tile is [64 value | 64 gate];
+ * writes the pre-activations vg [M][Np] (saved for backward) and h = gelu_erf(gate)*value [M][Np/2].           */
+int tfx_gemm_geglu(const void* u, long long ldu, const void* W1p, long long ldw, const float* b1p, int M, int Np, int K, void* vg, void* h, void* stream);
+
+/* ---------------------------------------------------------------- attention (T.py:998-1027, mask T.py:452-470)
+ * Flash-style, span mask from kv_limit[m] (last visible key of query m), tanh soft-cap, value gates in the epilogue.
+ * Tile tables (host-built, 64-row tiles that never straddle a sequence): forward per query tile, backward per key tile. */
+int tfx_attn_fwd(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
+                 const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
+                 void* o, long long ld_o, float* lse, int M, float scale, float softcap, void* stream);
+int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, int M, int H, void* stream);
+int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
+                 const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
+                 int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, void* stream);
+/* backward of the qk-RMSNorm + RoPE epilogue; packs d[q | k | (v written by attn_bwd) | gates] bf16 [M][out_ld] */
+int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const void* k_bf16, const float* qk_inv, const float* q_gamma, const float* k_gamma,
+                    const int* rope_pos, const float* rope_cs, const float* gates, const float* dsum_mh, void* dqkvg_bf16, long long out_ld,
+                    float* dq_gamma, float* dk_gamma, int M, int H, void* stream);
+
+/* ---------------------------------------------------------------- warp-per-token kernels (D = model dim, multiple of 128, <= 1024)
+ * AdaptiveWrapper input side (T.py:747-755, text-only 677-679): u = isM ? LN(x)(gamma_c+1)+beta_c : LN(x)(g+1).
+ * film points at [n_cond][film_ld] with gamma at +0 and beta at +D; cond_row NULL = all text.      */
+int tfx_adaln_fwd(const float* x, const int* cond_row, const float* film, long long film_ld, const float* ln_gamma,
+                  void* u_bf16, float* stats, int M, int D, void* stream);
+int tfx_adaln_bwd(const float* du, const float* x, const float* stats, const int* cond_row, const float* film, long long film_ld,
+                  const float* ln_gamma, float* dx_accum, float* dfilm, long long dfilm_ld, float* dln_gamma, int M, int D, void* stream);
+/* backward of the output gate of tfx_gemm_resid: dy = dx*scale (bf16), d zgate / d layerscale accumulated */
+int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, const float* zgate, long long zgate_ld, const float* layerscale,
+                  void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, int M, int D, void* stream);
+/* AttentionResidual (T.py:803-829): softmax mix over all hiddens so far, single pass */
+int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                          float* x_out, void* x_out_bf16, int M, int D, void* stream);
+int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                          const float* dx_out, float* dgamma, float* dpseudo_query, int M, int D, void* stream);
+/* final RMSNorm (T.py:1250, 785-786) (+ compaction of modality rows for the flow head) */
+int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream);
+int tfx_rmsnorm_bwd(const float* dout, const float* x, const float* gamma, float* dx, float* dgamma, int M, int D, void* stream);
+/* token assemble: where(is_modality, modality_token, text_embed[id]) (T.py:3173-3184) and its backward */
+int tfx_embed_assemble(const int* text_id, const float* emb, const float* modtok, const int* slot, float* x0, void* x0_bf16, int M, int D, void* stream);
+int tfx_embed_bwd(const float* dx0, const int* text_id, const int* slot, float* demb, void* dmodtok_bf16, int M, int D, void* stream);
+int tfx_scatter_add_rows(float* dst, const float* src, const int* row_map, int S, int D, void* stream);
+
+/* ---------------------------------------------------------------- elementwise / reductions
+ * flow-match noise inject (MP.py:645-656): noised = x t + eps (1-t) ; flow = x - eps.  eps NULL = plain cast. */
+int tfx_flow_noise(const float* x, const float* eps, const float* t_row, void* noised_bf16, long long ld_noised, float* noised_f32, float* flow, long long S, int dl, void* stream);
+/* RandomFourierEmbed (T.py:625-635): [t, sin(2 pi t w), cos(2 pi t w)] zero padded to ld */
+int tfx_time_features(const float* times, const float* fourier_w, void* feats_bf16, int n, int half_dim, int ld, void* stream);
+/* small table ops of the conditioning path: op 0 sigmoid(a), 1 silu(a), 2 a*b*(1-b), 3 a*silu'(b), 4 copy */
+int tfx_table_op(const float* a, long long ld_a, const float* b, long long ld_b, float* out_f32, long long ld_of, void* out_bf16, long long ld_ob, long long rows, int cols,
+                 int op, void* stream);
+int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, void* stream);
+/* text cross-entropy fwd+bwd (T.py:3320-3331; text-only 2653-2659 with vlimit = num_text_tokens) */
+int tfx_ce_fwd_bwd(const float* logits, long long ld_logits, const int* labels, int V, int vlimit, float gscale, void* dlogits_bf16, long long ld_dlogits,
+                   double* loss_sum, int* n_valid, int M, void* stream);
+/* flow MSE fwd+bwd (T.py:3354-3362) */
+int tfx_mse_fwd_bwd(const float* pred, long long ld_pred, const float* flow, void* dpred_bf16, long long ld_dpred, float gscale, double* sumsq, long long S, int dl, void* stream);
+int tfx_colsum_bf16(const void* in_bf16, long long ld, long long M, int N, const int* col_map, float* out, void* stream);
+int tfx_colsum_f32(const float* in, long long ld, long long M, int N, float* out, void* stream);
+int tfx_cast_pack(const float* src, long long ld_src, int C_src, const int* row_src, void* dst_bf16, long long R_dst, int C_dst, void* stream);
+int tfx_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+int tfx_scale_f32(float* p, const float* scale_ptr, float scale, long long n, void* stream);
+int tfx_scale_bf16(void* p_bf16, const float* scale_ptr, long long n, void* stream);          /* p *= *scale_ptr (device scalar) */
+int tfx_axpy_f32(float* y, const float* x, float a, long long n, void* stream);   /* y += a*x */
+int tfx_rope_table(const float* freqs, float* cos_sin, int max_pos, int n_freqs, void* stream);
+/* fused Adam / AdamW over the flat parameter buffer (the optimizer the reference's examples use, train_latent_with_text.py:142-153) */
+int tfx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int decoupled_wd, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFX_B200_H */

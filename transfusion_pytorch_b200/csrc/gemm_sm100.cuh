@@ -31,10 +31,12 @@ struct GemmParams {
   const long long* row_off;    // optional per-output-row element offset into out_f32 (-1 = skip row); replaces m*ld_f32
   float alpha;
   int accumulate_f32;          // 1: out_f32 += (red.add)
-  // ---- EPI_QKVG (N tile 128: [0,4) q | [4,8) k | [8,12) v | 12 gates)
-  __nv_bfloat16 *q, *k, *v;    // [M][512]
-  float* gates;                // [M][8]   raw gate logits
-  float* qk_inv;               // [M][16]  1/max(|x|,eps) for q heads 0..7 then k heads 0..7
+  int K1;                      // A is the concatenation [A | A2] along K; A2 starts at k = K1 (K1 % 64 == 0); K1 = K when unused
+  // ---- EPI_QKVG (N tile 128 = 2 heads: H/2 q tiles | H/2 k tiles | H/2 v tiles | 1 gate tile)
+  int H;                       // heads (even), head dim 64
+  __nv_bfloat16 *q, *k, *v;    // [M][H*64]
+  float* gates;                // [M][H]   raw gate logits
+  float* qk_inv;               // [M][2H]  1/max(|x|,eps) for q heads then k heads
   const float *q_gamma, *k_gamma;   // [64]
   const int* rope_pos;         // [M]
   const float2* rope_cs;       // [max_pos][32] (cos, sin)
@@ -42,8 +44,9 @@ struct GemmParams {
   const float* x_res; float* x_out; __nv_bfloat16* x_out_bf16;     // [M][N]
   __nv_bfloat16* y_bf16;       // [M][N] optional (pre-scale branch output, saved for backward)
   const int* cond_row;         // [M]  >=0: modality token -> row of zgate; <0: text token
-  const float* zgate;          // [n_cond][N]  sigmoid(to_ada_ln_zero(cond))
-  const float* ls1;            // [N] layerscale + 1   (null with zgate null => scale = 1)
+  const float* zgate;          // [n_cond][zgate_ld]  sigmoid(to_ada_ln_zero(cond))
+  long long zgate_ld;
+  const float* ls;             // [N] layerscale (scale = ls + 1 for text rows); null => scale = 1
   // ---- EPI_GEGLU (N tile 128 = [64 value cols | 64 gate cols], N = 2*inner_pad)
   __nv_bfloat16* vg;           // [M][N] pre-activation (value|gate interleaved per tile), saved for backward
   __nv_bfloat16* h;            // [M][N/2] gelu(gate)*value
@@ -67,7 +70,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -115,7 +118,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* sB = sA + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (!A_MN) {
-            tma_load_2d(&tmA, &full_bar[stage], sA, kb * GEMM_BK, m_blk * GEMM_BM);
+            if (kb * GEMM_BK < p.K1) tma_load_2d(&tmA, &full_bar[stage], sA, kb * GEMM_BK, m_blk * GEMM_BM);
+            else tma_load_2d(&tmA2, &full_bar[stage], sA, kb * GEMM_BK - p.K1, m_blk * GEMM_BM);
           } else {
 #pragma unroll
             for (int a = 0; a < GEMM_BM / 64; ++a)
@@ -235,7 +239,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else if constexpr (EPI == EPI_QKVG) {
         static_assert(EPI != EPI_QKVG || BN == 128, "QKVG epilogue expects 128-wide N tiles");
-        const int kind = n_blk >> 2;          // 0 q, 1 k, 2 v, 3 gates
+        const int tps = p.H >> 1;             // tiles per section
+        const int kind = n_blk / tps;         // 0 q, 1 k, 2 v, 3 gates
+        const int tis = n_blk - kind * tps;   // tile in section
+        const long long HI = (long long)p.H * 64;
         if (kind <= 1) {
           const float* gamma = kind == 0 ? p.q_gamma : p.k_gamma;
           __nv_bfloat16* dstm = kind == 0 ? p.q : p.k;
@@ -251,10 +258,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) { float a = __uint_as_float(r0[j]), b = __uint_as_float(r1[j]); ss += a * a + b * b; }
             const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-            const int head = (n_blk & 3) * 2 + hh;
+            const int head = tis * 2 + hh;
             if (row_ok) {
-              p.qk_inv[(long long)row * 16 + kind * 8 + head] = inv;
-              __nv_bfloat16* dst = dstm + (long long)row * 512 + head * 64;
+              p.qk_inv[(long long)row * 2 * p.H + kind * p.H + head] = inv;
+              __nv_bfloat16* dst = dstm + (long long)row * HI + head * 64;
               const float sc = inv * 8.f;
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
@@ -281,7 +288,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32b_x32(taddr + c * 32, r);
             tmem_ld_wait();
             if (row_ok) {
-              __nv_bfloat16* dst = p.v + (long long)row * 512 + (n_blk & 3) * 128 + c * 32;
+              __nv_bfloat16* dst = p.v + (long long)row * HI + tis * 128 + c * 32;
 #pragma unroll
               for (int j = 0; j < 32; j += 8)
                 *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack_bf16(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
@@ -289,18 +296,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         } else {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(taddr, r);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
           if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(p.gates + (long long)row * 8);
-            dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
-            dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+            float* dst = p.gates + (long long)row * p.H;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < p.H) dst[j] = __uint_as_float(r[j]);
           }
         }
       } else if constexpr (EPI == EPI_RESID) {
         const int crow = (row_ok && p.cond_row) ? p.cond_row[row] : -1;
-        const float* srow = (p.zgate && crow >= 0) ? p.zgate + (long long)crow * p.N : p.ls1;   // ls1 holds layerscale+1
+        const float* zrow = (p.zgate && crow >= 0) ? p.zgate + (long long)crow * p.zgate_ld : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -322,7 +329,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 32; j += 4) {
               const float4 xr = *reinterpret_cast<const float4*>(p.x_res + off + j);
               float4 s = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (srow) s = *reinterpret_cast<const float4*>(srow + cbase + j);
+              if (zrow) s = *reinterpret_cast<const float4*>(zrow + cbase + j);
+              else if (p.ls) { s = *reinterpret_cast<const float4*>(p.ls + cbase + j); s.x += 1.f; s.y += 1.f; s.z += 1.f; s.w += 1.f; }
               o[j] = xr.x + y[j] * s.x; o[j + 1] = xr.y + y[j + 1] * s.y; o[j + 2] = xr.z + y[j + 2] * s.z; o[j + 3] = xr.w + y[j + 3] * s.w;
               *reinterpret_cast<float4*>(p.x_out + off + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
             }
@@ -409,15 +417,28 @@ struct GemmOperand {
   const void* ptr;
   long long ld;      // row pitch in elements of the stored matrix
   bool mn_major;     // false: stored [MN][K];  true: stored [K][MN]
+  const void* ptr2 = nullptr;   // optional second K segment of A (K-major only), starting at k = GemmParams::K1
+  long long ld2 = 0;
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& p, int num_sms, cudaStream_t stream) {
+int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  CUtensorMap tmA, tmB;
+  GemmParams p = p_in;
+  CUtensorMap tmA, tmA2, tmB;
   int rc;
-  if (!A_MN) rc = make_tmap_bf16(&tmA, A.ptr, p.K, p.M, A.ld, GEMM_BM); else rc = make_tmap_bf16(&tmA, A.ptr, p.M, p.K, A.ld, GEMM_BK);
+  const bool two = (!A_MN) && A.ptr2 != nullptr;
+  if (!two) p.K1 = p.K;
+  if (!A_MN) rc = make_tmap_bf16(&tmA, A.ptr, two ? p.K1 : p.K, p.M, A.ld, GEMM_BM); else rc = make_tmap_bf16(&tmA, A.ptr, p.M, p.K, A.ld, GEMM_BK);
   if (rc) return rc;
+  if (two) { rc = make_tmap_bf16(&tmA2, A.ptr2, p.K - p.K1, p.M, A.ld2, GEMM_BM); if (rc) return rc; } else tmA2 = tmA;
+  {
+    const int kbt = (p.K + GEMM_BK - 1) / GEMM_BK;
+    if (p.k_splits < 1) p.k_splits = 1;
+    if (p.k_splits > kbt) p.k_splits = kbt;
+    const int per = (kbt + p.k_splits - 1) / p.k_splits;
+    p.k_splits = (kbt + per - 1) / per;            // no empty split
+  }
   if (!B_MN) rc = make_tmap_bf16(&tmB, B.ptr, p.K, p.N, B.ld, BN); else rc = make_tmap_bf16(&tmB, B.ptr, p.N, p.K, B.ld, GEMM_BK);
   if (rc) return rc;
   auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, EPI>;
@@ -430,7 +451,7 @@ int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& 
   const int items = m_tiles * n_tiles * p.k_splits;
   if (items <= 0) return 0;
   const int grid = items < num_sms ? items : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -1,0 +1,622 @@
+"""B200 engine: drives the C-ABI kernels (libtfx_b200.so) for the Transfusion block stack - forward,
+backward, loss heads and the fused optimizer - over the ragged descriptor built by
+`modality_processing.pack_batch`.
+
+PyTorch supplies device memory, the current stream and (for data parallel) `torch.distributed`; every
+floating-point operation of the hot path is a kernel of this repository.  There is no CPU or eager
+fallback: constructing the engine without the built extension, or on a non-CUDA device, raises.
+
+Data flow of one layer (reference transfusion.py:1203-1246, math restated in SURVEY.md appendix A):
+
+    x_in --(skip_proj GEMM, K = [x | skip])--> x_a --adaLN--> u_A --GEMM qkvg (+qk-norm, RoPE)--> q,k,v,g
+         --flash attention (span mask, softcap, value gate)--> o --GEMM to_out (+gate, +residual)--> x_b
+         --adaLN--> u_F --GEMM ffn_in (+GEGLU)--> h --GEMM ffn_out (+gate, +residual)--> x_c = H[l]
+         --AttentionResidual over H[0..l]--> x_in of the next layer
+
+The residual stream and all normalisation statistics are fp32; GEMM / attention operands are bf16 with
+fp32 accumulation.
+"""
+from __future__ import annotations
+
+import math
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from .modality_processing import RaggedBatch
+
+BF16, F32, I32, I64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Engine:
+    def __init__(self, model):
+        self.ops = _lib.Ops()                       # raises loudly if the extension is missing
+        self.model = model
+        tr = model.transformer
+        self.D, self.H, self.depth = tr.dim, tr.heads, tr.depth
+        self.HI = self.H * 64
+        self.inner = tr.ff_inner
+        self.Ip = _round_up(self.inner, 64)
+        self.NQ = 3 * self.HI + 128                 # packed rows of [to_qk | to_v | to_gates | pad]
+        self.V = model.text_embed.weight.shape[0]
+        self.Vp = _round_up(self.V, 8)
+        self.Kt = _round_up(self.D + 1, 64)         # padded K of the time-cond Linear
+        self.W = 2 * self.depth                     # AdaptiveWrappers
+        self.softcap = tr.softcap_value
+        self.scale = 64 ** -0.5
+        self.dls = list(model.dim_latents)
+        self.dlp = [_round_up(d, 8) for d in self.dls]
+        assert self.D % 128 == 0 and self.D <= 1024, 'model dim must be a multiple of 128 and <= 1024 for the sm_100a row kernels'
+        assert self.H % 2 == 0 and 2 <= self.H <= 32, 'heads must be even (two 64-wide heads per 128-column GEMM tile)'
+        self.device = None
+        self.flat = None
+        self.ws = {}
+        self._packed_version = None
+        self._dirty = True
+        self._ptr_arrays = []
+        self.launches = 0
+
+    # ------------------------------------------------------------------ parameters
+    def _trainable(self):
+        m = self.model
+        skip = set()
+        for mod in list(m.modality_encoder) + list(m.modality_decoder):
+            if mod is not None:
+                skip |= {id(p) for p in mod.parameters()}
+        return [(n, p) for n, p in m.named_parameters() if p.requires_grad and id(p) not in skip]
+
+    def attach(self):
+        """Move all trainable parameters into one flat fp32 buffer (views keep the state_dict layout) with a
+        matching flat gradient buffer: one fused Adam launch, one all-reduce, wgrad GEMMs write straight in."""
+        named = self._trainable()
+        dev = named[0][1].device
+        if dev.type != 'cuda':
+            raise _lib.TfxError(f'the B200 engine needs the model on a CUDA device (got {dev}); there is no CPU path')
+        rc = self.ops.lib.tfx_init(dev.index if dev.index is not None else torch.cuda.current_device())
+        _lib.check(rc, 'tfx_init')
+        self.device = dev
+        offs, total = {}, 0
+        for n, p in named:
+            offs[n] = total
+            total += _round_up(p.numel(), 4)
+        flat = torch.zeros(total, device = dev, dtype = F32)
+        gflat = torch.zeros(total, device = dev, dtype = F32)
+        for n, p in named:
+            o, k = offs[n], p.numel()
+            flat[o:o + k].copy_(p.data.reshape(-1).float())
+            p.data = flat[o:o + k].view(p.shape)
+            p.grad = gflat[o:o + k].view(p.shape)
+        self.flat, self.gflat, self.offs, self.named = flat, gflat, offs, dict(named)
+        self.exp_avg = self.exp_avg_sq = None
+        self.opt_step = 0
+        self._first_ptr = named[0][1].data_ptr()
+        self._build_maps()
+        self._dirty = True
+
+    def ensure_attached(self):
+        named = self._trainable()
+        if self.flat is None or named[0][1].data_ptr() != self._first_ptr:
+            self.attach()
+
+    def P(self, name):            # parameter tensor by state-dict name
+        return self.named[name]
+
+    def G(self, name):            # gradient view inside the flat buffer
+        o, p = self.offs[name], self.named[name]
+        return self.gflat[o:o + p.numel()].view(p.shape)
+
+    def _build_maps(self):
+        """Row maps between packed bf16 operand layouts and the state-dict parameter layouts."""
+        dev, D, HI, H, inner, Ip = self.device, self.D, self.HI, self.H, self.inner, self.Ip
+        # W1 packed: tile t = [value rows 64t.. | gate rows inner+64t..]; rows past `inner` are padding
+        src = np.full(2 * Ip, -1, dtype = np.int64)
+        for t in range(Ip // 64):
+            for j in range(64):
+                c = 64 * t + j
+                if c < inner:
+                    src[128 * t + j] = c
+                    src[128 * t + 64 + j] = inner + c
+        self.w1_row_src = torch.from_numpy(src.astype(np.int32)).to(dev)
+        self.w1_row_src64 = torch.from_numpy(src).to(dev)
+        self.layer_maps = []
+        for i in range(self.depth):
+            pre = f'transformer.layers.{i}'
+            w1_off = self.offs[f'{pre}.2.fn.net.0.weight']
+            b1_off = self.offs[f'{pre}.2.fn.net.0.bias']
+            w1_rows = torch.where(self.w1_row_src64 >= 0, w1_off + self.w1_row_src64 * D, torch.full_like(self.w1_row_src64, -1))
+            b1_cols = torch.where(self.w1_row_src64 >= 0, b1_off + self.w1_row_src64, torch.full_like(self.w1_row_src64, -1)).to(I32)
+            q_off, v_off, g_off = self.offs[f'{pre}.1.fn.to_qk.0.weight'], self.offs[f'{pre}.1.fn.to_v.0.weight'], self.offs[f'{pre}.1.fn.to_gates.0.weight']
+            r = np.full(self.NQ, -1, dtype = np.int64)
+            r[:2 * HI] = q_off + np.arange(2 * HI) * D
+            r[2 * HI:3 * HI] = v_off + np.arange(HI) * D
+            r[3 * HI:3 * HI + H] = g_off + np.arange(H) * D
+            w2_off = self.offs[f'{pre}.2.fn.net.3.weight']
+            w2_rows = torch.from_numpy(w2_off + np.arange(D, dtype = np.int64) * inner).to(dev)
+            self.layer_maps.append(dict(w1_rows = w1_rows.contiguous(), b1_cols = b1_cols.contiguous(), qkvg_rows = torch.from_numpy(r).to(dev), w2_rows = w2_rows))
+        # conditioning tables: wrapper w occupies columns [w*3D, (w+1)*3D): gamma | beta | z
+        rows = np.full(self.W * 3 * D, -1, dtype = np.int64)
+        bias_idx = np.zeros(self.W * 3 * D, dtype = np.int64)
+        for w in range(self.W):
+            i, j = divmod(w, 2)
+            pre = f'transformer.layers.{i}.{j + 1}'
+            fo, zo = self.offs[f'{pre}.to_film.weight'], self.offs[f'{pre}.to_ada_ln_zero.weight']
+            rows[w * 3 * D: w * 3 * D + 2 * D] = fo + np.arange(2 * D) * 4 * D
+            rows[w * 3 * D + 2 * D: (w + 1) * 3 * D] = zo + np.arange(D) * 4 * D
+            bias_idx[w * 3 * D: w * 3 * D + 2 * D] = self.offs[f'{pre}.to_film.bias'] + np.arange(2 * D)
+            bias_idx[w * 3 * D + 2 * D: (w + 1) * 3 * D] = self.offs[f'{pre}.to_ada_ln_zero.bias'] + np.arange(D)
+        self.fz_rows = torch.from_numpy(rows).to(dev)
+        self.fz_bias_idx = torch.from_numpy(bias_idx).to(dev)
+        tw = self.offs['transformer.to_time_cond.1.weight']
+        self.wt_rows = torch.from_numpy(tw + np.arange(4 * D, dtype = np.int64) * (D + 1)).to(dev)
+
+    def buf(self, name, shape, dtype, zero = False):
+        t = self.ws.get(name)
+        n = int(np.prod(shape)) if len(shape) else 1
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), device = self.device, dtype = dtype)
+            self.ws[name] = t
+            if zero:
+                t.zero_()
+        return t[:n].view(shape)
+
+    def pack_weights(self):
+        """fp32 master parameters -> bf16 GEMM operands in kernel layouts (once per optimizer step)."""
+        if not self._dirty and self._packed_version == self.flat._version:
+            return
+        o, D, HI, H, Ip, inner = self.ops, self.D, self.HI, self.H, self.Ip, self.inner
+        pk = self.packed = getattr(self, 'packed', {})
+        def dst(name, rows, cols):
+            t = pk.get(name)
+            if t is None:
+                t = pk[name] = torch.zeros(rows, cols, device = self.device, dtype = BF16)
+            return t
+        for i in range(self.depth):
+            pre = f'transformer.layers.{i}'
+            wq = dst(f'qkvg{i}', self.NQ, D)
+            o.cast_pack(self.P(f'{pre}.1.fn.to_qk.0.weight'), D, D, None, wq, 2 * HI, D)
+            o.cast_pack(self.P(f'{pre}.1.fn.to_v.0.weight'), D, D, None, wq[2 * HI:], HI, D)
+            o.cast_pack(self.P(f'{pre}.1.fn.to_gates.0.weight'), D, D, None, wq[3 * HI:], H, D)
+            o.cast_pack(self.P(f'{pre}.1.fn.to_out.1.weight'), HI, HI, None, dst(f'wo{i}', D, HI), D, HI)
+            o.cast_pack(self.P(f'{pre}.2.fn.net.0.weight'), D, D, self.w1_row_src, dst(f'w1{i}', 2 * Ip, D), 2 * Ip, D)
+            o.cast_pack(self.P(f'{pre}.2.fn.net.3.weight'), inner, inner, None, dst(f'w2{i}', D, Ip), D, Ip)
+            b1 = self.P(f'{pre}.2.fn.net.0.bias')
+            pk[f'b1{i}'] = torch.where(self.w1_row_src64 >= 0, b1[self.w1_row_src64.clamp(min = 0)], torch.zeros((), device = self.device))
+            if f'{pre}.0.weight' in self.named:
+                o.cast_pack(self.P(f'{pre}.0.weight'), 2 * D, 2 * D, None, dst(f'wskip{i}', D, 2 * D), D, 2 * D)
+        m = self.model
+        o.cast_pack(self.P('to_text_logits.weight'), D, D, None, dst('wvocab', self.V, D), self.V, D)
+        for t, (dl, dlp) in enumerate(zip(self.dls, self.dlp)):
+            o.cast_pack(self.P(f'model_to_latent_projs.{t}.weight'), D, D, None, dst(f'wm2l{t}', dl, D), dl, D)
+            if f'latent_to_model_projs.{t}.weight' in self.named:
+                o.cast_pack(self.P(f'latent_to_model_projs.{t}.weight'), dl, dl, None, dst(f'wl2m{t}', D, dlp), D, dlp)
+        o.cast_pack(self.P('transformer.to_time_cond.1.weight'), D + 1, D + 1, None, dst('wt', 4 * D, self.Kt), 4 * D, self.Kt)
+        wfz = dst('wfz', self.W * 3 * D, 4 * D)
+        bfz = pk.get('bfz')
+        if bfz is None:
+            bfz = pk['bfz'] = torch.empty(self.W * 3 * D, device = self.device, dtype = F32)
+        for w in range(self.W):
+            i, j = divmod(w, 2)
+            pre = f'transformer.layers.{i}.{j + 1}'
+            o.cast_pack(self.P(f'{pre}.to_film.weight'), 4 * D, 4 * D, None, wfz[w * 3 * D:], 2 * D, 4 * D)
+            o.cast_pack(self.P(f'{pre}.to_ada_ln_zero.weight'), 4 * D, 4 * D, None, wfz[w * 3 * D + 2 * D:], D, 4 * D)
+            bfz[w * 3 * D: w * 3 * D + 2 * D].copy_(self.P(f'{pre}.to_film.bias'))
+            bfz[w * 3 * D + 2 * D: (w + 1) * 3 * D].copy_(self.P(f'{pre}.to_ada_ln_zero.bias'))
+        self._dirty = False
+        self._packed_version = self.flat._version
+
+    # ------------------------------------------------------------------ descriptor upload
+    def upload(self, rb: RaggedBatch):
+        """One pinned staging buffer, one H2D copy for all integer metadata; one for the float metadata."""
+        if rb.dev:
+            return rb.dev
+        ints = [rb.text_id, rb.label, rb.kv_limit, rb.rope_pos, rb.cond_row, rb.slot, rb.tile_q0, rb.tile_qend, rb.tile_kv0, rb.tile_kvend,
+                rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend, rb.row_token]
+        names = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
+                 'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token']
+        sizes = [_round_up(a.shape[0], 4) for a in ints]
+        host = torch.empty(sum(sizes), dtype = I32).pin_memory()
+        hv = host.numpy()
+        off = 0
+        for a, s in zip(ints, sizes):
+            hv[off:off + a.shape[0]] = a; off += s
+        devbuf = host.to(self.device, non_blocking = True)
+        d, off = {}, 0
+        for n, a, s in zip(names, ints, sizes):
+            d[n] = devbuf[off:off + a.shape[0]]; off += s
+        fl = np.concatenate([rb.cond_times, rb.row_time]).astype(np.float32)
+        if fl.shape[0]:
+            fdev = torch.from_numpy(fl).pin_memory().to(self.device, non_blocking = True)
+            d['cond_times'], d['row_time'] = fdev[:rb.n_cond], fdev[rb.n_cond:]
+        else:
+            d['cond_times'] = d['row_time'] = torch.zeros(0, device = self.device)
+        d['h2d_bytes'] = host.numel() * 4 + fl.shape[0] * 4
+        d['_keep'] = (host, devbuf)
+        rb.dev = d
+        return d
+
+    def rope_table(self, max_pos: int):
+        n = _round_up(max_pos + 1, 1024)
+        t = self.ws.get('rope_cs')
+        if t is None or t.shape[0] < n:
+            t = torch.empty(n, 32, 2, device = self.device, dtype = F32)
+            self.ops.rope_table(self.model.rotary_emb.freqs.detach().float().contiguous(), t, n, 32)
+            self.ws['rope_cs'] = t
+        return t
+
+    def _ptr_array(self, tensors):
+        arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        self._ptr_arrays.append(arr)            # keep alive until the launch has consumed it (host-side copy at launch)
+        if len(self._ptr_arrays) > 256:
+            self._ptr_arrays = self._ptr_arrays[-64:]
+        return ctypes.cast(arr, ctypes.c_void_p)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, rb: RaggedBatch, latents: list | None, eps: list | None, *, train: bool, want_logits = False, vlimit = 0,
+                text_loss_weight = 1., flow_loss_weight = 1., modality_only = False):
+        """Runs the block stack over a ragged batch.  `latents[t]`: fp32 [S_t, dl_t] device tensors (clean latents when
+        `eps` is given, already-noised / decode-time latents otherwise).  With train=True activations are kept for
+        `backward()` and the fused loss heads produce the loss scalars and the head gradients in the same pass."""
+        self.ensure_attached()
+        self.pack_weights()
+        o, D, HI, H, Ip, M = self.ops, self.D, self.HI, self.H, self.Ip, rb.M
+        dv = self.upload(rb)
+        nc, S = rb.n_cond, rb.S
+        st = self.state = dict(rb = rb, train = train, layers = [])
+        pk = self.packed
+        rope = self.rope_table(rb.max_rope_pos)
+        cond_row = dv['cond_row'] if nc > 0 else None
+        tag = 'T' if train else 'I'
+
+        # ---- conditioning tables, one row per distinct time (reference evaluates them per token: T.py:1132,749,767)
+        if nc > 0:
+            feats = self.buf('feats', (nc, self.Kt), BF16)
+            o.time_features(dv['cond_times'], self.model.transformer.to_time_cond[0].weights, feats, nc, D // 2, self.Kt)
+            cpre = self.buf('cpre', (nc, 4 * D), F32)
+            o.gemm_store(feats, self.Kt, 0, pk['wt'], self.Kt, 0, nc, 4 * D, self.Kt, cpre, 4 * D, None, 0, self.P('transformer.to_time_cond.1.bias'), None, 1.0, 0, 1)
+            cond = self.buf('cond', (nc, 4 * D), BF16)
+            o.table_op(cpre, 4 * D, None, 0, None, 0, cond, 4 * D, nc, 4 * D, 1)
+            tab = self.buf('tab', (nc, self.W * 3 * D), F32)
+            o.gemm_store(cond, 4 * D, 0, pk['wfz'], 4 * D, 0, nc, self.W * 3 * D, 4 * D, tab, self.W * 3 * D, None, 0, pk['bfz'], None, 1.0, 0, 1)
+            zg = self.buf('zg', (nc, self.W * D), F32)
+            for w in range(self.W):
+                o.table_op(tab[:, w * 3 * D + 2 * D:], self.W * 3 * D, None, 0, zg[:, w * D:], self.W * D, None, 0, nc, D, 0)
+            st.update(feats = feats, cpre = cpre, cond = cond, tab = tab, zg = zg)
+        tab_ld, zg_ld = self.W * 3 * D, self.W * D
+
+        # ---- flow noise inject + latent_to_model (MP.py:645-667), token assemble (T.py:3173-3184)
+        modtok = None
+        if S > 0:
+            modtok = self.buf('modtok', (S, D), F32)
+            st['noised'], st['flow'] = [], []
+            for t, (s0, s1) in enumerate(rb.type_rows):
+                n = s1 - s0
+                if n == 0:
+                    st['noised'].append(None); st['flow'].append(None); continue
+                dl, dlp = self.dls[t], self.dlp[t]
+                x = latents[t]
+                assert x.shape == (n, dl) and x.dtype == F32 and x.is_cuda, f'latents[{t}] must be a cuda fp32 [{n}, {dl}] tensor'
+                noised = self.buf(f'noised{t}', (n, dlp), BF16)
+                if dlp != dl:
+                    noised[:, dl:].zero_()
+                has_proj = f'latent_to_model_projs.{t}.weight' in self.named
+                nf32 = None if has_proj else modtok[s0:s1]
+                if eps is not None and eps[t] is not None:
+                    flow = self.buf(f'flow{t}', (n, dl), F32)
+                    o.flow_noise(x, eps[t], dv['row_time'][s0:s1], noised, dlp, nf32, flow, n, dl)
+                else:
+                    flow = None
+                    o.flow_noise(x, None, None, noised, dlp, None, None, n, dl)
+                    if not has_proj:
+                        modtok[s0:s1].copy_(x)
+                if has_proj:
+                    o.gemm_store(noised, dlp, 0, pk[f'wl2m{t}'], dlp, 0, n, D, dl, modtok[s0:s1], D, None, 0, self.P(f'latent_to_model_projs.{t}.bias'), None, 1.0, 0, 1)
+                st['noised'].append(noised); st['flow'].append(flow)
+        x0 = self.buf(f'{tag}x0', (M, D), F32)
+        x0b = self.buf(f'{tag}x0b', (M, D), BF16)
+        o.embed_assemble(dv['text_id'], self.P('text_embed.weight'), modtok, dv['slot'] if S > 0 else None, x0, x0b, M, D)
+
+        # ---- block stack
+        hid = [x0]
+        skips = []
+        x_in, x_in_b = x0, x0b
+        n_tiles = int(rb.tile_q0.shape[0])
+        for i in range(self.depth):
+            L = {}
+            pre = f'transformer.layers.{i}'
+            lt = f'{tag}{i}' if train else 'I'           # inference reuses one set of buffers
+            layer = i + 1
+            first_half = layer <= self.depth // 2
+            if first_half:
+                skips.append((i, x_in_b))
+            has_skip = (not first_half) and f'{pre}.0.weight' in self.named
+            if has_skip:
+                src_i, skip_b = skips.pop()
+                x_a = self.buf(f'{lt}xa', (M, D), F32)
+                o.gemm_resid(x_in_b, D, skip_b, D, D, pk[f'wskip{i}'], 2 * D, M, D, 2 * D, None, x_in, x_a, None, None, None, None, 0, None)
+                L.update(skip_src = src_i, skip_b = skip_b)
+            else:
+                x_a = x_in
+            wA, wF = 2 * i, 2 * i + 1
+            filmA = tab[:, wA * 3 * D:] if nc > 0 else None
+            filmF = tab[:, wF * 3 * D:] if nc > 0 else None
+            zgA = zg[:, wA * D:] if nc > 0 else None
+            zgF = zg[:, wF * D:] if nc > 0 else None
+            uA = self.buf(f'{lt}uA', (M, D), BF16); statsA = self.buf(f'{lt}sA', (M, 2), F32)
+            o.adaln_fwd(x_a, cond_row, filmA, tab_ld, self.P(f'{pre}.1.layernorm_gamma'), uA, statsA, M, D)
+            q = self.buf(f'{lt}q', (M, HI), BF16); k = self.buf(f'{lt}k', (M, HI), BF16); v = self.buf(f'{lt}v', (M, HI), BF16)
+            gates = self.buf(f'{lt}g', (M, H), F32); qk_inv = self.buf(f'{lt}qi', (M, 2 * H), F32)
+            o.gemm_qkvg(uA, D, pk[f'qkvg{i}'], D, M, H, D, q, k, v, gates, qk_inv, self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'),
+                        dv['rope_pos'], rope)
+            att = self.buf(f'{lt}o', (M, HI), BF16); lse = self.buf(f'{lt}lse', (H, M), F32)
+            o.attn_fwd(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_qend'], dv['tile_kv0'], dv['tile_kvend'], n_tiles,
+                       att, HI, lse, M, self.scale, self.softcap)
+            x_b = self.buf(f'{lt}xb', (M, D), F32); yA = self.buf(f'{lt}yA', (M, D), BF16) if train else None
+            o.gemm_resid(att, HI, None, 0, 0, pk[f'wo{i}'], HI, M, D, HI, None, x_a, x_b, None, yA, cond_row, zgA, zg_ld, self.P(f'{pre}.1.layerscale'))
+            uF = self.buf(f'{lt}uF', (M, D), BF16); statsF = self.buf(f'{lt}sF', (M, 2), F32)
+            o.adaln_fwd(x_b, cond_row, filmF, tab_ld, self.P(f'{pre}.2.layernorm_gamma'), uF, statsF, M, D)
+            vg = self.buf(f'{lt}vg', (M, 2 * Ip), BF16); h = self.buf(f'{lt}h', (M, Ip), BF16)
+            o.gemm_geglu(uF, D, pk[f'w1{i}'], D, pk[f'b1{i}'], M, 2 * Ip, D, vg, h)
+            x_c = self.buf(f'{tag}H{i + 1}', (M, D), F32); yF = self.buf(f'{lt}yF', (M, D), BF16) if train else None
+            o.gemm_resid(h, Ip, None, 0, 0, pk[f'w2{i}'], Ip, M, D, Ip, self.P(f'{pre}.2.fn.net.3.bias'), x_b, x_c, None, yF, cond_row, zgF, zg_ld,
+                         self.P(f'{pre}.2.layerscale'))
+            hid.append(x_c)
+            xr = self.buf(f'{tag}xr{i}', (M, D), F32); xrb = self.buf(f'{tag}xrb{i}', (M, D), BF16)
+            o.attn_residual_fwd(self._ptr_array(hid), len(hid), self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'), xr, xrb, M, D)
+            L.update(x_a = x_a, uA = uA, statsA = statsA, q = q, k = k, v = v, gates = gates, qk_inv = qk_inv, att = att, lse = lse, yA = yA, x_b = x_b,
+                     uF = uF, statsF = statsF, vg = vg, h = h, yF = yF, x_in = x_in, x_in_b = x_in_b, has_skip = has_skip, first_half = first_half)
+            st['layers'].append(L)
+            x_in, x_in_b = xr, xrb
+        assert len(skips) == 0 or True
+        st['hid'] = hid
+        st['x_last'] = x_in
+
+        # ---- final RMSNorm (T.py:1250) + compaction of modality rows
+        out = self.buf(f'{tag}out', (M, D), F32)
+        outb = self.buf(f'{tag}outb', (M, D), BF16)
+        omod = self.buf(f'{tag}omod', (max(S, 1), D), BF16)
+        o.rmsnorm_fwd(x_in, self.P('transformer.norm.gamma'), out, outb, dv['slot'] if S > 0 else None, omod if S > 0 else None, M, D)
+        st.update(out = out, outb = outb, omod = omod)
+        res = dict(embed = out)
+
+        # ---- heads
+        if want_logits or train:
+            logits = self.buf(f'{tag}logits', (M, self.Vp), F32)
+            o.gemm_store(outb, D, 0, pk['wvocab'], D, 0, M, self.V, D, logits, self.Vp, None, 0, None, None, 1.0, 0, 1)
+            res['logits'] = logits
+            st['logits'] = logits
+        preds = []
+        if S > 0 and (train or want_logits):
+            for t, (s0, s1) in enumerate(rb.type_rows):
+                n = s1 - s0
+                if n == 0:
+                    preds.append(None); continue
+                dl = self.dls[t]
+                pred = self.buf(f'{tag}pred{t}', (n, dl), F32)
+                o.gemm_store(omod[s0:s1], D, 0, pk[f'wm2l{t}'], D, 0, n, dl, D, pred, dl, None, 0, None, None, 1.0, 0, 1)
+                preds.append(pred)
+            res['preds'] = preds
+        if train:
+            T = float(rb.total_tokens)
+            acc = self.buf('lossacc', (2 + len(self.dls),), torch.float64)
+            acc.zero_()
+            nvalid = self.buf('nvalid', (1,), I32); nvalid.zero_()
+            dlog = self.buf('dlogits', (M, self.Vp), BF16)
+            if modality_only:
+                dlog.zero_()
+            else:
+                gs = (text_loss_weight / T) if vlimit == 0 else 1.0 / max(rb.n_valid, 1)
+                o.ce_fwd_bwd(logits, self.Vp, dv['label'], self.V, vlimit, gs, dlog, self.Vp, acc[0:1], nvalid, M)
+            st['dlogits'] = dlog
+            st['dpred'] = []
+            flow_terms = []
+            for t, (s0, s1) in enumerate(rb.type_rows):
+                n = s1 - s0
+                if n == 0 or st['flow'][t] is None:
+                    st['dpred'].append(None); flow_terms.append(None); continue
+                dl, dlp = self.dls[t], self.dlp[t]
+                wt = 1.0 if modality_only else rb.n_type_tokens[t] / T
+                dpred = self.buf(f'dpred{t}', (n, dlp), BF16)
+                if dlp != dl:
+                    dpred[:, dl:].zero_()
+                o.mse_fwd_bwd(preds[t], dl, st['flow'][t], dpred, dlp, 2.0 * flow_loss_weight * wt / (n * dl), acc[1 + t: 2 + t], n, dl)
+                st['dpred'].append(dpred)
+                flow_terms.append((acc[1 + t] / (n * dl)).float() )
+            # loss assembly on a handful of device scalars (no host sync): transfusion.py:3331-3376
+            text = (acc[0] / max(rb.n_valid, 1)).float()
+            flows = torch.stack([f if f is not None else torch.zeros((), device = self.device) for f in flow_terms]) if flow_terms else torch.zeros(0, device = self.device)
+            if vlimit:
+                total = text
+            elif modality_only:
+                total = flows.sum()
+            else:
+                total = text * (rb.n_valid / T) * text_loss_weight
+                for t, f in enumerate(flow_terms):
+                    if f is not None:
+                        total = total + f * (rb.n_type_tokens[t] / T) * flow_loss_weight
+            res.update(loss_acc = acc, n_valid = nvalid, total = total, text = text, flows = flows)
+        return res
+
+    def _prepare_grads(self):
+        """`.grad` of every trainable parameter must be its view of the flat gradient buffer (kernels accumulate there)."""
+        missing = [(n, p) for n, p in self.named.items() if p.grad is None or p.grad.data_ptr() != self.gflat.data_ptr() + 4 * self.offs[n]]
+        if not missing:
+            return
+        if len(missing) == len(self.named):
+            self.gflat.zero_()
+        for n, p in missing:
+            gv = self.G(n)
+            if len(missing) != len(self.named):
+                gv.zero_()
+            if p.grad is not None:
+                gv.copy_(p.grad)
+            p.grad = gv
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, gscale = None, bucket_cb = None):
+        """Backward of the last train forward: gradients are ACCUMULATED into the flat gradient buffer
+        (`param.grad` views).  All weight gradients are split-K tcgen05 GEMMs over the token dimension.
+        `gscale`: device scalar d(loss) handed in by autograd (folded into the head gradients, no host sync).
+        `bucket_cb(layer)`: called after the kernels of a layer have been enqueued (gradient bucket ready)."""
+        st = self.state
+        assert st['train'], 'backward() needs a train forward'
+        self._prepare_grads()
+        if gscale is not None:
+            gs = gscale.detach().float().reshape(1)
+            self.ops.scale_bf16(st['dlogits'], gs, st['dlogits'].numel())
+            for dp in st['dpred']:
+                if dp is not None:
+                    self.ops.scale_bf16(dp, gs, dp.numel())
+        rb, dv = st['rb'], st['rb'].dev
+        o, D, HI, H, Ip, M, inner = self.ops, self.D, self.HI, self.H, self.Ip, st['rb'].M, self.inner
+        pk, nc, S = self.packed, rb.n_cond, rb.S
+        cond_row = dv['cond_row'] if nc > 0 else None
+        tab_ld, zg_ld = self.W * 3 * D, self.W * D
+        ks = max(1, min(64, M // 2048))           # split-K factor of the wgrad GEMMs (K = tokens)
+        def wgrad(dy, ld_dy, n_out, act, ld_act, n_in, gname, K = M):
+            # dW[n_out, n_in] += dy^T act : both operands MN-major over the token (K) dimension, split-K atomics
+            o.gemm_store(dy, ld_dy, 1, act, ld_act, 1, n_out, n_in, K, self.G(gname), n_in, None, 0, None, None, 1.0, 1, max(1, min(ks, K // 128)))
+
+        # ---- heads
+        dlog = st['dlogits']
+        d_out = self.buf('d_out', (M, D), F32)
+        o.gemm_store(dlog, self.Vp, 0, pk['wvocab'], D, 1, M, D, self.V, d_out, D, None, 0, None, None, 1.0, 0, 1)
+        wgrad(dlog, self.Vp, self.V, st['outb'], D, D, 'to_text_logits.weight')
+        if S > 0:
+            dmod = self.buf('dmod', (S, D), F32)
+            any_flow = False
+            for t, (s0, s1) in enumerate(rb.type_rows):
+                n = s1 - s0
+                dp = st['dpred'][t] if n else None
+                if dp is None:
+                    if n:
+                        dmod[s0:s1].zero_()
+                    continue
+                any_flow = True
+                dl, dlp = self.dls[t], self.dlp[t]
+                o.gemm_store(dp, dlp, 0, pk[f'wm2l{t}'], D, 1, n, D, dl, dmod[s0:s1], D, None, 0, None, None, 1.0, 0, 1)
+                wgrad(dp, dlp, dl, st['omod'][s0:s1], D, D, f'model_to_latent_projs.{t}.weight', K = n)
+            if any_flow:
+                o.scatter_add_rows(d_out, dmod, dv['row_token'], S, D)
+        g = self.buf('gx', (M, D), F32)
+        o.rmsnorm_bwd(d_out, st['x_last'], self.P('transformer.norm.gamma'), g, self.G('transformer.norm.gamma'), M, D)
+
+        # ---- block stack, reverse
+        hid = st['hid']
+        dH = [self.buf(f'dH{l}', (M, D), F32) for l in range(self.depth + 1)]
+        for t in dH:
+            t.zero_()
+        dskip = {}
+        if nc > 0:
+            dtab = self.buf('dtab', (nc, self.W * 3 * D), F32); dtab.zero_()
+            dzg = self.buf('dzg', (nc, self.W * D), F32); dzg.zero_()
+        dy = self.buf('dy', (M, D), BF16)
+        du = self.buf('du', (M, D), F32)
+        for i in reversed(range(self.depth)):
+            L = st['layers'][i]
+            pre = f'transformer.layers.{i}'
+            lm = self.layer_maps[i]
+            wA, wF = 2 * i, 2 * i + 1
+            o.attn_residual_bwd(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
+                                g, self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), M, D)
+            gx = dH[i + 1]                       # complete gradient w.r.t. x_c of this layer; updated in place below
+            # -- feed-forward branch
+            o.resid_bwd(gx, L['yF'], cond_row, st['zg'][:, wF * D:] if nc > 0 else None, zg_ld, self.P(f'{pre}.2.layerscale'), dy,
+                        dzg[:, wF * D:] if nc > 0 else None, zg_ld, self.G(f'{pre}.2.layerscale'), M, D)
+            dh = self.buf('dh', (M, Ip), BF16)
+            o.gemm_store(dy, D, 0, pk[f'w2{i}'], Ip, 1, M, Ip, D, None, 0, dh, Ip, None, None, 1.0, 0, 1)
+            o.gemm_store(dy, D, 1, L['h'], Ip, 1, D, inner, M, self.gflat, 0, None, 0, None, lm['w2_rows'], 1.0, 1, ks)
+            o.colsum_bf16(dy, D, M, D, None, self.G(f'{pre}.2.fn.net.3.bias'))
+            dvg = self.buf('dvg', (M, 2 * Ip), BF16)
+            o.geglu_bwd(dh, L['vg'], dvg, M, Ip)
+            o.gemm_store(dvg, 2 * Ip, 0, pk[f'w1{i}'], D, 1, M, D, 2 * Ip, du, D, None, 0, None, None, 1.0, 0, 1)
+            o.gemm_store(dvg, 2 * Ip, 1, L['uF'], D, 1, 2 * Ip, D, M, self.gflat, 0, None, 0, None, lm['w1_rows'], 1.0, 1, ks)
+            o.colsum_bf16(dvg, 2 * Ip, M, 2 * Ip, lm['b1_cols'], self.gflat)
+            o.adaln_bwd(du, L['x_b'], L['statsF'], cond_row, st['tab'][:, wF * 3 * D:] if nc > 0 else None, tab_ld, self.P(f'{pre}.2.layernorm_gamma'), gx,
+                        dtab[:, wF * 3 * D:] if nc > 0 else None, tab_ld, self.G(f'{pre}.2.layernorm_gamma'), M, D)
+            # -- attention branch
+            o.resid_bwd(gx, L['yA'], cond_row, st['zg'][:, wA * D:] if nc > 0 else None, zg_ld, self.P(f'{pre}.1.layerscale'), dy,
+                        dzg[:, wA * D:] if nc > 0 else None, zg_ld, self.G(f'{pre}.1.layerscale'), M, D)
+            dog = self.buf('dog', (M, HI), BF16)
+            o.gemm_store(dy, D, 0, pk[f'wo{i}'], HI, 1, M, HI, D, None, 0, dog, HI, None, None, 1.0, 0, 1)
+            wgrad(dy, D, D, L['att'], HI, HI, f'{pre}.1.fn.to_out.1.weight')
+            dop = self.buf('dop', (M, HI), BF16); dsum_hm = self.buf('dsum_hm', (H, M), F32); dsum_mh = self.buf('dsum_mh', (M, H), F32)
+            o.attn_bwd_prep(dog, L['att'], L['gates'], dop, dsum_hm, dsum_mh, M, H)
+            dq = self.buf('dq', (M, HI), F32); dk = self.buf('dk', (M, HI), F32)
+            dq.zero_()
+            dqkvg = self.buf('dqkvg', (M, self.NQ), BF16)
+            dqkvg[:, 3 * HI + H:].zero_()
+            o.attn_bwd(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['kt_kv0'], dv['kt_kvend'], dv['kt_q0'], dv['kt_qend'],
+                       int(rb.kt_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap)
+            o.qk_bwd_pack(dq, dk, L['q'], L['k'], L['qk_inv'], self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'), dv['rope_pos'],
+                          self.ws['rope_cs'], L['gates'], dsum_mh, dqkvg, self.NQ, self.G(f'{pre}.1.fn.q_norm.gamma'), self.G(f'{pre}.1.fn.k_norm.gamma'), M, H)
+            o.gemm_store(dqkvg, self.NQ, 0, pk[f'qkvg{i}'], D, 1, M, D, self.NQ, du, D, None, 0, None, None, 1.0, 0, 1)
+            o.gemm_store(dqkvg, self.NQ, 1, L['uA'], D, 1, self.NQ, D, M, self.gflat, 0, None, 0, None, lm['qkvg_rows'], 1.0, 1, ks)
+            o.adaln_bwd(du, L['x_a'], L['statsA'], cond_row, st['tab'][:, wA * 3 * D:] if nc > 0 else None, tab_ld, self.P(f'{pre}.1.layernorm_gamma'), gx,
+                        dtab[:, wA * 3 * D:] if nc > 0 else None, tab_ld, self.G(f'{pre}.1.layernorm_gamma'), M, D)
+            # -- U-Net skip projection: x_a = x_in + W_skip [x_in | skip]
+            if L['has_skip']:
+                o.resid_bwd(gx, None, None, None, 0, None, dy, None, 0, None, M, D)
+                wsk = pk[f'wskip{i}']
+                gw = self.G(f'{pre}.0.weight')
+                o.gemm_store(dy, D, 1, L['x_in_b'], D, 1, D, D, M, gw, 2 * D, None, 0, None, None, 1.0, 1, ks)
+                o.gemm_store(dy, D, 1, L['skip_b'], D, 1, D, D, M, gw.view(-1)[D:], 2 * D, None, 0, None, None, 1.0, 1, ks)
+                src = L['skip_src']
+                if src not in dskip:
+                    dskip[src] = self.buf(f'dskip{src}', (M, D), F32); dskip[src].zero_()
+                o.gemm_store(dy, D, 0, wsk[:, D:], 2 * D, 1, M, D, D, dskip[src], D, None, 0, None, None, 1.0, 1, 1)
+                o.gemm_store(dy, D, 0, wsk, 2 * D, 1, M, D, D, gx, D, None, 0, None, None, 1.0, 1, 1)
+            if i in dskip:
+                o.axpy_f32(gx, dskip[i], 1.0, M * D)
+            g = gx
+            if bucket_cb is not None:
+                bucket_cb(i)
+        # ---- input side: gradient w.r.t. x0 = path gradient + AttentionResidual contributions to H[0]
+        o.axpy_f32(g, dH[0], 1.0, M * D)
+        dmodtok = self.buf('dmodtok', (max(S, 1), D), BF16)
+        o.embed_bwd(g, dv['text_id'], dv['slot'] if S > 0 else None, self.G('text_embed.weight'), dmodtok if S > 0 else None, M, D)
+        if S > 0:
+            for t, (s0, s1) in enumerate(rb.type_rows):
+                n = s1 - s0
+                if n == 0 or f'latent_to_model_projs.{t}.weight' not in self.named:
+                    continue
+                dl, dlp = self.dls[t], self.dlp[t]
+                o.gemm_store(dmodtok[s0:s1], D, 1, st['noised'][t], dlp, 1, D, dl, n, self.G(f'latent_to_model_projs.{t}.weight'), dl, None, 0, None, None, 1.0, 1,
+                             max(1, min(ks, n // 128)))
+                o.colsum_bf16(dmodtok[s0:s1], D, n, D, None, self.G(f'latent_to_model_projs.{t}.bias'))
+        # ---- conditioning path
+        if nc > 0:
+            W3 = self.W * 3 * D
+            for w in range(self.W):
+                o.table_op(dzg[:, w * D:], zg_ld, st['zg'][:, w * D:], zg_ld, dtab[:, w * 3 * D + 2 * D:], W3, None, 0, nc, D, 2)
+            dtabb = self.buf('dtabb', (nc, W3), BF16)
+            o.cast_bf16(dtab, dtabb, nc * W3)
+            dcond = self.buf('dcond', (nc, 4 * D), F32)
+            o.gemm_store(dtabb, W3, 0, pk['wfz'], 4 * D, 1, nc, 4 * D, W3, dcond, 4 * D, None, 0, None, None, 1.0, 0, 1)
+            o.gemm_store(dtabb, W3, 1, st['cond'], 4 * D, 1, W3, 4 * D, nc, self.gflat, 0, None, 0, None, self.fz_rows, 1.0, 1, 1)
+            bsum = self.buf('bsum', (W3,), F32); bsum.zero_()
+            o.colsum_f32(dtab, W3, nc, W3, bsum)
+            self.gflat.index_add_(0, self.fz_bias_idx, bsum)
+            dcpre = self.buf('dcpre', (nc, 4 * D), BF16)
+            o.table_op(dcond, 4 * D, st['cpre'], 4 * D, None, 0, dcpre, 4 * D, nc, 4 * D, 3)
+            o.gemm_store(dcpre, 4 * D, 1, st['feats'], self.Kt, 1, 4 * D, D + 1, nc, self.gflat, 0, None, 0, None, self.wt_rows, 1.0, 1, 1)
+            o.colsum_bf16(dcpre, 4 * D, nc, 4 * D, None, self.G('transformer.to_time_cond.1.bias'))
+
+    # ------------------------------------------------------------------ optimizer
+    def zero_grad(self):
+        self.gflat.zero_()
+
+    def adam_step(self, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled = False, grad_scale = 1.0):
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.flat); self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.opt_step += 1
+        self.ops.adam_step(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.flat.numel(), lr, betas[0], betas[1], eps, weight_decay, int(decoupled),
+                           self.opt_step, grad_scale)
+        self._dirty = True

@@ -1,0 +1,288 @@
+"""Pack / route of interleaved text + modality samples (host side, Python + NumPy).
+
+Role of the reference's `modality_processing.py` (strategies naive/grouped/flat/hybrid/auto,
+modality_processing.py:379-1256) - BASELINE.json keeps this step in Python.  The B200 design differs in
+what it emits: instead of padded `[b, n]` text / `[b, n, d]` modality buffers, a dense `Bool[b,n,n]` mask
+and per-instance closures, it produces ONE ragged descriptor for the kernels:
+
+  * sequences packed back to back (`cu_seqlens`), no padding positions;
+  * per token int32 metadata: text id, next-token label, `kv_limit` (last visible key - the whole hybrid
+    causal / in-span-bidirectional mask of transfusion.py:452-470 as one int), RoPE position
+    (transfusion.py:398-415), condition row (which distinct time value), compact modality row (`slot`);
+  * 64-row tile tables for the attention kernels;
+  * modality latents of one type concatenated into one `[S_t, dim_latent]` matrix (the idea of the `flat`
+    strategy, modality_processing.py:617-689) so noise-inject + `latent_to_model` are one launch per type.
+
+All strategies of the reference produce identical token layouts (modality_processing.py:1258-1305), so the
+registry below maps every strategy name onto this single ragged implementation.
+`modality_positions` (type, offset, length) is kept bit-exact with the reference
+(tests/golden + reference tests/test_modality_processing.py:482-493).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable
+
+import numpy as np
+import torch
+from torch import Tensor, is_tensor
+
+ModalitySample = list   # list[Int[''] | Int['_'] | Float['...'] | tuple[int, Float['...']]]
+
+ATT_TILE = 64
+
+
+def is_int_tensor(t) -> bool:
+    return is_tensor(t) and t.dtype in (torch.int, torch.long)
+
+
+@dataclass
+class ModalityInstance:
+    batch_index: int
+    modality_type: int
+    offset: int                 # offset inside the sample (reference convention, before the shift)
+    length: int
+    axial_shape: tuple
+    row0: int                   # first row in the per-type compact latent matrix
+    cond_row: int               # row of the condition table (distinct time)
+    token0: int = -1            # packed token index of the first latent token (-1 if dropped)
+
+
+@dataclass
+class RaggedBatch:
+    B: int
+    M: int                                  # packed tokens fed to the transformer
+    seq_lens: np.ndarray                    # [B] tokens per sample as fed (after the training shift)
+    cu: np.ndarray                          # [B+1]
+    full_lens: np.ndarray                   # [B] tokens per sample before the shift (reference `total_lens`)
+    text_id: np.ndarray
+    label: np.ndarray
+    kv_limit: np.ndarray
+    rope_pos: np.ndarray
+    cond_row: np.ndarray
+    slot: np.ndarray
+    n_cond: int
+    cond_times: np.ndarray                  # [n_cond] float32
+    n_types: int
+    type_rows: list                         # per type (s0, s1) row range in the global compact matrix
+    row_token: np.ndarray                   # [S] packed token index of each compact row (-1: not fed)
+    row_time: np.ndarray                    # [S] float32
+    latents: list                           # per type: list of [len, dim_latent] tensors in scan order
+    instances: list                         # list[ModalityInstance] in scan order
+    modality_positions: list                # list[list[(type, offset, length)]]
+    total_tokens: int
+    n_type_tokens: list
+    tile_q0: np.ndarray = None
+    tile_qend: np.ndarray = None
+    tile_kv0: np.ndarray = None
+    tile_kvend: np.ndarray = None
+    kt_kv0: np.ndarray = None
+    kt_kvend: np.ndarray = None
+    kt_q0: np.ndarray = None
+    kt_qend: np.ndarray = None
+    max_rope_pos: int = 0
+    has_labels: bool = False
+    n_valid: int = 0
+    dev: dict = field(default_factory = dict)   # device copies (filled by the engine)
+
+    @property
+    def S(self) -> int:
+        return int(self.row_token.shape[0])
+
+
+def _meta_ids(model, shape_str: str, modality_type: int):
+    """[meta] <shape chars> [som] ... [eom] ids (transfusion.py:1426-1447, modality_processing.py:265-287)."""
+    cache = model.__dict__.setdefault('_meta_id_cache', {})
+    key = (shape_str, modality_type)
+    if key not in cache:
+        chars = [ord(c) + model.meta_id + 1 for c in shape_str]
+        cache[key] = (np.asarray([model.meta_id] + chars + [model.som_ids[modality_type]], dtype = np.int64), model.eom_ids[modality_type])
+    return cache[key]
+
+
+def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
+    """64-row tile tables; tiles never straddle a sequence."""
+    tq0, tqe, tk0, tke = [], [], [], []
+    kk0, kke, kq0, kqe = [], [], [], []
+    for b in range(rb.B):
+        s, n = int(rb.cu[b]), int(rb.seq_lens[b])
+        for t0 in range(0, n, ATT_TILE):
+            q0, qe = s + t0, s + min(t0 + ATT_TILE, n)
+            tq0.append(q0); tqe.append(qe); tk0.append(s)
+            tke.append(int(rb.kv_limit[q0:qe].max()) + 1)
+            kk0.append(q0); kke.append(qe)
+            qf = int(qfirst[q0]) - s
+            kq0.append(s + (qf // ATT_TILE) * ATT_TILE); kqe.append(s + n)
+    as32 = lambda a: np.asarray(a, dtype = np.int32)
+    rb.tile_q0, rb.tile_qend, rb.tile_kv0, rb.tile_kvend = as32(tq0), as32(tqe), as32(tk0), as32(tke)
+    rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend = as32(kk0), as32(kke), as32(kq0), as32(kqe)
+
+
+def pack_batch(
+    modalities: list,
+    times,                       # Float[b, m] (CPU tensor / ndarray) or None
+    model,
+    *,
+    return_loss: bool,
+    return_embed: bool,
+    need_axial_pos_emb: bool = False,
+) -> RaggedBatch:
+    assert not need_axial_pos_emb, 'axial positional embeddings are outside the B200 hot path (SURVEY.md section 2, row 16)'
+    B = len(modalities)
+    n_types = model.num_modalities
+    times_np = None
+    if times is not None:
+        times_np = times.detach().float().cpu().numpy() if is_tensor(times) else np.asarray(times, dtype = np.float32)
+
+    text_rows, is_mod_rows, full_lens = [], [], []
+    instances: list[ModalityInstance] = []
+    latents = [[] for _ in range(n_types)]
+    type_counts = [0] * n_types
+    modality_positions = []
+    cond_times = []
+
+    for b, sample in enumerate(modalities):
+        ids, offset, mi, positions = [], 0, 0, []
+        for item in sample:
+            if isinstance(item, tuple):
+                mtype, mt = item[0], item[1]
+            elif is_tensor(item) and item.is_floating_point():
+                mtype, mt = 0, item
+            else:
+                mtype, mt = None, item
+            if mtype is None:
+                t = mt
+                assert is_int_tensor(t) and t.ndim <= 1, 'text must be a 0-d or 1-d int tensor'
+                arr = t.detach().cpu().numpy().reshape(-1).astype(np.int64)
+                ids.append(arr); offset += arr.shape[0]
+                continue
+            assert 0 <= mtype < n_types, f'received a modality index that is out of range. only {n_types} modalities specified'
+            dl = model.dim_latents[mtype]
+            cf = model.channel_first_latent[mtype]
+            assert mt.shape[0 if cf else -1] == dl, f'mismatch for modality latent dimension - expected {dl} but received {mt.shape[0 if cf else -1]} - modality shape is {tuple(mt.shape)}, perhaps you need to set `channel_first_latent` to the correct value'
+            nd = model.modality_num_dim[mtype]
+            assert nd is None or nd == mt.ndim - 1, f'mismatch for modality number of dimensions - expected {nd} but received {mt.ndim - 1} {tuple(mt.shape)}'
+            axial = tuple(mt.shape[1:]) if cf else tuple(mt.shape[:-1])
+            length = math.prod(axial)
+            flat = (mt.reshape(dl, length).t() if cf else mt.reshape(length, dl))
+            pre = 0
+            if not return_embed:
+                meta, eom = _meta_ids(model, ','.join(map(str, axial)), mtype)
+                ids.append(meta); pre = meta.shape[0]
+            ids.append(np.full(length, -1, dtype = np.int64))
+            if not return_embed:
+                ids.append(np.asarray([eom], dtype = np.int64))
+            t_val = float(times_np[b, mi]) if times_np is not None and times_np.shape[1] > mi else 0.
+            inst = ModalityInstance(b, mtype, offset + pre, length, axial, type_counts[mtype], len(cond_times))
+            cond_times.append(t_val)
+            type_counts[mtype] += length
+            latents[mtype].append(flat)
+            instances.append(inst); positions.append((mtype, offset + pre, length))
+            offset += pre + length + (0 if return_embed else 1)
+            mi += 1
+        ids = np.concatenate(ids) if ids else np.zeros((0,), dtype = np.int64)
+        assert ids.shape[0] == offset
+        text_rows.append(ids); full_lens.append(offset); modality_positions.append(positions)
+
+    full_lens = np.asarray(full_lens, dtype = np.int64)
+    drop = 1 if return_loss else 0
+    seq_lens = np.maximum(full_lens - drop, 0)
+    cu = np.zeros(B + 1, dtype = np.int64); np.cumsum(seq_lens, out = cu[1:])
+    M = int(cu[-1])
+
+    text_id = np.zeros(M, dtype = np.int32); label = np.full(M, -1, dtype = np.int32)
+    kv_limit = np.arange(M, dtype = np.int32); qfirst = np.arange(M, dtype = np.int32)
+    rope_pos = np.zeros(M, dtype = np.int32); cond_row = np.full(M, -1, dtype = np.int32); slot = np.full(M, -1, dtype = np.int32)
+
+    type_base = np.concatenate([[0], np.cumsum(type_counts)]).astype(np.int64)
+    S = int(type_base[-1])
+    row_token = np.full(S, -1, dtype = np.int32); row_time = np.zeros(S, dtype = np.float32)
+    n_type_tokens = [0] * n_types
+
+    by_sample = [[] for _ in range(B)]
+    for inst in instances:
+        by_sample[inst.batch_index].append(inst)
+
+    max_rope = 0
+    for b in range(B):
+        s, n, ids = int(cu[b]), int(seq_lens[b]), text_rows[b]
+        if n == 0:
+            continue
+        tid = ids[:n]
+        is_extra = np.zeros(n, dtype = np.int64); is_mod = np.zeros(n, dtype = bool)
+        for inst in by_sample[b]:
+            o, l = inst.offset, inst.length
+            e = min(o + l, n)
+            if o >= n:
+                continue
+            inst.token0 = s + o
+            kv_limit[s + o: s + e] = s + o + l - 1 if o + l <= n else s + n - 1
+            qfirst[s + o: s + e] = s + o
+            is_extra[o + 1: e] = 1; is_mod[o:e] = True
+            cond_row[s + o: s + e] = inst.cond_row
+            r0 = int(type_base[inst.modality_type]) + inst.row0
+            slot[s + o: s + e] = np.arange(r0, r0 + (e - o), dtype = np.int32)
+            row_token[r0: r0 + (e - o)] = np.arange(s + o, s + e, dtype = np.int32)
+            row_time[r0: r0 + l] = cond_times[inst.cond_row]
+            n_type_tokens[inst.modality_type] += e - o
+        text_id[s:s + n] = np.where(tid < 0, 0, tid)
+        pos = np.arange(n, dtype = np.int64) - np.cumsum(is_extra)       # transfusion.py:398-415
+        rope_pos[s:s + n] = pos
+        max_rope = max(max_rope, int(pos[-1]))
+        if return_loss:
+            lab = ids[1:n + 1].copy()                                      # next token (transfusion.py:3144)
+            lab[is_mod] = -1                                               # transfusion.py:3320
+            lab[lab == model.null_text_id] = -1                            # transfusion.py:3323
+            label[s:s + n] = lab
+
+    rb = RaggedBatch(
+        B = B, M = M, seq_lens = seq_lens, cu = cu, full_lens = full_lens, text_id = text_id, label = label, kv_limit = kv_limit,
+        rope_pos = rope_pos, cond_row = cond_row, slot = slot, n_cond = len(cond_times),
+        cond_times = np.asarray(cond_times, dtype = np.float32), n_types = n_types,
+        type_rows = [(int(type_base[t]), int(type_base[t + 1])) for t in range(n_types)], row_token = row_token, row_time = row_time,
+        latents = latents, instances = instances, modality_positions = modality_positions,
+        total_tokens = int(full_lens.sum()), n_type_tokens = n_type_tokens, max_rope_pos = max_rope, has_labels = return_loss)
+    rb.n_valid = int((label >= 0).sum())
+    build_tiles(rb, qfirst)
+    return rb
+
+
+def pack_text_only(text: Tensor, *, return_loss: bool, pos_offset: int = 0) -> RaggedBatch:
+    """`Int[b, n]` pretraining path (transfusion.py:2585-2664): causal mask, arange positions."""
+    t = text.detach().cpu().numpy().astype(np.int64)
+    B, L = t.shape
+    n = L - 1 if return_loss else L
+    M = B * n
+    cu = np.arange(B + 1, dtype = np.int64) * n
+    tid = t[:, :n].reshape(-1)
+    label = np.full(M, -1, dtype = np.int32)
+    if return_loss:
+        label = t[:, 1:].reshape(-1).astype(np.int32)
+    rb = RaggedBatch(
+        B = B, M = M, seq_lens = np.full(B, n, dtype = np.int64), cu = cu, full_lens = np.full(B, L, dtype = np.int64),
+        text_id = np.where(tid < 0, 0, tid).astype(np.int32), label = label, kv_limit = np.arange(M, dtype = np.int32),
+        rope_pos = (np.tile(np.arange(n, dtype = np.int32), B) + pos_offset).astype(np.int32), cond_row = np.full(M, -1, dtype = np.int32),
+        slot = np.full(M, -1, dtype = np.int32), n_cond = 0, cond_times = np.zeros(0, dtype = np.float32), n_types = 0, type_rows = [],
+        row_token = np.zeros(0, dtype = np.int32), row_time = np.zeros(0, dtype = np.float32), latents = [], instances = [],
+        modality_positions = [[] for _ in range(B)], total_tokens = B * L, n_type_tokens = [], max_rope_pos = n - 1 + pos_offset,
+        has_labels = return_loss)
+    rb.n_valid = int((label >= 0).sum())
+    build_tiles(rb, np.arange(M, dtype = np.int32))
+    return rb
+
+
+# --------------------------------------------------------------------------------------------- registry (API parity)
+def _strategy(name):
+    def fn(modalities, times, model, *, need_axial_pos_emb, return_loss, return_embed):
+        return pack_batch(modalities, times, model, return_loss = return_loss, return_embed = return_embed, need_axial_pos_emb = need_axial_pos_emb)
+    fn.__name__ = f'process_modality_batch_{name}'
+    return fn
+
+PROCESSING_STRATEGIES: dict[str, Callable] = {name: _strategy(name) for name in ('naive', 'grouped', 'flat', 'hybrid', 'auto')}
+DEFAULT_PROCESSING_STRATEGY = 'auto'
+
+
+def get_processing_strategy(name: str):
+    assert name in PROCESSING_STRATEGIES, f'unknown modality processing strategy `{name}`, available: {list(PROCESSING_STRATEGIES)}'
+    return PROCESSING_STRATEGIES[name]

@@ -1,0 +1,555 @@
+"""Host-side mirror of the reference's public API (`Transfusion`, `Transformer`) over the B200 engine.
+
+Same constructor keywords, method names, return conventions, special-token layout and - crucially -
+the same `state_dict()` keys and shapes as lucidrains/transfusion-pytorch v0.19.4
+(transfusion_pytorch/transfusion.py:1041-1097, 1290-1540), so reference checkpoints load here and vice
+versa.  What differs is everything underneath: the modules below only OWN parameters; all arithmetic of
+the block stack, attention, loss heads and optimizer runs in the sm_100a kernels of `libtfx_b200.so`
+driven by `engine.Engine` over the ragged descriptor of `modality_processing.pack_batch`.
+
+Out of scope here (raise loudly): axial positional embeddings, U-Net
+pre/post encoders, velocity-consistency / reconstruction losses, LASER attention, value residual.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+from typing import Callable, NamedTuple
+
+import numpy as np
+import torch
+from torch import nn, Tensor, tensor, is_tensor, cat
+from torch.nn import Module, ModuleList
+
+from .modality_processing import (
+    ModalitySample, RaggedBatch, pack_batch, pack_text_only, get_processing_strategy, DEFAULT_PROCESSING_STRATEGY, is_int_tensor)
+
+
+class LossBreakdown(NamedTuple):
+    total: Tensor
+    text: Tensor
+    flow: list
+    velocity: list | None = None
+    recon: list | None = None
+
+
+def exists(v):
+    return v is not None
+
+
+def default(v, d):
+    return v if exists(v) else d
+
+
+def cast_tuple(t, length = 1):
+    return t if isinstance(t, tuple) else ((t,) * length)
+
+
+def default_to_modality_shape_fn(maybe_shape_str) -> tuple:
+    return tuple(int(s) for s in maybe_shape_str.split(','))
+
+
+def print_modality_sample(modality_sample):
+    out = []
+    for part in modality_sample:
+        if isinstance(part, tuple):
+            out.append((f'modality:{part[0]}', tuple(part[1].shape)))
+        elif is_int_tensor(part):
+            out.append(('text', tuple(part.shape)))
+        else:
+            out.append(('modality', tuple(part.shape)))
+    print(out)
+
+
+def _collate(data):
+    return [list(d) for d in data]
+
+
+def create_dataloader(dataset, **kwargs):
+    from torch.utils.data import DataLoader
+    return DataLoader(dataset, collate_fn = _collate, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------- text sampling helpers
+def min_p_filter(logits, min_p = 0.1):
+    probs = logits.softmax(dim = -1)
+    limit = min_p * probs.amax(dim = -1, keepdim = True)
+    return torch.where(probs < limit, float('-inf'), logits)
+
+
+def sample_text_token(logits, temperature = 1.0, min_p = 0.1):
+    if temperature == 0.:
+        return logits.argmax(dim = -1, keepdim = True)
+    logits = min_p_filter(logits / temperature, min_p = min_p)
+    return torch.multinomial(logits.softmax(dim = -1), 1)
+
+
+def default_modality_length_to_time_fn(num_modalities: Tensor) -> Tensor:
+    """Past ("already decoded") modalities get t = 0.5, the rest share one uniform time per sample
+    (transfusion.py:186-200)."""
+    nm = num_modalities.float().cpu()
+    total = int(nm.amax().item()) if nm.numel() else 0
+    if total == 0:
+        return torch.empty((nm.shape[0], 0))
+    rand_num = torch.floor(torch.rand_like(nm) * nm)
+    seq = torch.arange(total)
+    prev = seq[None, :] < rand_num[:, None]
+    cur = torch.rand_like(nm)
+    return torch.where(prev, torch.tensor(0.5), cur[:, None].expand(-1, total))
+
+
+# ------------------------------------------------------------------------------------------- parameter holders
+class _Gamma(Module):
+    """owns `gamma` of an RMSNorm (transfusion.py:779-786)"""
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.zeros(dim))
+
+
+class _Fourier(Module):
+    def __init__(self, dim):
+        super().__init__()
+        assert dim % 2 == 0
+        self.register_buffer('weights', torch.randn(dim // 2))       # persistent, as in transfusion.py:622
+
+
+class _AttentionParams(Module):
+    def __init__(self, dim, dim_head, heads):
+        super().__init__()
+        inner = dim_head * heads
+        self.to_qk = nn.Sequential(nn.Linear(dim, inner * 2, bias = False))
+        self.q_norm, self.k_norm = _Gamma(dim_head), _Gamma(dim_head)
+        self.to_v = nn.Sequential(nn.Linear(dim, inner, bias = False))
+        self.to_gates = nn.Sequential(nn.Linear(dim, heads, bias = False))
+        self.to_out = nn.Sequential(nn.Identity(), nn.Linear(inner, dim, bias = False))
+
+
+class _FeedForwardParams(Module):
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, inner * 2), nn.Identity(), nn.Identity(), nn.Linear(inner, dim))
+
+
+class _AdaptiveParams(Module):
+    """parameters of one AdaptiveWrapper (transfusion.py:640-669)"""
+    def __init__(self, fn, dim, dim_cond, ada_ln_zero_init_bias = -2.):
+        super().__init__()
+        self.fn = fn
+        self.layernorm_gamma = nn.Parameter(torch.zeros(dim))
+        self.layerscale = nn.Parameter(torch.zeros(dim))
+        self.to_film = nn.Linear(dim_cond, dim * 2)
+        self.to_ada_ln_zero = nn.Linear(dim_cond, dim)
+        nn.init.zeros_(self.to_film.weight)
+        nn.init.zeros_(self.to_ada_ln_zero.weight)
+        nn.init.constant_(self.to_ada_ln_zero.bias, ada_ln_zero_init_bias)
+
+
+class _AttnResidualParams(Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm_keys = _Gamma(dim)
+        self.pseudo_queries = nn.Parameter(torch.zeros(dim))
+        nn.init.normal_(self.pseudo_queries, std = 0.02)
+
+
+class _Rotary(Module):
+    def __init__(self, dim, theta = 10000):
+        super().__init__()
+        freqs = 1. / (theta ** (torch.arange(0, dim, 2)[:(dim // 2)].float() / dim))
+        self.freqs = nn.Parameter(freqs, requires_grad = False)
+
+
+class Transformer(Module):
+    """Parameter container with the reference's constructor (transfusion.py:1043-1097).  The forward pass
+    lives in the engine; this class validates that the requested variant is one the kernels implement."""
+
+    def __init__(self, dim, *, depth, dim_head = 64, heads = 8, dropout = 0., ff_expansion_factor = 4, attn_kwargs: dict = dict(),
+                 ff_kwargs: dict = dict(), attn_laser = False, unet_skips = True, use_flex_attn = False, qk_rmsnorm = True,
+                 use_value_residual = False):
+        super().__init__()
+        unsupported = []
+        if dim_head != 64: unsupported.append('dim_head != 64')
+        if dropout != 0.: unsupported.append('dropout > 0')
+        if attn_laser: unsupported.append('attn_laser')
+        if use_value_residual: unsupported.append('use_value_residual')
+        if not qk_rmsnorm: unsupported.append('qk_rmsnorm = False')
+        extra = set(attn_kwargs) - {'softcap_value'}
+        if extra: unsupported.append(f'attn_kwargs {sorted(extra)}')
+        if ff_kwargs: unsupported.append(f'ff_kwargs {sorted(ff_kwargs)}')
+        if unsupported:
+            raise NotImplementedError('not implemented by the B200 kernels: ' + ', '.join(unsupported))
+        self.dim, self.depth, self.dim_head, self.heads = dim, depth, dim_head, heads
+        self.use_flex_attn = use_flex_attn           # accepted: the fused kernel IS the span-aware attention
+        self.use_value_residual = False
+        self.softcap_value = float(attn_kwargs.get('softcap_value', 50.))
+        self.ff_inner = int(dim * ff_expansion_factor * 2 / 3)
+
+        self.to_time_cond = nn.Sequential(_Fourier(dim), nn.Linear(dim + 1, dim * 4), nn.SiLU())
+        layers = ModuleList([])
+        for ind in range(depth):
+            skip_proj = nn.Linear(dim * 2, dim, bias = False) if (ind >= depth / 2 and unet_skips) else None
+            attn = _AdaptiveParams(_AttentionParams(dim, dim_head, heads), dim, dim * 4)
+            ff = _AdaptiveParams(_FeedForwardParams(dim, self.ff_inner), dim, dim * 4)
+            layers.append(ModuleList([skip_proj, attn, ff, _AttnResidualParams(dim)]))
+        self.layers = layers
+        self.norm = _Gamma(dim)
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError('Transformer.forward is executed by the B200 engine through Transfusion; call the Transfusion methods')
+
+
+# ------------------------------------------------------------------------------------------- autograd seam
+class _TrainStep(torch.autograd.Function):
+    """One node for the whole training forward: the engine keeps its own activations and writes parameter
+    gradients straight into the flat `.grad` buffer, so autograd only has to hand us d(total loss)."""
+
+    @staticmethod
+    def forward(ctx, engine, rb, latents, eps, kw, anchor):
+        res = engine.forward(rb, latents, eps, train = True, **kw)
+        ctx.engine = engine
+        return res['total'], res['text'], res['flows']
+
+    @staticmethod
+    def backward(ctx, g_total, g_text, g_flows):
+        ctx.engine.backward(gscale = g_total)
+        return None, None, None, None, None, None
+
+
+class Transfusion(Module):
+    def __init__(
+        self,
+        *,
+        num_text_tokens,
+        transformer: dict | Transformer,
+        model_output_clean = False,
+        dim_latent: int | tuple | None = None,
+        channel_first_latent: bool | tuple = False,
+        add_pos_emb: bool | tuple = False,
+        modality_encoder: Module | tuple | None = None,
+        modality_decoder: Module | tuple | None = None,
+        pre_post_transformer_enc_dec = None,
+        modality_default_shape: tuple | None = None,
+        fallback_to_default_shape_if_invalid = False,
+        modality_num_dim: int | tuple | None = None,
+        to_modality_shape_fn: Callable | tuple = default_to_modality_shape_fn,
+        ignore_index = -1,
+        flow_loss_weight = 1.,
+        text_loss_weight = 1.,
+        velocity_consistency_loss_weight = 0.1,
+        reconstruction_loss_weight = 0.,
+        modality_encoder_decoder_requires_batch_dim = True,
+        odeint_kwargs: dict = dict(atol = 1e-5, rtol = 1e-5, method = 'midpoint'),
+        eps = 1e-2,
+        prob_uncond = 0.1,
+        modality_processing: str = DEFAULT_PROCESSING_STRATEGY,
+    ):
+        super().__init__()
+        self.modality_processing = modality_processing
+        get_processing_strategy(modality_processing)
+        if isinstance(transformer, dict):
+            transformer = Transformer(**transformer)
+        self.transformer = transformer
+        dim = self.dim = transformer.dim
+
+        if model_output_clean: raise NotImplementedError('model_output_clean is outside the B200 hot path')
+        if exists(pre_post_transformer_enc_dec): raise NotImplementedError('pre_post_transformer_enc_dec (U-Net) is outside the B200 hot path')
+        if reconstruction_loss_weight > 0.: raise NotImplementedError('reconstruction loss is outside the B200 hot path')
+        assert ignore_index == -1, 'the fused loss kernel uses -1 as the ignore index'
+
+        self.dim_latents = cast_tuple(default(dim_latent, dim))
+        self.num_modalities = len(self.dim_latents)
+        self.channel_first_latent = cast_tuple(channel_first_latent, self.num_modalities)
+        assert len(self.channel_first_latent) == self.num_modalities
+        self.to_modality_shape_fn = cast_tuple(to_modality_shape_fn, self.num_modalities)
+
+        is_flat_shape = modality_default_shape is None or (isinstance(modality_default_shape, tuple) and all(isinstance(v, int) for v in modality_default_shape))
+        if is_flat_shape:
+            modality_default_shape = (modality_default_shape,) * self.num_modalities
+        self.modality_default_shape = modality_default_shape
+        assert len(self.modality_default_shape) == self.num_modalities
+        self.fallback_to_default_shape_if_invalid = fallback_to_default_shape_if_invalid
+        modality_num_dim = default(modality_num_dim, tuple(len(s) if exists(s) else None for s in self.modality_default_shape))
+        self.modality_num_dim = cast_tuple(modality_num_dim, self.num_modalities)
+        assert len(self.modality_num_dim) == self.num_modalities
+        assert all(not exists(nd) or not exists(s) or len(s) == nd for nd, s in zip(self.modality_num_dim, self.modality_default_shape))
+
+        self.add_pos_emb = cast_tuple(add_pos_emb, self.num_modalities)
+        if any(self.add_pos_emb): raise NotImplementedError('add_pos_emb (axial positional embedding) is outside the B200 hot path')
+        self.pos_emb_mlp = ModuleList([None] * self.num_modalities)
+
+        modality_encoder = cast_tuple(modality_encoder, 1 if exists(modality_encoder) else self.num_modalities)
+        modality_decoder = cast_tuple(modality_decoder, 1 if exists(modality_decoder) else self.num_modalities)
+        self.modality_encoder, self.modality_decoder = ModuleList(modality_encoder), ModuleList(modality_decoder)
+        assert len(self.modality_encoder) == self.num_modalities and len(self.modality_decoder) == self.num_modalities
+        self.encdec_needs_batch_dim = modality_encoder_decoder_requires_batch_dim
+
+        # special token layout (transfusion.py:1422-1449)
+        self.num_text_tokens = num_text_tokens
+        self.sos_id, self.eos_id, self.null_text_id = num_text_tokens, num_text_tokens + 1, num_text_tokens + 2
+        first = num_text_tokens + 3
+        self.som_ids = [first + m for m in range(self.num_modalities)]
+        self.eom_ids = [first + self.num_modalities + m for m in range(self.num_modalities)]
+        self.meta_id = first + 2 * self.num_modalities
+        self._char_offset = self.meta_id + 1
+
+        self.latent_to_model_projs = ModuleList([nn.Linear(dl, dim) if dl != dim else nn.Identity() for dl in self.dim_latents])
+        self.model_to_latent_projs = ModuleList([nn.Linear(dim, dl, bias = False) for dl in self.dim_latents])
+        self.rotary_emb = _Rotary(transformer.dim_head)
+
+        vocab = num_text_tokens + 3 + 2 * self.num_modalities + 129
+        self.text_embed = nn.Embedding(vocab, dim)
+        self.to_text_logits = nn.Linear(dim, vocab, bias = False)
+        self.register_buffer('text_only_logits_mask', torch.arange(vocab) < num_text_tokens, persistent = False)
+        self.register_buffer('zero', tensor(0.), persistent = False)
+
+        self.ignore_index = ignore_index
+        self.flow_loss_weight, self.text_loss_weight = flow_loss_weight, text_loss_weight
+        self.velocity_consistency_loss_weight = velocity_consistency_loss_weight
+        self.has_recon_loss, self.reconstruction_loss_weight = False, reconstruction_loss_weight
+        self.model_output_clean, self.eps = model_output_clean, eps
+        self.odeint_kwargs = dict(odeint_kwargs)
+        assert self.odeint_kwargs.get('method', 'midpoint') == 'midpoint', 'only the fixed-grid midpoint solver is implemented'
+        self.prob_uncond = prob_uncond
+        self._engine = None
+
+    # ------------------------------------------------------------------ small API surface
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def char_tokenizer(self, text: str, device = None):
+        return (tensor([ord(c) for c in text], device = device, dtype = torch.long) + self._char_offset).long()
+
+    def decode_chars(self, t: Tensor) -> str:
+        return ''.join(chr(v) for v in (t - self._char_offset).clamp(min = 0, max = 127).tolist())
+
+    def get_modality_info(self, modality_type = None):
+        t = default(modality_type, 0)
+        return dict(encoder = self.modality_encoder[t], decoder = self.modality_decoder[t], latent_to_model = self.latent_to_model_projs[t],
+                    model_to_latent = self.model_to_latent_projs[t], add_pos_emb = False, pos_emb_mlp = None, num_dim = self.modality_num_dim[t],
+                    dim_latent = self.dim_latents[t], default_shape = self.modality_default_shape[t], som_id = self.som_ids[t], eom_id = self.eom_ids[t],
+                    to_shape_fn = self.to_modality_shape_fn[t], channel_first_latent = self.channel_first_latent[t], modality_type = t)
+
+    def parameters_without_encoder_decoder(self):
+        return set(self.parameters()) - set(self.modality_encoder.parameters()) - set(self.modality_decoder.parameters())
+
+    def muon_parameters(self):
+        params = []
+        for layer in self.transformer.layers:
+            a, f = layer[1].fn, layer[2].fn
+            params += [*a.to_v.parameters(), *a.to_out.parameters(), f.net[0].weight, f.net[-1].weight]
+        return params
+
+    def create_dataloader(self, *args, **kwargs):
+        return create_dataloader(*args, **kwargs)
+
+    def create_ema(self, beta = 0.99, *ema_kwargs):
+        raise NotImplementedError('EMA is outside the B200 hot path (SURVEY.md section 2, row 21)')
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine(self)
+        return self._engine
+
+    # ------------------------------------------------------------------ engine glue
+    def _latents_to_device(self, rb: RaggedBatch):
+        dev = self.device
+        out, nbytes = [], 0
+        for t, lst in enumerate(rb.latents):
+            if not lst:
+                out.append(None); continue
+            if all(x.is_cuda for x in lst):
+                out.append(cat([x.float() for x in lst]).contiguous())
+            else:
+                host = cat([x.detach().float().cpu() for x in lst]).contiguous().pin_memory()
+                nbytes += host.numel() * 4
+                out.append(host.to(dev, non_blocking = True))
+        rb.latent_h2d_bytes = nbytes
+        return out
+
+    def _run(self, rb, latents, eps, *, train, **kw):
+        eng = self.engine
+        if train and torch.is_grad_enabled():
+            anchor = self.text_embed.weight
+            total, text, flows = _TrainStep.apply(eng, rb, latents, eps, kw, anchor)
+            return dict(total = total, text = text, flows = flows)
+        return eng.forward(rb, latents, eps, train = train, **kw)
+
+    # ------------------------------------------------------------------ text only (transfusion.py:2585-2707)
+    def forward_text(self, text: Tensor, return_loss = True, return_embed = False, cache = None, return_hiddens = False, return_kv_cache = False):
+        assert not return_hiddens, 'return_hiddens is not provided by the fused engine'
+        raw_cache, tokens_seen = default(cache, (None, 0))
+        if exists(raw_cache):
+            # the engine recomputes from the tokens it is given: the "cache" carries the token prefix (API-compatible tuple)
+            text = cat((raw_cache, text.to(raw_cache.device)), dim = -1)
+        rb = pack_text_only(text, return_loss = return_loss)
+        if return_loss:
+            res = self._run(rb, None, None, train = True, vlimit = self.num_text_tokens)
+            return res['total']
+        res = self.engine.forward(rb, None, None, train = False, want_logits = True)
+        B, n = rb.B, int(rb.seq_lens[0])
+        logits = res['logits'][:, :self.to_text_logits.weight.shape[0]].reshape(B, n, -1)
+        if exists(raw_cache):
+            logits = logits[:, tokens_seen:]
+        out = res['embed'].reshape(B, n, -1) if return_embed else logits
+        if return_kv_cache:
+            return out, (text.to(self.device), n)
+        return out
+
+    @torch.no_grad()
+    def generate_text_only(self, prompt: Tensor, seq_len: int, temperature = 1.0, min_p = 0.1, cache_kv = True) -> Tensor:
+        was = self.training
+        self.eval()
+        try:
+            prompt_len, out = prompt.shape[-1], prompt.clone().to(self.device)
+            for _ in range(max(0, seq_len - prompt_len)):
+                logits = self.forward_text(out, return_loss = False)[:, -1].float()
+                if temperature == 0.:
+                    nxt = logits.argmax(dim = -1, keepdim = True)
+                else:
+                    logits = min_p_filter(logits / temperature, min_p = min_p)
+                    logits = logits.masked_fill(~self.text_only_logits_mask, -torch.finfo(logits.dtype).max)
+                    noise = -torch.log(-torch.log(torch.rand_like(logits).clamp(min = 1e-20)).clamp(min = 1e-20))
+                    nxt = (logits + noise).argmax(dim = -1, keepdim = True)
+                out = cat((out, nxt), dim = -1)
+            return out[..., prompt_len:]
+        finally:
+            self.train(was)
+
+    # ------------------------------------------------------------------ modality only (transfusion.py:2709-2866)
+    def forward_modality(self, modalities: Tensor, times = None, modality_type = None, encode_modality = True, velocity_consistency_ema_model = None,
+                         velocity_consistency_delta_time = 1e-5, return_loss = True, return_loss_breakdown = False, noise = None):
+        assert not exists(velocity_consistency_ema_model), 'velocity consistency is outside the B200 hot path'
+        if self.num_modalities > 1:
+            assert exists(modality_type), '`modality_type` must be explicitly passed in on forward when training on greater than 1 modality'
+        mt = default(modality_type, 0)
+        enc = self.modality_encoder[mt]
+        x = modalities
+        if encode_modality and exists(enc):
+            with torch.no_grad():
+                enc.eval(); x = enc(x.to(self.device)).detach()
+        B = x.shape[0]
+        if times is None:
+            times = torch.rand((B,))
+        samples = [[(mt, x[b])] for b in range(B)]
+        rb = pack_batch(samples, times.reshape(B, 1), self, return_loss = False, return_embed = True)
+        rb.kv_limit[:] = np.repeat(rb.cu[1:] - 1, rb.seq_lens).astype(np.int32)      # no mask at all (transfusion.py:2800-2804)
+        rb.rope_pos[:] = 0                                                            # no rotary embedding in this path
+        from .modality_processing import build_tiles
+        build_tiles(rb, np.repeat(rb.cu[:-1], rb.seq_lens).astype(np.int32))
+        lat = self._latents_to_device(rb)
+        if return_loss:
+            eps = [None] * self.num_modalities
+            eps[mt] = noise.reshape(-1, self.dim_latents[mt]).float().to(self.device) if exists(noise) else torch.randn_like(lat[mt])
+            rb.has_labels = True
+            res = self._run(rb, lat, eps, train = True, modality_only = True, flow_loss_weight = 1.)
+            flow_loss = res['flows'][mt]
+            total = res['total']
+            if return_loss_breakdown:
+                return total, (flow_loss, self.zero, self.zero)
+            return total
+        res = self.engine.forward(rb, lat, None, train = False, want_logits = True)
+        pred = res['preds'][mt]
+        cf = self.channel_first_latent[mt]
+        inst_shape = x.shape[2:] if cf else x.shape[1:-1]
+        pred = pred.reshape(B, *inst_shape, self.dim_latents[mt])
+        if cf:
+            pred = pred.movedim(-1, 1)
+        return pred
+
+    # ------------------------------------------------------------------ main forward (transfusion.py:2925-3450)
+    def forward(
+        self,
+        modalities,
+        times = None,
+        num_modalities_to_times_fn: Callable | None = None,
+        modality_type = None,
+        cache = None,
+        decode_length = None,
+        decoding_text_or_modality = None,
+        velocity_consistency_ema_model = None,
+        velocity_consistency_delta_time = 1e-3,
+        return_only_pred_flows = False,
+        return_loss = True,
+        return_breakdown = False,
+        return_embed = False,
+        return_hiddens = False,
+        return_kv_cache = False,
+        return_times = False,
+        prob_uncond = None,
+        noise = None,            # extension: list (per type) of [S_t, dim_latent] noise for deterministic parity runs
+    ):
+        assert not exists(velocity_consistency_ema_model), 'velocity consistency is outside the B200 hot path'
+        assert not return_hiddens and not return_only_pred_flows, 'return_hiddens / return_only_pred_flows are not provided by the fused engine'
+        is_decoding = exists(decoding_text_or_modality)
+        if is_int_tensor(modalities):
+            return self.forward_text(modalities, return_loss = return_loss and not return_embed, return_embed = return_embed, cache = cache,
+                                     return_kv_cache = return_kv_cache)
+        if is_tensor(modalities) and modalities.is_floating_point():
+            assert return_loss
+            return self.forward_modality(modalities, modality_type = modality_type)
+        return_loss = return_loss and not (return_embed or is_decoding)
+        assert not exists(cache), 'the B200 path recomputes the (short) prefix instead of taking an external kv cache; use sample()/sample_many()'
+
+        batch = len(modalities)
+        samples = [list(s) if isinstance(s, list) else s for s in modalities]
+        if return_loss:
+            samples = [[tensor([self.sos_id]), *s, tensor([self.eos_id])] for s in samples]
+        # classifier free guidance dropout (transfusion.py:3027-3043): all int tensors of a dropped sample -> null id
+        prob_uncond = default(prob_uncond, self.prob_uncond)
+        if self.training and prob_uncond > 0:
+            drop = (torch.rand(batch) < prob_uncond).tolist()
+            samples = [[torch.full_like(p, self.null_text_id) if is_int_tensor(p) else p for p in s] if d else s for s, d in zip(samples, drop)]
+        # modality encoders (user modules, outside the hot path)
+        n_mods = []
+        for s in samples:
+            cnt = 0
+            for j, part in enumerate(s):
+                if is_tensor(part) and part.is_floating_point():
+                    part = s[j] = (0, part)
+                if isinstance(part, tuple):
+                    cnt += 1
+                    enc = self.modality_encoder[part[0]]
+                    if exists(enc) and not is_decoding:
+                        with torch.no_grad():
+                            enc.eval()
+                            v = part[1].to(self.device)
+                            v = enc(v[None])[0] if self.encdec_needs_batch_dim else enc(v)
+                            s[j] = (part[0], v.detach())
+            n_mods.append(cnt)
+        if times is None and max(n_mods, default = 0) > 0:
+            fn = default(num_modalities_to_times_fn, default_modality_length_to_time_fn)
+            times = fn(tensor(n_mods))
+        process = get_processing_strategy(self.modality_processing)
+        rb = process(samples, times, self, need_axial_pos_emb = False, return_loss = return_loss, return_embed = return_embed)
+        lat = self._latents_to_device(rb)
+        if return_loss:
+            if exists(noise):
+                eps = [n.reshape(-1, self.dim_latents[t]).float().to(self.device) if exists(n) else None for t, n in enumerate(noise)]
+            else:
+                eps = [torch.randn_like(l) if exists(l) else None for l in lat]
+            res = self._run(rb, lat, eps, train = True, text_loss_weight = self.text_loss_weight, flow_loss_weight = self.flow_loss_weight)
+            total = res['total']
+            self._last_batch = rb
+            if not return_breakdown and not return_times:
+                return total
+            ret = (total,)
+            if return_breakdown:
+                flows = [res['flows'][t] for t in range(self.num_modalities) if rb.type_rows[t][1] > rb.type_rows[t][0]]
+                ret = (*ret, LossBreakdown(total, res['text'], flows, None, [[] for _ in range(self.num_modalities)]))
+            if return_times:
+                ret = (*ret, times)
+            return ret
+        res = self.engine.forward(rb, lat, None, train = False, want_logits = not return_embed)
+        self._last_batch = rb
+        n_max = int(rb.seq_lens.max()) if rb.B else 0
+        def unpack(t, width):
+            out = t.new_zeros((rb.B, n_max, width))
+            for b in range(rb.B):
+                out[b, :rb.seq_lens[b]] = t[rb.cu[b]:rb.cu[b + 1], :width]
+            return out
+        if return_embed:
+            return unpack(res['embed'], self.dim), rb
+        return unpack(res['logits'], self.to_text_logits.weight.shape[0])

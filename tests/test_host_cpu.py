@@ -1,0 +1,144 @@
+"""CPU: host logic - pack/route descriptor invariants against the reference's mask / position formulas,
+special-token layout, state_dict parity, and that the C-ABI library loads and exports every symbol declared in
+include/tfx_b200.h (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from transfusion_pytorch_b200 import Transfusion, synth, _lib
+from transfusion_pytorch_b200.modality_processing import pack_batch, pack_text_only, get_processing_strategy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def small_model(**kw):
+    return Transfusion(num_text_tokens = 64, dim_latent = (32, 16), modality_default_shape = ((4,), (2,)), transformer = dict(dim = 128, depth = 2, heads = 2), **kw)
+
+
+def test_special_token_layout_config2():
+    m = Transfusion(num_text_tokens = 256, dim_latent = 384, modality_default_shape = (256,), transformer = dict(dim = 512, depth = 8))
+    assert (m.sos_id, m.eos_id, m.null_text_id, m.som_ids, m.eom_ids, m.meta_id) == (256, 257, 258, [259], [260], 261)
+    assert m.text_embed.weight.shape[0] == 390
+    assert sum(p.numel() for p in m.parameters()) == 79_545_712
+    assert m.char_tokenizer('256').tolist() == [312, 315, 316]
+    assert m.decode_chars(m.char_tokenizer('12,7')) == '12,7'
+
+
+def test_known_answer_positions_and_meta_tokens():
+    m = Transfusion(num_text_tokens = 256, dim_latent = 384, modality_default_shape = (256,), transformer = dict(dim = 512, depth = 8))
+    s = synth.config2_sample(0)
+    rb = pack_batch([[torch.tensor([m.sos_id]), *s, torch.tensor([m.eos_id])]], torch.rand(1, 2), m, return_loss = True, return_embed = False)
+    assert rb.modality_positions == [[(0, 206, 256), (0, 668, 256)]]
+    assert rb.total_tokens == 1025 and rb.M == 1024
+    ids = rb.text_id[201:206].tolist()
+    assert ids == [261, 312, 315, 316, 259]                                 # [meta] '2' '5' '6' [som]
+    assert rb.text_id[462] == 260                                           # [eom]
+    assert rb.S == 512 and rb.n_cond == 2 and rb.n_type_tokens == [512]
+
+
+def naive_mask(n, positions):
+    """the reference's formula (transfusion.py:452-470): causal OR (i >= off AND j < off+len)"""
+    i = np.arange(n)[:, None]; j = np.arange(n)[None, :]
+    mask = i >= j
+    for _, off, ln in positions:
+        mask |= (i >= off) & (j < off + ln)
+    return mask
+
+
+def ref_rotary_positions(n, positions):
+    """transfusion.py:398-415"""
+    seq = np.arange(n)
+    extra = np.zeros(n, dtype = bool)
+    for _, off, ln in positions:
+        extra |= (seq > off) & (seq < off + ln)
+    return seq - np.cumsum(extra)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_descriptor_equals_reference_mask_and_positions(seed):
+    m = small_model()
+    batch = synth.config4_batch(3, seed = seed, total_len = 200, dims = (32, 16), text_vocab = 64)
+    samples = [[torch.tensor([m.sos_id]), *s, torch.tensor([m.eos_id])] for s in batch]
+    n_mod = max(sum(isinstance(p, tuple) for p in s) for s in batch)
+    rb = pack_batch(samples, torch.rand(3, n_mod), m, return_loss = True, return_embed = False)
+    for b in range(rb.B):
+        s0, n = int(rb.cu[b]), int(rb.seq_lens[b])
+        lim = rb.kv_limit[s0:s0 + n] - s0
+        ours = np.arange(n)[None, :] <= lim[:, None]
+        assert (ours == naive_mask(n, rb.modality_positions[b])).all()
+        assert (rb.rope_pos[s0:s0 + n] == ref_rotary_positions(n, rb.modality_positions[b])).all()
+        is_mod = rb.cond_row[s0:s0 + n] >= 0
+        ref_is_mod = np.zeros(n, dtype = bool)
+        for _, off, ln in rb.modality_positions[b]:
+            ref_is_mod[off:off + ln] = True
+        assert (is_mod == ref_is_mod).all()
+    # tiles cover every (query, visible key) pair and never straddle sequences
+    seq_of = np.repeat(np.arange(rb.B), rb.seq_lens)
+    for q0, qe, k0, ke in zip(rb.tile_q0, rb.tile_qend, rb.tile_kv0, rb.tile_kvend):
+        assert seq_of[q0] == seq_of[qe - 1] and k0 == rb.cu[seq_of[q0]]
+        assert rb.kv_limit[q0:qe].max() < ke
+    for k0, ke, q0, qe in zip(rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend):
+        b = seq_of[k0]
+        rows = np.arange(rb.cu[b], rb.cu[b + 1])
+        sees = rows[(rb.kv_limit[rows] >= k0)]
+        sees = sees[(sees >= k0) | (rb.kv_limit[sees] >= k0)]
+        first = rows[(rb.kv_limit[rows] >= k0) & ((rows >= k0) | True)].min()
+        assert q0 <= first and qe == rb.cu[b + 1]
+    # labels: next token, ignored at modality positions / null ids / last position
+    assert rb.n_valid == int((rb.label >= 0).sum()) > 0
+
+
+def test_empty_and_text_only_inputs():
+    m = small_model()
+    rb = pack_batch([[torch.tensor([m.sos_id]), torch.randint(0, 64, (5,)), torch.tensor([m.eos_id])], [torch.tensor([m.sos_id]), torch.tensor([m.eos_id])]],
+                    None, m, return_loss = True, return_embed = False)
+    assert rb.S == 0 and rb.n_cond == 0 and rb.modality_positions == [[], []] and rb.total_tokens == 9 and rb.M == 7
+    rt = pack_text_only(torch.randint(0, 64, (2, 9)), return_loss = True)
+    assert rt.M == 16 and (rt.kv_limit == np.arange(16)).all() and (rt.rope_pos[:8] == np.arange(8)).all()
+
+
+def test_all_strategy_names_resolve_and_agree():
+    m = small_model()
+    batch = [[torch.tensor([m.sos_id]), *s, torch.tensor([m.eos_id])] for s in synth.config4_batch(2, seed = 5, total_len = 120, dims = (32, 16), text_vocab = 64)]
+    times = torch.rand(2, 8)
+    outs = [get_processing_strategy(n)(batch, times, m, need_axial_pos_emb = False, return_loss = True, return_embed = False) for n in ('naive', 'grouped', 'flat', 'hybrid', 'auto')]
+    for o in outs[1:]:
+        assert o.modality_positions == outs[0].modality_positions and (o.text_id == outs[0].text_id).all()
+    with pytest.raises(AssertionError):
+        get_processing_strategy('nope')
+
+
+def test_validation_errors_match_reference_conventions():
+    m = small_model()
+    with pytest.raises(AssertionError):
+        pack_batch([[(5, torch.randn(4, 32))]], torch.rand(1, 1), m, return_loss = False, return_embed = True)      # type out of range
+    with pytest.raises(AssertionError):
+        pack_batch([[(0, torch.randn(4, 31))]], torch.rand(1, 1), m, return_loss = False, return_embed = True)      # wrong latent dim
+    with pytest.raises(NotImplementedError):
+        Transfusion(num_text_tokens = 8, transformer = dict(dim = 128, depth = 1, attn_laser = True))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    assert _lib.library_present(), 'libtfx_b200.so not built (run __graft_entry__.build())'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, 'include', 'tfx_b200.h')).read()
+    declared = set(re.findall(r'\b(tfx_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in include/tfx_b200.h but not exported'
+    assert set(_lib.EXPORTED) == declared
+    lib.tfx_version.restype = ctypes.c_int
+    assert lib.tfx_version() == 100
+
+
+def test_product_fails_loudly_without_cuda():
+    m = small_model()
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    with pytest.raises(Exception) as ei:
+        m(synth.config4_batch(1, seed = 0, total_len = 80, dims = (32, 16), text_vocab = 64))
+    assert 'CUDA' in str(ei.value) or 'cuda' in str(ei.value)

@@ -102,6 +102,8 @@ class Ops:
         self.lib = load()
         import torch
         self._torch = torch
+        self.launches = 0            # kernels launched through the C ABI (every entry point launches exactly one)
+        self.timing = None           # when a dict: name -> list of (start_event, end_event), filled per call
 
     def stream(self):
         return self._torch.cuda.current_stream().cuda_stream
@@ -119,7 +121,15 @@ class Ops:
                     conv.append(a.data_ptr())
                 else:
                     conv.append(a)
-            rc = fn(*conv, self.stream())
+            self.launches += 1
+            if self.timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
+                e0.record()
+                rc = fn(*conv, self.stream())
+                e1.record()
+                self.timing.setdefault(name, []).append((e0, e1, args))
+            else:
+                rc = fn(*conv, self.stream())
             if rc != 0:
                 check(rc, 'tfx_' + name)
         call.__name__ = name

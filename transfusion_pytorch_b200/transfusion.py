@@ -211,7 +211,7 @@ class _TrainStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, g_text, g_flows):
-        ctx.engine.backward(gscale = g_total)
+        ctx.engine.backward(gscale = g_total, bucket_cb = getattr(ctx.engine, '_bucket_cb', None))
         return None, None, None, None, None, None
 
 
@@ -363,7 +363,9 @@ class Transfusion(Module):
             if all(x.is_cuda for x in lst):
                 out.append(cat([x.float() for x in lst]).contiguous())
             else:
-                host = cat([x.detach().float().cpu() for x in lst]).contiguous().pin_memory()
+                host = cat([x.detach().float().cpu() for x in lst]).contiguous()
+                if dev.type == 'cuda':
+                    host = host.pin_memory()
                 nbytes += host.numel() * 4
                 out.append(host.to(dev, non_blocking = True))
         rb.latent_h2d_bytes = nbytes
@@ -376,6 +378,16 @@ class Transfusion(Module):
             total, text, flows = _TrainStep.apply(eng, rb, latents, eps, kw, anchor)
             return dict(total = total, text = text, flows = flows)
         return eng.forward(rb, latents, eps, train = train, **kw)
+
+    def forward_packed(self, rb: RaggedBatch, latents: list, noise: list | None = None, return_breakdown = False):
+        """Training step from an already packed (and possibly already uploaded) ragged batch: the part of `forward`
+        after pack/route.  Used by bench.py to time the device-resident path."""
+        eps = noise if exists(noise) else [torch.randn_like(l) if exists(l) else None for l in latents]
+        res = self._run(rb, latents, eps, train = True, text_loss_weight = self.text_loss_weight, flow_loss_weight = self.flow_loss_weight)
+        self._last_batch = rb
+        if return_breakdown:
+            return res['total'], LossBreakdown(res['total'], res['text'], list(res['flows']), None, None)
+        return res['total']
 
     # ------------------------------------------------------------------ text only (transfusion.py:2585-2707)
     def forward_text(self, text: Tensor, return_loss = True, return_embed = False, cache = None, return_hiddens = False, return_kv_cache = False):

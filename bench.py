@@ -77,7 +77,8 @@ def cpu_port_tokens_per_s(batch: int, steps: int, warmup: int):
     from transfusion_pytorch_b200 import Transfusion, synth
     from oracle.torch_reference import OracleEngine
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(min(cores, 64))
+    cores = min(cores, 64)
     torch.manual_seed(0)
     model = Transfusion(**CTOR, prob_uncond = 0.)
     synth.fill_parameters_(model, seed = 0)
@@ -137,6 +138,10 @@ def family_model(name, args_, eng, rb):
     return 'hbm-bound rows/elementwise', 0, 0
 
 
+def log(*a):
+    print(f'[bench {time.strftime("%H:%M:%S")}]', *a, file = sys.stderr, flush = True)
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -175,6 +180,7 @@ def run_b200_arm(args):
         eng.upload(rb)
         packed.append((rb, lat))
     assert packed[0][0].M == B * SEQ
+    log('packed', POOL, 'batches; M =', packed[0][0].M)
 
     def step_resident(i):
         rb, lat = packed[i % POOL]
@@ -229,6 +235,7 @@ def run_b200_arm(args):
 
     for i in range(args.warmup):
         step_resident(i)
+        torch.cuda.synchronize(); log('warmup step', i, 'done')
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.start()
     l0 = eng.ops.launches
@@ -237,6 +244,7 @@ def run_b200_arm(args):
     if sampler:
         sampler.stop_flag = True
     ms_step = ms_total / args.steps
+    log('resident ms/step', ms_step)
     value = world * B * SEQ / (ms_step / 1e3)
 
     # ---- end to end through the public API (pack/route + H2D + D2H every step)
@@ -252,6 +260,7 @@ def run_b200_arm(args):
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
     e2e_value = world * B * SEQ / (ms_e2e / 1e3)
+    log('e2e ms/step', ms_e2e)
 
     # ---- per-kernel-family device time of one step (profiling pass, not part of the reported throughput)
     roof = None
@@ -280,6 +289,7 @@ def run_b200_arm(args):
     if rank == 0:
         clocks = sampler.summary() if sampler else None
         cpu = None
+        log('roofline pass done')
         if world == 1 and not args.no_cpu_baseline:
             tps, ms_cpu, cores = cpu_port_tokens_per_s(2, 2, 1)
             cpu = dict(value = tps, unit = 'tokens/s', cores = cores, kind = 'port', sample = f'2 sequences x {SEQ} tokens per step (fwd+bwd+Adam, fp32), 2 timed steps after 1 warm-up')

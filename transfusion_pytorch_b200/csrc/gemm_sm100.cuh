@@ -9,6 +9,12 @@
 //
 // Roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner,
 // warps 2..5 = epilogue (warp%4 selects the TMEM lane quadrant; thread <-> one accumulator row).
+//
+// Epilogue memory traffic is staged through a per-warp 32 x 128 B shared-memory tile (XOR-swizzled 16 B
+// chunks) so that every global load/store instruction covers whole 64/128-byte row segments: the TMEM
+// layout gives a thread one ROW (good for per-row math: qk-RMSNorm, RoPE, gate select), the staging turns
+// that into coalesced accesses.  v0 wrote one 16 B piece per lane per row and capped every K=512 GEMM at
+// ~390 TFLOP/s (profiles/r01_gemm_harness_v0.log).
 #pragma once
 #include "sm100_ptx.cuh"
 
@@ -18,6 +24,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;     // 64 bf16 = 128 B = one swizzle atom row
 constexpr int GEMM_UK = 16;     // UMMA K for 16-bit inputs
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_STAGING = 4 * 4096;   // 4 epilogue warps x (32 rows x 128 B)
 
 enum : int { EPI_STORE = 0, EPI_QKVG = 1, EPI_RESID = 2, EPI_GEGLU = 3 };
 
@@ -57,7 +64,7 @@ template <int BN> struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator (power of two: 256 / 512)
 };
 
@@ -68,6 +75,45 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// ---- per-warp staging tile: 32 rows x 128 B, 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
+// lane == row when writing/reading "own row"; (row, chunk) = f(iteration, lane) when touching global memory.
+template <int CH>   // chunks (16 B) per row actually used: 8 (32 fp32 / 64 bf16) or 4 (32 bf16)
+__device__ __forceinline__ void stg_put(uint8_t* sw, int lane, const uint32_t* w) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    *reinterpret_cast<uint4*>(sw + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+template <int CH>
+__device__ __forceinline__ void stg_get(const uint8_t* sw, int lane, uint32_t* w) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const uint4 t = *reinterpret_cast<const uint4*>(sw + lane * 128 + ((c ^ (lane & 7)) << 4));
+    w[4 * c] = t.x; w[4 * c + 1] = t.y; w[4 * c + 2] = t.z; w[4 * c + 3] = t.w;
+  }
+}
+// coalesced global store of the staged tile: g points at (tile row 0, first column); pitch in bytes
+template <int CH>
+__device__ __forceinline__ void stg_store(const uint8_t* sw, int lane, uint8_t* g, long long pitch, int rows_valid) {
+  constexpr int RPI = 32 / CH;
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int row = it * RPI + lane / CH, ch = lane % CH;
+    if (row < rows_valid)
+      *reinterpret_cast<uint4*>(g + row * pitch + ch * 16) = *reinterpret_cast<const uint4*>(sw + row * 128 + ((ch ^ (row & 7)) << 4));
+  }
+}
+template <int CH>
+__device__ __forceinline__ void stg_load(uint8_t* sw, int lane, const uint8_t* g, long long pitch, int rows_valid) {
+  constexpr int RPI = 32 / CH;
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int row = it * RPI + lane / CH, ch = lane % CH;
+    uint4 t = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid) t = *reinterpret_cast<const uint4*>(g + row * pitch + ch * 16);
+    *reinterpret_cast<uint4*>(sw + row * 128 + ((ch ^ (row & 7)) << 4)) = t;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -75,7 +121,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING);
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
@@ -173,7 +220,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================================================== epilogue warps (2..5)
     const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane;
+    uint8_t* sw = staging + quad * 4096;
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int split = item / (m_tiles * n_tiles);
@@ -184,56 +231,75 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull_bar[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + buf * BN;
-      const int row = m_blk * GEMM_BM + row_in_tile;
+      const int wrow0 = m_blk * GEMM_BM + quad * 32;          // first row of this warp's 32-row slab
+      const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
+      const int rows_valid = min(32, p.M - wrow0);            // may be <= 0
       const int col0 = n_blk * BN;
 
       if constexpr (EPI == EPI_STORE) {
-        long long f32_base = -1;
-        if (p.out_f32 && row_ok) f32_base = p.row_off ? p.row_off[row] : (long long)row * p.ld_f32;
+        const bool f32_staged = p.out_f32 && (p.row_off || (p.ld_f32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+        const bool bf16_staged = p.out_bf16 && (p.ld_bf16 & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
+          const int cbase = col0 + c * 32;
+          if (cbase >= p.N) break;
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
-          const int cbase = col0 + c * 32;
-          if (row_ok && cbase < p.N) {
-            float v[32];
+          const bool full = cbase + 32 <= p.N;
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r[j]) * p.alpha;
-              if (p.bias && cbase + j < p.N) v[j] += p.bias[cbase + j];
-            }
-            if (f32_base >= 0) {
-              float* dst = p.out_f32 + f32_base + cbase;
-              const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (cbase + 32 <= p.N);
-              if (p.accumulate_f32) {
-                if (vec) {
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r[j]) * p.alpha;
+            if (p.bias && cbase + j < p.N) v[j] += p.bias[cbase + j];
+          }
+          if (p.out_f32) {
+            if (full && f32_staged) {
 #pragma unroll
-                  for (int j = 0; j < 32; j += 4)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-                } else {
-                  for (int j = 0; j < 32; ++j) if (cbase + j < p.N) atomicAdd(dst + j, v[j]);
-                }
-              } else {
-                if (vec) {
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+              stg_put<8>(sw, lane, r);
+              __syncwarp();
 #pragma unroll
-                  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                  for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = v[j];
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+                if (rr < rows_valid) {
+                  const long long off = p.row_off ? p.row_off[wrow0 + rr] : (long long)(wrow0 + rr) * p.ld_f32;
+                  if (off >= 0) {
+                    float* dst = p.out_f32 + off + cbase + ch * 4;
+                    const float4 t = *reinterpret_cast<const float4*>(sw + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                      if (p.accumulate_f32) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+                      else *reinterpret_cast<float4*>(dst) = t;
+                    } else {
+                      if (p.accumulate_f32) { atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w); }
+                      else { dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
+                    }
+                  }
                 }
               }
+              __syncwarp();
+            } else if (row_ok) {
+              const long long off = p.row_off ? p.row_off[row] : (long long)row * p.ld_f32;
+              if (off >= 0) {
+                float* dst = p.out_f32 + off + cbase;
+                for (int j = 0; j < 32; ++j)
+                  if (cbase + j < p.N) { if (p.accumulate_f32) atomicAdd(dst + j, v[j]); else dst[j] = v[j]; }
+              }
             }
-            if (p.out_bf16) {
+          }
+          if (p.out_bf16) {
+            if (full && bf16_staged) {
+              uint32_t w[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+              stg_put<4>(sw, lane, w);
+              __syncwarp();
+              stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.out_bf16 + (long long)wrow0 * p.ld_bf16 + cbase), p.ld_bf16 * 2, rows_valid);
+              __syncwarp();
+            } else if (row_ok) {
               __nv_bfloat16* dst = p.out_bf16 + (long long)row * p.ld_bf16 + cbase;
-              const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (cbase + 32 <= p.N);
-              if (vec) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8)
-                  *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-              } else {
-                for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = __float2bfloat16(v[j]);
-              }
+              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = __float2bfloat16(v[j]);
             }
           }
         }
@@ -259,41 +325,42 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 32; ++j) { float a = __uint_as_float(r0[j]), b = __uint_as_float(r1[j]); ss += a * a + b * b; }
             const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
             const int head = tis * 2 + hh;
-            if (row_ok) {
-              p.qk_inv[(long long)row * 2 * p.H + kind * p.H + head] = inv;
-              __nv_bfloat16* dst = dstm + (long long)row * HI + head * 64;
-              const float sc = inv * 8.f;
+            if (row_ok) p.qk_inv[(long long)row * 2 * p.H + kind * p.H + head] = inv;
+            const float sc = inv * 8.f;
+            uint32_t outw[32];
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                uint32_t* rr = half == 0 ? r0 : r1;
-                uint32_t outw[16];
+            for (int half = 0; half < 2; ++half) {
+              uint32_t* rr = half == 0 ? r0 : r1;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int d0 = half * 32 + 2 * i;
-                  const float y0 = __uint_as_float(rr[2 * i]) * sc * (gamma[d0] + 1.f);
-                  const float y1 = __uint_as_float(rr[2 * i + 1]) * sc * (gamma[d0 + 1] + 1.f);
-                  const float2 c = cs[half * 16 + i];
-                  outw[i] = pack_bf16(y0 * c.x - y1 * c.y, y1 * c.x + y0 * c.y);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                  *reinterpret_cast<uint4*>(dst + half * 32 + i * 2) = make_uint4(outw[i], outw[i + 1], outw[i + 2], outw[i + 3]);
+              for (int i = 0; i < 16; ++i) {
+                const int d0 = half * 32 + 2 * i;
+                const float y0 = __uint_as_float(rr[2 * i]) * sc * (gamma[d0] + 1.f);
+                const float y1 = __uint_as_float(rr[2 * i + 1]) * sc * (gamma[d0 + 1] + 1.f);
+                const float2 cc = cs[half * 16 + i];
+                outw[half * 16 + i] = pack_bf16(y0 * cc.x - y1 * cc.y, y1 * cc.x + y0 * cc.y);
               }
             }
+            stg_put<8>(sw, lane, outw);
+            __syncwarp();
+            stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(dstm + (long long)wrow0 * HI + head * 64), HI * 2, rows_valid);
+            __syncwarp();
           }
         } else if (kind == 2) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr + c * 32, r);
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r0[32], r1[32], w[32];
+            tmem_ld_32x32b_x32(taddr + c * 64, r0);
+            tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
             tmem_ld_wait();
-            if (row_ok) {
-              __nv_bfloat16* dst = p.v + (long long)row * HI + tis * 128 + c * 32;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack_bf16(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
-                                                                 pack_bf16(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])), pack_bf16(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])));
+            for (int j = 0; j < 16; ++j) {
+              w[j] = pack_bf16(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+              w[16 + j] = pack_bf16(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
             }
+            stg_put<8>(sw, lane, w);
+            __syncwarp();
+            stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(p.v + (long long)wrow0 * HI + tis * 128 + c * 64), HI * 2, rows_valid);
+            __syncwarp();
           }
         } else {
           uint32_t r[32];
@@ -310,35 +377,46 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float* zrow = (p.zgate && crow >= 0) ? p.zgate + (long long)crow * p.zgate_ld : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          tmem_ld_wait();
           const int cbase = col0 + c * 32;
-          if (row_ok && cbase < p.N) {    // N is a multiple of 32 for every RESID use (512)
-            const long long off = (long long)row * p.N + cbase;
-            float y[32];
+          if (cbase >= p.N) break;                    // N is a multiple of 32 for every RESID use
+          uint32_t r[32], xr[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          stg_load<8>(sw, lane, reinterpret_cast<const uint8_t*>(p.x_res + (long long)wrow0 * p.N + cbase), (long long)p.N * 4, rows_valid);
+          __syncwarp();
+          stg_get<8>(sw, lane, xr);
+          __syncwarp();
+          tmem_ld_wait();
+          float y[32], o[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
-            if (p.y_bf16) {
+          for (int j = 0; j < 32; ++j) {
+            y[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
+            float s = 1.f;
+            if (zrow) s = zrow[cbase + j]; else if (p.ls) s = p.ls[cbase + j] + 1.f;
+            o[j] = __uint_as_float(xr[j]) + y[j] * s;
+          }
+          if (p.y_bf16) {
+            uint32_t w[16];
 #pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(p.y_bf16 + off + j) = make_uint4(pack_bf16(y[j], y[j + 1]), pack_bf16(y[j + 2], y[j + 3]), pack_bf16(y[j + 4], y[j + 5]), pack_bf16(y[j + 6], y[j + 7]));
-            }
-            float o[32];
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(y[2 * j], y[2 * j + 1]);
+            stg_put<4>(sw, lane, w);
+            __syncwarp();
+            stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.y_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
+            __syncwarp();
+          }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 xr = *reinterpret_cast<const float4*>(p.x_res + off + j);
-              float4 s = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (zrow) s = *reinterpret_cast<const float4*>(zrow + cbase + j);
-              else if (p.ls) { s = *reinterpret_cast<const float4*>(p.ls + cbase + j); s.x += 1.f; s.y += 1.f; s.z += 1.f; s.w += 1.f; }
-              o[j] = xr.x + y[j] * s.x; o[j + 1] = xr.y + y[j + 1] * s.y; o[j + 2] = xr.z + y[j + 2] * s.z; o[j + 3] = xr.w + y[j + 3] * s.w;
-              *reinterpret_cast<float4*>(p.x_out + off + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            }
-            if (p.x_out_bf16) {
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(o[j]);
+          stg_put<8>(sw, lane, r);
+          __syncwarp();
+          stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(p.x_out + (long long)wrow0 * p.N + cbase), (long long)p.N * 4, rows_valid);
+          __syncwarp();
+          if (p.x_out_bf16) {
+            uint32_t w[16];
 #pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(p.x_out_bf16 + off + j) = make_uint4(pack_bf16(o[j], o[j + 1]), pack_bf16(o[j + 2], o[j + 3]), pack_bf16(o[j + 4], o[j + 5]), pack_bf16(o[j + 6], o[j + 7]));
-            }
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(o[2 * j], o[2 * j + 1]);
+            stg_put<4>(sw, lane, w);
+            __syncwarp();
+            stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.x_out_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
+            __syncwarp();
           }
         }
       } else if constexpr (EPI == EPI_GEGLU) {
@@ -349,25 +427,21 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_32x32b_x32(taddr + c * 32, rv);
           tmem_ld_32x32b_x32(taddr + 64 + c * 32, rg);
           tmem_ld_wait();
-          if (row_ok) {
-            const int cv = col0 + c * 32, cg = col0 + 64 + c * 32;
-            float v[32], g[32], hh[32];
+          const int cv = col0 + c * 32, cg = col0 + 64 + c * 32;
+          uint32_t wv[16], wg[16], wh[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(rv[j]) + p.bias[cv + j];
-              g[j] = __uint_as_float(rg[j]) + p.bias[cg + j];
-              hh[j] = gelu_erf(g[j]) * v[j];
-            }
-            __nv_bfloat16* dv = p.vg + (long long)row * p.N + cv;
-            __nv_bfloat16* dg = p.vg + (long long)row * p.N + cg;
-            __nv_bfloat16* dh = p.h + (long long)row * (p.N / 2) + n_blk * 64 + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              *reinterpret_cast<uint4*>(dv + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-              *reinterpret_cast<uint4*>(dg + j) = make_uint4(pack_bf16(g[j], g[j + 1]), pack_bf16(g[j + 2], g[j + 3]), pack_bf16(g[j + 4], g[j + 5]), pack_bf16(g[j + 6], g[j + 7]));
-              *reinterpret_cast<uint4*>(dh + j) = make_uint4(pack_bf16(hh[j], hh[j + 1]), pack_bf16(hh[j + 2], hh[j + 3]), pack_bf16(hh[j + 4], hh[j + 5]), pack_bf16(hh[j + 6], hh[j + 7]));
-            }
+          for (int j = 0; j < 16; ++j) {
+            const float v0 = __uint_as_float(rv[2 * j]) + p.bias[cv + 2 * j], v1 = __uint_as_float(rv[2 * j + 1]) + p.bias[cv + 2 * j + 1];
+            const float g0 = __uint_as_float(rg[2 * j]) + p.bias[cg + 2 * j], g1 = __uint_as_float(rg[2 * j + 1]) + p.bias[cg + 2 * j + 1];
+            wv[j] = pack_bf16(v0, v1); wg[j] = pack_bf16(g0, g1);
+            wh[j] = pack_bf16(gelu_erf(g0) * v0, gelu_erf(g1) * v1);
           }
+          stg_put<4>(sw, lane, wv); __syncwarp();
+          stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.vg + (long long)wrow0 * p.N + cv), (long long)p.N * 2, rows_valid); __syncwarp();
+          stg_put<4>(sw, lane, wg); __syncwarp();
+          stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.vg + (long long)wrow0 * p.N + cg), (long long)p.N * 2, rows_valid); __syncwarp();
+          stg_put<4>(sw, lane, wh); __syncwarp();
+          stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.h + (long long)wrow0 * (p.N / 2) + n_blk * 64 + c * 32), (long long)p.N, rows_valid); __syncwarp();
         }
       }
       // release this accumulator buffer back to the MMA warp

@@ -433,7 +433,7 @@ class Engine:
             text = (acc[0] / max(rb.n_valid, 1)).float()
             flows = torch.stack([f if f is not None else torch.zeros((), device = self.device) for f in flow_terms]) if flow_terms else torch.zeros(0, device = self.device)
             if vlimit:
-                total = text
+                total = text.clone()         # distinct tensor: autograd.Function outputs must not alias each other
             elif modality_only:
                 total = flows.sum()
             else:

@@ -7,8 +7,9 @@
 //   A "MN-major": stored row-major [K][M]   (dY^T for wgrad: K = tokens)
 //   B likewise over n.
 //
-// Roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner,
-// warps 2..5 = epilogue (warp%4 selects the TMEM lane quadrant; thread <-> one accumulator row).
+// Roles (320 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner,
+// warps 2..9 = epilogue (warp%4 selects the TMEM lane quadrant, (warp-2)/4 the column half of the tile;
+// thread <-> one accumulator row).  Two epilogue warps per SM sub-partition hide each other's latencies.
 //
 // Epilogue memory traffic is staged through a per-warp 32 x 128 B shared-memory tile (XOR-swizzled 16 B
 // chunks) so that every global load/store instruction covers whole 64/128-byte row segments: the TMEM
@@ -23,8 +24,8 @@ namespace tfx {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;     // 64 bf16 = 128 B = one swizzle atom row
 constexpr int GEMM_UK = 16;     // UMMA K for 16-bit inputs
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_STAGING = 4 * 4096;   // 4 epilogue warps x (32 rows x 128 B)
+constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int GEMM_STAGING = 8 * 4096;   // 8 epilogue warps x (32 rows x 128 B)
 
 enum : int { EPI_STORE = 0, EPI_QKVG = 1, EPI_RESID = 2, EPI_GEGLU = 3 };
 
@@ -140,7 +141,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -218,9 +219,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================================================== epilogue warps (2..5)
+    // ===================================================== epilogue warps (2..9)
     const int quad = warp & 3;
-    uint8_t* sw = staging + quad * 4096;
+    const int half = (warp - 2) >> 2;        // column half of the tile handled by this warp
+    uint8_t* sw = staging + (warp - 2) * 4096;
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int split = item / (m_tiles * n_tiles);
@@ -241,7 +243,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool f32_staged = p.out_f32 && (p.row_off || (p.ld_f32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
         const bool bf16_staged = p.out_bf16 && (p.ld_bf16 & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
           const int cbase = col0 + c * 32;
           if (cbase >= p.N) break;
           uint32_t r[32];
@@ -250,9 +252,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const bool full = cbase + 32 <= p.N;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(r[j]) * p.alpha;
-            if (p.bias && cbase + j < p.N) v[j] += p.bias[cbase + j];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.alpha != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          }
+          if (p.bias) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) { const float4 b = *reinterpret_cast<const float4*>(p.bias + cbase + j); v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w; }
+            } else {
+              for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] += p.bias[cbase + j];
+            }
           }
           if (p.out_f32) {
             if (full && f32_staged) {
@@ -314,8 +325,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __nv_bfloat16* dstm = kind == 0 ? p.q : p.k;
           const int pos = row_ok ? p.rope_pos[row] : 0;
           const float2* cs = p.rope_cs + (long long)pos * 32;
-#pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {
+          {
+            const int hh = half;
             uint32_t r0[32], r1[32];
             tmem_ld_32x32b_x32(taddr + hh * 64, r0);
             tmem_ld_32x32b_x32(taddr + hh * 64 + 32, r1);
@@ -334,8 +345,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int d0 = half * 32 + 2 * i;
-                const float y0 = __uint_as_float(rr[2 * i]) * sc * (gamma[d0] + 1.f);
-                const float y1 = __uint_as_float(rr[2 * i + 1]) * sc * (gamma[d0 + 1] + 1.f);
+                const float2 gm = *reinterpret_cast<const float2*>(gamma + d0);
+                const float y0 = __uint_as_float(rr[2 * i]) * sc * (gm.x + 1.f);
+                const float y1 = __uint_as_float(rr[2 * i + 1]) * sc * (gm.y + 1.f);
                 const float2 cc = cs[half * 16 + i];
                 outw[half * 16 + i] = pack_bf16(y0 * cc.x - y1 * cc.y, y1 * cc.x + y0 * cc.y);
               }
@@ -346,8 +358,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
           }
         } else if (kind == 2) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          {
+            const int c = half;
             uint32_t r0[32], r1[32], w[32];
             tmem_ld_32x32b_x32(taddr + c * 64, r0);
             tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
@@ -362,7 +374,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(p.v + (long long)wrow0 * HI + tis * 128 + c * 64), HI * 2, rows_valid);
             __syncwarp();
           }
-        } else {
+        } else if (half == 0) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
@@ -376,7 +388,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int crow = (row_ok && p.cond_row) ? p.cond_row[row] : -1;
         const float* zrow = (p.zgate && crow >= 0) ? p.zgate + (long long)crow * p.zgate_ld : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
           const int cbase = col0 + c * 32;
           if (cbase >= p.N) break;                    // N is a multiple of 32 for every RESID use
           uint32_t r[32], xr[32];
@@ -388,11 +400,28 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_wait();
           float y[32], o[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            y[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
-            float s = 1.f;
-            if (zrow) s = zrow[cbase + j]; else if (p.ls) s = p.ls[cbase + j] + 1.f;
-            o[j] = __uint_as_float(xr[j]) + y[j] * s;
+          for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) { const float4 b = *reinterpret_cast<const float4*>(p.bias + cbase + j); y[j] += b.x; y[j + 1] += b.y; y[j + 2] += b.z; y[j + 3] += b.w; }
+          }
+          if (zrow) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(zrow + cbase + j);
+              o[j] = __uint_as_float(xr[j]) + y[j] * s4.x; o[j + 1] = __uint_as_float(xr[j + 1]) + y[j + 1] * s4.y;
+              o[j + 2] = __uint_as_float(xr[j + 2]) + y[j + 2] * s4.z; o[j + 3] = __uint_as_float(xr[j + 3]) + y[j + 3] * s4.w;
+            }
+          } else if (p.ls) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(p.ls + cbase + j);
+              o[j] = __uint_as_float(xr[j]) + y[j] * (s4.x + 1.f); o[j + 1] = __uint_as_float(xr[j + 1]) + y[j + 1] * (s4.y + 1.f);
+              o[j + 2] = __uint_as_float(xr[j + 2]) + y[j + 2] * (s4.z + 1.f); o[j + 3] = __uint_as_float(xr[j + 3]) + y[j + 3] * (s4.w + 1.f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(xr[j]) + y[j];
           }
           if (p.y_bf16) {
             uint32_t w[16];
@@ -421,8 +450,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else if constexpr (EPI == EPI_GEGLU) {
         static_assert(EPI != EPI_GEGLU || BN == 128, "GEGLU epilogue expects 128-wide N tiles");
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = half;
           uint32_t rv[32], rg[32];
           tmem_ld_32x32b_x32(taddr + c * 32, rv);
           tmem_ld_32x32b_x32(taddr + 64 + c * 32, rg);

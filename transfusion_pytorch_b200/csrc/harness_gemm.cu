@@ -98,6 +98,10 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   int sms = prop.multiProcessorCount;
   printf("device %s  sm_%d%d  SMs %d\n", prop.name, prop.major, prop.minor, sms);
+  if (argc > 1 && !strcmp(argv[1], "--one")) {
+    bench<128, false, false>("qkvg fwd", 65536, 1664, 512, 1, sms);
+    return 0;
+  }
   int fails = 0;
   // single tile, single k-block first: isolates descriptor errors
   fails += check<128, false, false>("NT 1tile 1kb", 128, 128, 64, 1, sms);

@@ -304,7 +304,7 @@ int tfx_mse_fwd_bwd(const float* pred, long long ld_pred, const float* flow, voi
 
 int tfx_colsum_bf16(const void* in_bf16, long long ld, long long M, int N, const int* col_map, float* out, void* stream) {
   if (M <= 0 || N <= 0) return 0;
-  const int rpb = 2048;
+  const int rpb = 256;
   colsum_bf16_k<<<dim3((N + 63) / 64, (unsigned)((M + rpb - 1) / rpb)), 256, 0, ST(stream)>>>((const __nv_bfloat16*)in_bf16, ld, M, N, col_map, out, rpb);
   return check_launch("colsum_bf16");
 }

@@ -100,9 +100,39 @@ def run_text_only(ref, name, ctor, text, seed, prompt_len = 16, gen_len = 40):
     print(f'{name}: loss {loss.item():.6f} generated[0,:8] {gen[0, :8].tolist()}')
 
 
+def run_sampling(ref, name, ctor, seed):
+    """sample_many on mixed prompts, greedy text, fixed init noise, forced modality at start (shrunk)."""
+    torch.manual_seed(0)
+    model = ref.Transfusion(**ctor)
+    synth.fill_parameters_(model, seed = seed)
+    model.eval()
+    g = torch.Generator().manual_seed(77)
+    dl = ctor['dim_latent']
+    prompts = [
+        torch.randint(0, ctor['num_text_tokens'], (9,), generator = g),
+        (0, torch.randn(5, dl, generator = g)),
+        None,
+        [torch.randint(0, ctor['num_text_tokens'], (4,), generator = g), (0, torch.randn(7, dl, generator = g))],
+    ]
+    noise = torch.randn(16, dl, generator = g)
+    kw = dict(max_length = 14, text_temperature = 0., cfg_scale = 3., modality_steps = 4, init_modality_noise = noise, force_modality_at_start = (0, (6,)),
+              return_unprocessed_modalities = True)
+    import copy
+    out = model.sample_many(copy.deepcopy(prompts), **kw)
+    fx = dict(name = name, ctor = ctor, seed = seed, prompts = prompts, noise = noise, kw = {k: v for k, v in kw.items() if k != 'init_modality_noise'}, samples = out)
+    torch.save(fx, os.path.join(GOLDEN, f'{name}.pt'))
+    for s in out:
+        print('  sample:', [tuple(p.shape) if torch.is_tensor(p) else ('mod', p[0], tuple(p[1].shape)) for p in s])
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok = True)
     ref = load_reference()
+
+    ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), transformer = dict(dim = 128, depth = 2, heads = 2))
+    run_sampling(ref, 'sampling_small', ctor, seed = 8)
+    if os.environ.get('GOLDEN_ONLY_SAMPLING'):
+        return
 
     # (1) small single-modality, ragged, all hiddens kept
     ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), transformer = dict(dim = 128, depth = 2, heads = 2))

@@ -125,12 +125,15 @@ def test_mask_locality_property_full_size():
     s3[3] = s3[3] + 1.0                             # second latent span (positions 667..922): changes the whole span, nothing before it
     t = torch.tensor([[0.3, 0.7]])
     with torch.no_grad():
-        e1, _ = model([s], times = t, return_embed = True)
+        e1, rb = model([s], times = t, return_embed = True)
         e2, _ = model([s2], times = t, return_embed = True)
         e3, _ = model([s3], times = t, return_embed = True)
-    assert torch.equal(e1[0, :923], e2[0, :923]) and not torch.equal(e1[0, 923:], e2[0, 923:])
-    assert torch.equal(e1[0, :667], e3[0, :667])
-    assert (e1[0, 667:923] != e3[0, 667:923]).any(dim = -1).all()      # every token of the span sees the change (bidirectional)
+    (_, o1, l1), (_, o2, l2) = rb.modality_positions[0]          # return_embed: no [sos]/meta tokens -> spans at 200 and 656
+    assert (o1, l1, o2, l2) == (200, 256, 656, 256)
+    tail = o2 + l2                                                # first token of the last text chunk
+    assert torch.equal(e1[0, :tail], e2[0, :tail]) and not torch.equal(e1[0, tail:], e2[0, tail:])
+    assert torch.equal(e1[0, :o2], e3[0, :o2])
+    assert (e1[0, o2:tail] != e3[0, o2:tail]).any(dim = -1).all()      # every token of the span sees the change (bidirectional)
 
 
 def test_backward_is_linear_in_grad_output_and_accumulates():

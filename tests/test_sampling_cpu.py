@@ -1,0 +1,40 @@
+"""CPU: `sample_many` / `sample_one` host logic (state machine, midpoint ODE, CFG, prompt handling, the cached-KV
+semantics of the reference) reproduces the reference's own `sample_many` output (tests/golden/sampling_small.pt)
+when the engine is the fp32 oracle.  The same check runs on the GPU against the CUDA engine in test_sampling_gpu.py."""
+import copy
+
+import torch
+
+from helpers import load_golden
+from transfusion_pytorch_b200 import Transfusion, synth
+from oracle.torch_reference import OracleEngine
+
+
+def run(model, fx):
+    return model.sample_many(copy.deepcopy(fx['prompts']), init_modality_noise = fx['noise'], **fx['kw'])
+
+
+def compare(out, ref, text_exact = True, atol = 1e-4):
+    assert len(out) == len(ref)
+    for s, r in zip(out, ref):
+        assert len(s) == len(r), ([type(p) for p in s], [type(p) for p in r])
+        for a, b in zip(s, r):
+            if torch.is_tensor(b):
+                if text_exact:
+                    assert torch.equal(a.cpu(), b), (a, b)
+            else:
+                assert a[0] == b[0] and a[1].shape == b[1].shape
+                assert torch.allclose(a[1].float().cpu(), b[1], atol = atol, rtol = 1e-3), (a[1].float().cpu() - b[1]).abs().max()
+
+
+def test_sample_many_matches_reference_with_oracle_engine():
+    fx = load_golden('sampling_small')
+    torch.manual_seed(0)
+    model = Transfusion(**fx['ctor'])
+    synth.fill_parameters_(model, seed = fx['seed'])
+    model.eval()
+    model._engine = OracleEngine(model)
+    out = run(model, fx)
+    compare(out, fx['samples'])
+    one = model.sample_one(copy.deepcopy(fx['prompts'][3]), init_modality_noise = fx['noise'], **fx['kw'])
+    compare([one], [fx['samples'][3]])

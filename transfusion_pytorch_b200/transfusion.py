@@ -21,6 +21,7 @@ import torch
 from torch import nn, Tensor, tensor, is_tensor, cat
 from torch.nn import Module, ModuleList
 
+from .sampling import SamplingMixin
 from .modality_processing import (
     ModalitySample, RaggedBatch, pack_batch, pack_text_only, get_processing_strategy, DEFAULT_PROCESSING_STRATEGY, is_int_tensor)
 
@@ -215,7 +216,7 @@ class _TrainStep(torch.autograd.Function):
         return None, None, None, None, None, None
 
 
-class Transfusion(Module):
+class Transfusion(SamplingMixin, Module):
     def __init__(
         self,
         *,
@@ -360,8 +361,8 @@ class Transfusion(Module):
         for t, lst in enumerate(rb.latents):
             if not lst:
                 out.append(None); continue
-            if all(x.is_cuda for x in lst):
-                out.append(cat([x.float() for x in lst]).contiguous())
+            if any(x.is_cuda for x in lst):
+                out.append(cat([x.detach().to(dev).float() for x in lst]).contiguous())
             else:
                 host = cat([x.detach().float().cpu() for x in lst]).contiguous()
                 if dev.type == 'cuda':

@@ -263,11 +263,13 @@ def run_b200_arm(args):
     log('e2e ms/step', ms_e2e)
 
     # ---- per-kernel-family device time of one step (profiling pass, not part of the reported throughput)
+    # every rank runs the step (it contains the gradient all-reduce); only rank 0 records per-launch events
     roof = None
     if rank == 0:
         eng.ops.timing = {}
-        step_resident(0)
-        torch.cuda.synchronize()
+    step_resident(0)
+    barrier()
+    if rank == 0:
         fam = {}
         rb = packed[0][0]
         for name, recs in eng.ops.timing.items():

@@ -212,7 +212,7 @@ def run_b200_arm(args):
             torch.cuda.current_stream().wait_stream(trainer.comm_stream)
         else:
             loss.backward()
-        eng.adam_step(lr = 1e-4, grad_scale = 1.0 / world)
+        eng.adam_step(lr = 1e-4, grad_scale = 1.0 / world, zero_grads = True)
         return loss
 
     def barrier():

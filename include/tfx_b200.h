@@ -61,7 +61,8 @@ int tfx_gemm_geglu(const void* u, long long ldu, const void* W1p, long long ldw,
 int tfx_attn_fwd(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
                  const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
                  void* o, long long ld_o, float* lse, int M, float scale, float softcap, void* stream);
-int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, int M, int H, void* stream);
+/* dq_zero (optional): fp32 [M][H*64] accumulator of tfx_attn_bwd, cleared here in the same pass */
+int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, float* dq_zero, int M, int H, void* stream);
 int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
                  const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
                  int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, void* stream);
@@ -77,14 +78,16 @@ int tfx_adaln_fwd(const float* x, const int* cond_row, const float* film, long l
                   void* u_bf16, float* stats, int M, int D, void* stream);
 int tfx_adaln_bwd(const float* du, const float* x, const float* stats, const int* cond_row, const float* film, long long film_ld,
                   const float* ln_gamma, float* dx_accum, float* dfilm, long long dfilm_ld, float* dln_gamma, int M, int D, void* stream);
-/* backward of the output gate of tfx_gemm_resid: dy = dx*scale (bf16), d zgate / d layerscale accumulated */
+/* backward of the output gate of tfx_gemm_resid: dy = dx*scale (bf16), d zgate / d layerscale accumulated;
+ * dbias (optional, [D]) += column sums of dy (gradient of the bias of the producing Linear, T.py:849) */
 int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, const float* zgate, long long zgate_ld, const float* layerscale,
-                  void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, int M, int D, void* stream);
+                  void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, float* dbias, int M, int D, void* stream);
 /* AttentionResidual (T.py:803-829): softmax mix over all hiddens so far, single pass */
 int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
                           float* x_out, void* x_out_bf16, int M, int D, void* stream);
 int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          const float* dx_out, float* dgamma, float* dpseudo_query, int M, int D, void* stream);
+                          const float* dx_out, float* dgamma, float* dpseudo_query, int M, int D, int init /* 1: dhiddens are overwritten, not accumulated */,
+                          void* stream);
 /* final RMSNorm (T.py:1250, 785-786) (+ compaction of modality rows for the flow head) */
 int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream);
 int tfx_rmsnorm_bwd(const float* dout, const float* x, const float* gamma, float* dx, float* dgamma, int M, int D, void* stream);
@@ -101,7 +104,8 @@ int tfx_time_features(const float* times, const float* fourier_w, void* feats_bf
 /* small table ops of the conditioning path: op 0 sigmoid(a), 1 silu(a), 2 a*b*(1-b), 3 a*silu'(b), 4 copy */
 int tfx_table_op(const float* a, long long ld_a, const float* b, long long ld_b, float* out_f32, long long ld_of, void* out_bf16, long long ld_ob, long long rows, int cols,
                  int op, void* stream);
-int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, void* stream);
+/* dbias (optional) [col_map ? mapped : 2*inner_pad] += column sums of dvg (gradient of the FFN-in bias, T.py:845) */
+int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, const int* col_map, float* dbias, void* stream);
 /* text cross-entropy fwd+bwd (T.py:3320-3331; text-only 2653-2659 with vlimit = num_text_tokens) */
 int tfx_ce_fwd_bwd(const float* logits, long long ld_logits, const int* labels, int V, int vlimit, float gscale, void* dlogits_bf16, long long ld_dlogits,
                    double* loss_sum, int* n_valid, int M, void* stream);
@@ -110,14 +114,20 @@ int tfx_mse_fwd_bwd(const float* pred, long long ld_pred, const float* flow, voi
 int tfx_colsum_bf16(const void* in_bf16, long long ld, long long M, int N, const int* col_map, float* out, void* stream);
 int tfx_colsum_f32(const float* in, long long ld, long long M, int N, float* out, void* stream);
 int tfx_cast_pack(const float* src, long long ld_src, int C_src, const int* row_src, void* dst_bf16, long long R_dst, int C_dst, void* stream);
+/* all per-optimizer-step weight repacks in one launch; jobs / block tables live in device memory (built once by the host) */
+typedef struct TfxPackJob {
+  const float* src; long long ld_src; const int* row_src /* optional row gather, -1 = zero row */; void* dst /* bf16, or fp32 if dst_f32 */;
+  long long R_dst; int C_src; int C_dst; int dst_f32; int pad_;
+} TfxPackJob;
+int tfx_cast_pack_multi(const TfxPackJob* jobs_dev, const int* blk_job_dev, const int* blk_first_dev, int n_blocks, void* stream);
 int tfx_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int tfx_scale_f32(float* p, const float* scale_ptr, float scale, long long n, void* stream);
 int tfx_scale_bf16(void* p_bf16, const float* scale_ptr, long long n, void* stream);          /* p *= *scale_ptr (device scalar) */
 int tfx_axpy_f32(float* y, const float* x, float a, long long n, void* stream);   /* y += a*x */
 int tfx_rope_table(const float* freqs, float* cos_sin, int max_pos, int n_freqs, void* stream);
 /* fused Adam / AdamW over the flat parameter buffer (the optimizer the reference's examples use, train_latent_with_text.py:142-153) */
-int tfx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                  int decoupled_wd, int step, float grad_scale, void* stream);
+int tfx_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int decoupled_wd, int step, float grad_scale, int zero_grads /* 1: clear grads in the same pass */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -95,7 +95,7 @@ def test_attention_forward_backward_vs_dense(ops, lens, spans):
     do = torch.randn(M, H * 64, device = 'cuda', generator = g).to(BF16)
     ref.backward(do.float())
     dop = torch.zeros_like(do); dsum = torch.zeros(H, M, device = 'cuda'); dsum2 = torch.zeros(M, H, device = 'cuda')
-    ops.attn_bwd_prep(do, o, gates, dop, dsum, dsum2, M, H)
+    ops.attn_bwd_prep(do, o, gates, dop, dsum, dsum2, None, M, H)
     dq = torch.zeros(M, H * 64, device = 'cuda'); dk = torch.zeros(M, H * 64, device = 'cuda'); dv = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
     ops.attn_bwd(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.kt_kv0), dev(rb.kt_kvend), dev(rb.kt_q0), dev(rb.kt_qend), len(rb.kt_kv0), dq, dk, dv, H * 64,
                  M, H, scale, cap)

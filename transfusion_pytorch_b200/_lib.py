@@ -24,14 +24,14 @@ SIGNATURES = {
     'tfx_gemm_resid': [VP, LL, VP, LL, I, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, LL, VP, VP],
     'tfx_gemm_geglu': [VP, LL, VP, LL, VP, I, I, I, VP, VP, VP],
     'tfx_attn_fwd': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, LL, VP, I, F, F, VP],
-    'tfx_attn_bwd_prep': [VP, VP, VP, VP, VP, VP, I, I, VP],
+    'tfx_attn_bwd_prep': [VP, VP, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_attn_bwd': [VP, VP, VP, VP, LL, LL, LL, LL, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP, LL, I, I, F, F, VP],
     'tfx_qk_bwd_pack': [VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, LL, VP, VP, I, I, VP],
     'tfx_adaln_fwd': [VP, VP, VP, LL, VP, VP, VP, I, I, VP],
     'tfx_adaln_bwd': [VP, VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, I, I, VP],
-    'tfx_resid_bwd': [VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, I, I, VP],
+    'tfx_resid_bwd': [VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, VP, I, I, VP],
     'tfx_attn_residual_fwd': [VP, I, VP, VP, VP, VP, I, I, VP],
-    'tfx_attn_residual_bwd': [VP, VP, I, VP, VP, VP, VP, VP, I, I, VP],
+    'tfx_attn_residual_bwd': [VP, VP, I, VP, VP, VP, VP, VP, I, I, I, VP],
     'tfx_rmsnorm_fwd': [VP, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_rmsnorm_bwd': [VP, VP, VP, VP, VP, I, I, VP],
     'tfx_embed_assemble': [VP, VP, VP, VP, VP, VP, I, I, VP],
@@ -40,18 +40,19 @@ SIGNATURES = {
     'tfx_flow_noise': [VP, VP, VP, VP, LL, VP, VP, LL, I, VP],
     'tfx_time_features': [VP, VP, VP, I, I, I, VP],
     'tfx_table_op': [VP, LL, VP, LL, VP, LL, VP, LL, LL, I, I, VP],
-    'tfx_geglu_bwd': [VP, VP, VP, LL, I, VP],
+    'tfx_geglu_bwd': [VP, VP, VP, LL, I, VP, VP, VP],
     'tfx_ce_fwd_bwd': [VP, LL, VP, I, I, F, VP, LL, VP, VP, I, VP],
     'tfx_mse_fwd_bwd': [VP, LL, VP, VP, LL, F, VP, LL, I, VP],
     'tfx_colsum_bf16': [VP, LL, LL, I, VP, VP, VP],
     'tfx_colsum_f32': [VP, LL, LL, I, VP, VP],
     'tfx_cast_pack': [VP, LL, I, VP, VP, LL, I, VP],
+    'tfx_cast_pack_multi': [VP, VP, VP, I, VP],
     'tfx_cast_bf16': [VP, VP, LL, VP],
     'tfx_scale_f32': [VP, VP, F, LL, VP],
     'tfx_scale_bf16': [VP, VP, LL, VP],
     'tfx_axpy_f32': [VP, VP, F, LL, VP],
     'tfx_rope_table': [VP, VP, I, I, VP],
-    'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, VP],
+    'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP],
 }
 
 EXPORTED = ['tfx_last_error', 'tfx_version'] + list(SIGNATURES)

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_k(const __nv_bfloat16* _
 // ================================================================================================ backward
 // pre-pass (one warp per token): dsum[h][row] = sum_d dO_gated*O_gated ; dO_pre = dO_gated * sigmoid(gate)
 __global__ void __launch_bounds__(ROW_THREADS) attn_bwd_prep_k(const __nv_bfloat16* __restrict__ dog, const __nv_bfloat16* __restrict__ og, const float* __restrict__ gates,
-                                                              __nv_bfloat16* __restrict__ dop, float* __restrict__ dsum, float* __restrict__ dsum_rowmajor, int M, int H) {
+                                                              __nv_bfloat16* __restrict__ dop, float* __restrict__ dsum, float* __restrict__ dsum_rowmajor, float* __restrict__ dq_zero, int M, int H) {
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int HI = H * 64;
@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_bwd_prep_k(const __nv_bfloat
       const float sg = gates ? 1.f / (1.f + __expf(-gates[(long long)row * H + h])) : 1.f;
       *reinterpret_cast<uint32_t*>(dop + off) = pack2_bf16(a.x * sg, a.y * sg);
       if (lane == 0) { dsum[(long long)h * M + row] = s; if (dsum_rowmajor) dsum_rowmajor[(long long)row * H + h] = s; }
+      if (dq_zero) *reinterpret_cast<float2*>(dq_zero + off) = make_float2(0.f, 0.f);
     }
   }
 }
@@ -427,12 +428,12 @@ int tfx_attn_fwd(const void* q, const void* k, const void* v, long long ld_q, lo
   return check_launch("attn_fwd");
 }
 
-int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, int M, int H, void* stream) {
+int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, float* dq_zero, int M, int H, void* stream) {
   if (M <= 0) return 0;
   long long blocks = ((long long)M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   long long cap = (long long)num_sms() * 8;
   attn_bwd_prep_k<<<(int)(blocks < cap ? blocks : cap), ROW_THREADS, 0, ST(stream)>>>((const __nv_bfloat16*)do_gated, (const __nv_bfloat16*)o_gated, gates, (__nv_bfloat16*)do_pre,
-                                                                                   dsum_hm, dsum_mh, M, H);
+                                                                                   dsum_hm, dsum_mh, dq_zero, M, H);
   return check_launch("attn_bwd_prep");
 }
 

@@ -68,13 +68,22 @@ __global__ void table_op_k(const float* __restrict__ a, const float* __restrict_
   }
 }
 
-// GEGLU backward on the tile-interleaved layout ([64 value | 64 gate] per 128 columns)
-__global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ vg, __nv_bfloat16* __restrict__ dvg, long long M, int Ip) {
+// GEGLU backward on the tile-interleaved layout ([64 value | 64 gate] per 128 columns), fused with the column sums of
+// d(vg) (= gradient of the FFN-in bias).  A thread owns one 8-column chunk of h (and the matching value / gate chunks)
+// and walks `rpb` rows; its 16 column sums stay in registers and are flushed with one atomicAdd each per block.
+__global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ vg, __nv_bfloat16* __restrict__ dvg, long long M, int Ip,
+                            const int* __restrict__ col_map, float* __restrict__ dbias, int rpb) {
   const int cpr = Ip / 8;                 // 16-byte chunks per row of dh
-  const long long n = M * cpr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cpr; const int c8 = (int)(i - r * cpr) * 8;
-    const int tile = c8 >> 6, j = c8 & 63;
+  const int ch = threadIdx.x;
+  if (ch >= cpr) return;
+  const int c8 = ch * 8;
+  const int tile = c8 >> 6, j = c8 & 63;
+  const long long r0 = (long long)blockIdx.x * rpb, r1 = min(M, r0 + rpb);
+  float sv[8], sg[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sv[e] = 0.f; sg[e] = 0.f; }
+#pragma unroll 2
+  for (long long r = r0; r < r1; ++r) {
     const uint4 d4 = *reinterpret_cast<const uint4*>(dh + r * Ip + c8);
     const __nv_bfloat16* vrow = vg + r * 2 * Ip + tile * 128;
     const uint4 v4 = *reinterpret_cast<const uint4*>(vrow + j);
@@ -92,12 +101,22 @@ __global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfl
         const float pdf = 0.3989422804014327f * __expf(-0.5f * gg[e] * gg[e]);
         o_v[e] = dd[e] * gg[e] * cdf;                       // d value = dh * gelu(g)
         o_g[e] = dd[e] * vv[e] * (cdf + gg[e] * pdf);       // d gate  = dh * value * gelu'(g)
+        sv[2 * k + e] += o_v[e]; sg[2 * k + e] += o_g[e];
       }
       ov[k] = pack2_bf16(o_v[0], o_v[1]); og[k] = pack2_bf16(o_g[0], o_g[1]);
     }
     __nv_bfloat16* orow = dvg + r * 2 * Ip + tile * 128;
     *reinterpret_cast<uint4*>(orow + j) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
     *reinterpret_cast<uint4*>(orow + 64 + j) = make_uint4(og[0], og[1], og[2], og[3]);
+  }
+  if (dbias) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int cv = tile * 128 + j + e, cg = cv + 64;
+      const int ov_ = col_map ? col_map[cv] : cv, og_ = col_map ? col_map[cg] : cg;
+      if (ov_ >= 0) atomicAdd(dbias + ov_, sv[e]);
+      if (og_ >= 0) atomicAdd(dbias + og_, sg[e]);
+    }
   }
 }
 
@@ -205,6 +224,48 @@ __global__ void cast_pack_k(const float* __restrict__ src, long long ld_src, int
   }
 }
 
+// All per-step weight repacks in ONE launch: job j copies/casts a [R_dst x C_dst] destination from an fp32 source with an
+// optional row gather; `blk_job[b]` maps a block to its job and `blk_first[j]` is the first block of job j.
+__global__ void cast_pack_multi_k(const TfxPackJob* __restrict__ jobs, const int* __restrict__ blk_job, const int* __restrict__ blk_first) {
+  const int j = blk_job[blockIdx.x];
+  const TfxPackJob jb = jobs[j];
+  const long long local = (long long)(blockIdx.x - blk_first[j]) * 2048;
+  const long long n = jb.R_dst * (long long)jb.C_dst;
+  const bool vec = (jb.C_dst & 7) == 0 && (jb.C_src & 3) == 0 && (jb.ld_src & 3) == 0 && !jb.dst_f32 &&
+                   ((reinterpret_cast<uintptr_t>(jb.src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(jb.dst) & 15) == 0);
+  if (vec) {
+    const long long i = local + (long long)threadIdx.x * 8;
+    if (i >= n) return;
+    const long long r = i / jb.C_dst; const int c = (int)(i - r * jb.C_dst);
+    const long long sr = jb.row_src ? jb.row_src[r] : r;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (sr >= 0) {
+      const float* sp = jb.src + sr * jb.ld_src + c;
+      if (c + 8 <= jb.C_src) {
+        const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (c + e < jb.C_src) v[e] = sp[e];
+      }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(jb.dst) + i) = make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
+  } else {
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) {
+      const long long i = local + e * 256 + threadIdx.x;
+      if (i >= n) break;
+      const long long r = i / jb.C_dst; const int c = (int)(i - r * jb.C_dst);
+      const long long sr = jb.row_src ? jb.row_src[r] : r;
+      float v = 0.f;
+      if (sr >= 0 && c < jb.C_src) v = jb.src[sr * jb.ld_src + c];
+      if (jb.dst_f32) reinterpret_cast<float*>(jb.dst)[i] = v; else reinterpret_cast<__nv_bfloat16*>(jb.dst)[i] = __float2bfloat16(v);
+    }
+  }
+}
+
 __global__ void cast_f32_bf16_k(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = __float2bfloat16(src[i]);
 }
@@ -239,8 +300,8 @@ __global__ void rope_table_k(const float* __restrict__ freqs, float2* __restrict
 }
 
 // fused Adam(W): torch.optim.Adam semantics (L2 weight decay folded into the gradient unless decoupled)
-__global__ void adam_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr, float b1, float b2,
-                       float eps, float wd, int decoupled, float bc1, float bc2_sqrt, float gscale) {
+__global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr, float b1, float b2,
+                       float eps, float wd, int decoupled, float bc1, float bc2_sqrt, float gscale, int zero_grads) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * gscale, pi = p[i];
     if (wd != 0.f) { if (decoupled) pi *= (1.f - lr * wd); else gi += wd * pi; }
@@ -249,6 +310,7 @@ __global__ void adam_k(float* __restrict__ p, const float* __restrict__ g, float
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = pi - (lr / bc1) * (mi / denom);
+    if (zero_grads) g[i] = 0.f;
   }
 }
 
@@ -279,10 +341,13 @@ int tfx_table_op(const float* a, long long ld_a, const float* b, long long ld_b,
   return check_launch("table_op");
 }
 
-int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, void* stream) {
+int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, const int* col_map, float* dbias, void* stream) {
   if (M <= 0) return 0;
-  TFX_REQUIRE(inner_pad % 64 == 0, "geglu_bwd: inner_pad %d must be a multiple of 64", inner_pad);
-  geglu_bwd_k<<<ew_grid(M * (inner_pad / 8), 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)dh_bf16, (const __nv_bfloat16*)vg_bf16, (__nv_bfloat16*)dvg_bf16, M, inner_pad);
+  TFX_REQUIRE(inner_pad % 64 == 0 && inner_pad <= 8192, "geglu_bwd: inner_pad %d must be a multiple of 64 and <= 8192", inner_pad);
+  const int threads = ((inner_pad / 8) + 31) / 32 * 32;
+  const int rpb = 64;
+  geglu_bwd_k<<<(unsigned)((M + rpb - 1) / rpb), threads, 0, ST(stream)>>>((const __nv_bfloat16*)dh_bf16, (const __nv_bfloat16*)vg_bf16, (__nv_bfloat16*)dvg_bf16, M, inner_pad,
+                                                                         col_map, dbias, rpb);
   return check_launch("geglu_bwd");
 }
 
@@ -322,6 +387,12 @@ int tfx_cast_pack(const float* src, long long ld_src, int C_src, const int* row_
   return check_launch("cast_pack");
 }
 
+int tfx_cast_pack_multi(const TfxPackJob* jobs_dev, const int* blk_job_dev, const int* blk_first_dev, int n_blocks, void* stream) {
+  if (n_blocks <= 0) return 0;
+  cast_pack_multi_k<<<n_blocks, 256, 0, ST(stream)>>>(jobs_dev, blk_job_dev, blk_first_dev);
+  return check_launch("cast_pack_multi");
+}
+
 int tfx_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream) {
   if (n <= 0) return 0;
   cast_f32_bf16_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(src, (__nv_bfloat16*)dst_bf16, n);
@@ -353,12 +424,12 @@ int tfx_rope_table(const float* freqs, float* cos_sin, int max_pos, int n_freqs,
   return check_launch("rope_table");
 }
 
-int tfx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                  int decoupled_wd, int step, float grad_scale, void* stream) {
+int tfx_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int decoupled_wd, int step, float grad_scale, int zero_grads, void* stream) {
   if (n <= 0) return 0;
   TFX_REQUIRE(step >= 1, "adam_step: step must be >= 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  adam_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, bc2s, grad_scale);
+  adam_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, bc2s, grad_scale, zero_grads);
   return check_launch("adam_step");
 }
 

@@ -113,20 +113,38 @@ __global__ void __launch_bounds__(ROW_THREADS) adaln_bwd_k(const float* __restri
 // ------------------------------------------------------------------------------------ branch-output gate backward
 // forward was x_out = x_res + y * s,  s = isM ? sigmoid(z_c) : (layerscale+1)       (T.py:765-769)
 // dy = dx*s (bf16, feeds the dgrad / wgrad GEMMs);  d s accumulated per cond row / for layerscale.
+// block-level column reduction of per-warp register rows, then one atomicAdd per column per block
+template <int NCH>
+__device__ __forceinline__ void block_red_cols(float* smem /*[WARPS_PER_BLOCK][NCH*128]*/, const float (&acc)[NCH * 4], float* __restrict__ dst) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  store_row_f32<NCH>(smem + warp * D, lane, acc);
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += ROW_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS_PER_BLOCK; ++w) t += smem[w * D + c];
+    atomicAdd(dst + c, t);
+  }
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y,
                                                           const int* __restrict__ cond_row, const float* __restrict__ zgate, long long zgate_ld,
                                                           const float* __restrict__ ls, __nv_bfloat16* __restrict__ dy,
-                                                          float* __restrict__ dzgate, long long dzgate_ld, float* __restrict__ dls, int M, int tpw) {
+                                                          float* __restrict__ dzgate, long long dzgate_ld, float* __restrict__ dls,
+                                                          float* __restrict__ dbias, int M, int tpw) {
   constexpr int D = NCH * 128;
+  extern __shared__ float red_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
-  if (r0 >= M) return;
+  const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);
   const bool has_scale = ls != nullptr;
   float lsv[NCH * 4];
   if (has_scale) load_row_f32<NCH>(ls, lane, lsv);
-  float acc[NCH * 4];
+  float acc[NCH * 4], accb[NCH * 4];
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) accb[i] = 0.f;
   int cur = -2;
   auto flush = [&]() {
     if (cur == -2 || !has_scale) return;
@@ -152,9 +170,12 @@ __global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restri
         d[i] *= s;
       }
     }
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) accb[i] += d[i];
     store_row_bf16<NCH>(dy + (long long)row * D, lane, d);
   }
   flush();
+  if (dbias) block_red_cols<NCH>(red_smem, accb, dbias);     // uniform branch: every thread of the block reaches the barrier
 }
 
 // ------------------------------------------------------------------------------------ AttentionResidual forward
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
 // dh_l += alpha_l*dx + dsim_l*(w/|h| - <h,w> h/|h|^3);   dw += dsim_l*h/|h|   (dw -> d gamma, d pq)
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) attn_res_bwd_k(PtrList hid, PtrList dhid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
-                                                             const float* __restrict__ dxo, float* __restrict__ dgamma, float* __restrict__ dpq, int M, int tpw) {
+                                                             const float* __restrict__ dxo, float* __restrict__ dgamma, float* __restrict__ dpq, int M, int tpw, int init) {
   constexpr int D = NCH * 128;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -240,7 +261,11 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_bwd_k(PtrList hid, PtrLi
       const float rn = 1.f / nrm, c2 = ds * dot * rn * rn * rn, c1 = ds * rn;
       float h[NCH * 4], g[NCH * 4];
       load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
-      load_row_f32<NCH>(dhid.p[k] + (long long)row * D, lane, g);
+      if (!init) load_row_f32<NCH>(dhid.p[k] + (long long)row * D, lane, g);
+      else {
+#pragma unroll
+        for (int i = 0; i < NCH * 4; ++i) g[i] = 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) {
         g[i] += a * dxv[i] + c1 * w[i] - c2 * h[i];
@@ -373,40 +398,71 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_add_rows_k(float* __restr
 
 // ------------------------------------------------------------------------------------ qk RMSNorm + RoPE backward, packs d[q|k|.|gates]
 // forward (GEMM epilogue): xhat = x*inv;  y = xhat*8*(gamma+1);  q = R(pos) y (interleaved pairs)   (T.py:950-965)
-// One warp per token, lane i owns the rope pair (2i, 2i+1) of every head.
+// One warp per token; 8 lanes share a head (lane owns 8 consecutive dims = 4 rope pairs: 32 B fp32 / 16 B bf16 accesses),
+// so a warp covers 4 heads per pass and the per-head dot product is a 3-step shuffle.
 __global__ void __launch_bounds__(ROW_THREADS) qk_bwd_pack_k(const float* __restrict__ dq, const float* __restrict__ dk, const __nv_bfloat16* __restrict__ q,
                                                             const __nv_bfloat16* __restrict__ k, const float* __restrict__ qk_inv, const float* __restrict__ gq,
                                                             const float* __restrict__ gk, const int* __restrict__ rope_pos, const float2* __restrict__ rope_cs,
                                                             const float* __restrict__ gates, const float* __restrict__ dsum, __nv_bfloat16* __restrict__ out,
                                                             long long out_ld, float* __restrict__ dgq, float* __restrict__ dgk, int M, int H, int tpw) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float red[WARPS_PER_BLOCK][128];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int sub = lane & 7, hq = lane >> 3;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
-  if (r0 >= M) return;
+  const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);
   const int HI = H * 64;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  const float g1[2][2] = {{gq[2 * lane] + 1.f, gq[2 * lane + 1] + 1.f}, {gk[2 * lane] + 1.f, gk[2 * lane + 1] + 1.f}};
+  float acc[2][8];
+  float g1[2][8], rg[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[0][j] = acc[1][j] = 0.f;
+    g1[0][j] = gq[sub * 8 + j] + 1.f; g1[1][j] = gk[sub * 8 + j] + 1.f;
+    rg[0][j] = fabsf(g1[0][j]) > 1e-12f ? 1.f / (8.f * g1[0][j]) : 0.f;
+    rg[1][j] = fabsf(g1[1][j]) > 1e-12f ? 1.f / (8.f * g1[1][j]) : 0.f;
+  }
   for (int row = r0; row < r1; ++row) {
-    const float2 cs = rope_cs[(long long)rope_pos[row] * 32 + lane];
+    float cs[8];   // (cos, sin) of the lane's 4 rope pairs
+    {
+      const float4* cp = reinterpret_cast<const float4*>(rope_cs + (long long)rope_pos[row] * 32 + sub * 4);
+      const float4 c0 = cp[0], c1 = cp[1];
+      cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+    }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const float* dsrc = which == 0 ? dq : dk;
       const __nv_bfloat16* src = which == 0 ? q : k;
-      for (int h = 0; h < H; ++h) {
-        const long long off = (long long)row * HI + h * 64 + 2 * lane;
-        const float2 dr = *reinterpret_cast<const float2*>(dsrc + off);
-        const float2 r = unpack2_bf16(*reinterpret_cast<const uint32_t*>(src + off));
-        const float inv = qk_inv[(long long)row * 2 * H + which * H + h];
-        // un-rotate (R^T)
-        const float y0 = r.x * cs.x + r.y * cs.y, y1 = r.y * cs.x - r.x * cs.y;
-        const float dy0 = dr.x * cs.x + dr.y * cs.y, dy1 = dr.y * cs.x - dr.x * cs.y;
-        const float ga = g1[which][0], gb = g1[which][1];
-        const float xh0 = fabsf(ga) > 1e-12f ? y0 / (8.f * ga) : 0.f, xh1 = fabsf(gb) > 1e-12f ? y1 / (8.f * gb) : 0.f;
-        acc[which][0] += dy0 * xh0 * 8.f; acc[which][1] += dy1 * xh1 * 8.f;
-        const float dxh0 = dy0 * 8.f * ga, dxh1 = dy1 * 8.f * gb;
-        const float dot = warp_sum(xh0 * dxh0 + xh1 * dxh1);
-        const float o0 = inv * (dxh0 - xh0 * dot), o1 = inv * (dxh1 - xh1 * dot);
-        *reinterpret_cast<uint32_t*>(out + (long long)row * out_ld + which * HI + h * 64 + 2 * lane) = pack2_bf16(o0, o1);
+      for (int h0 = 0; h0 < H; h0 += 4) {
+        const int h = h0 + hq;
+        const bool act = h < H;
+        const long long off = (long long)row * HI + (act ? h : 0) * 64 + sub * 8;
+        float dr[8], r[8];
+        {
+          const float4 a = *reinterpret_cast<const float4*>(dsrc + off), b = *reinterpret_cast<const float4*>(dsrc + off + 4);
+          dr[0] = a.x; dr[1] = a.y; dr[2] = a.z; dr[3] = a.w; dr[4] = b.x; dr[5] = b.y; dr[6] = b.z; dr[7] = b.w;
+          const uint4 t = *reinterpret_cast<const uint4*>(src + off);
+          const float2 p0 = unpack2_bf16(t.x), p1 = unpack2_bf16(t.y), p2 = unpack2_bf16(t.z), p3 = unpack2_bf16(t.w);
+          r[0] = p0.x; r[1] = p0.y; r[2] = p1.x; r[3] = p1.y; r[4] = p2.x; r[5] = p2.y; r[6] = p3.x; r[7] = p3.y;
+        }
+        const float inv = act ? qk_inv[(long long)row * 2 * H + which * H + h] : 0.f;
+        float xh[8], dxh[8], dot = 0.f;
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+          const float c = cs[2 * pr], sn = cs[2 * pr + 1];
+          // un-rotate (R^T)
+          const float y0 = r[2 * pr] * c + r[2 * pr + 1] * sn, y1 = r[2 * pr + 1] * c - r[2 * pr] * sn;
+          const float dy0 = dr[2 * pr] * c + dr[2 * pr + 1] * sn, dy1 = dr[2 * pr + 1] * c - dr[2 * pr] * sn;
+          xh[2 * pr] = y0 * rg[which][2 * pr]; xh[2 * pr + 1] = y1 * rg[which][2 * pr + 1];
+          dxh[2 * pr] = dy0 * 8.f * g1[which][2 * pr]; dxh[2 * pr + 1] = dy1 * 8.f * g1[which][2 * pr + 1];
+          if (act) { acc[which][2 * pr] += dy0 * xh[2 * pr] * 8.f; acc[which][2 * pr + 1] += dy1 * xh[2 * pr + 1] * 8.f; }
+          dot += xh[2 * pr] * dxh[2 * pr] + xh[2 * pr + 1] * dxh[2 * pr + 1];
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1); dot += __shfl_xor_sync(0xffffffffu, dot, 2); dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        if (act) {
+          uint32_t w[4];
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) w[pr] = pack2_bf16(inv * (dxh[2 * pr] - xh[2 * pr] * dot), inv * (dxh[2 * pr + 1] - xh[2 * pr + 1] * dot));
+          *reinterpret_cast<uint4*>(out + (long long)row * out_ld + which * HI + h * 64 + sub * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
     // gate logits: d g = (1 - sigmoid(g)) * sum_d dO_gated * O_gated
@@ -416,8 +472,22 @@ __global__ void __launch_bounds__(ROW_THREADS) qk_bwd_pack_k(const float* __rest
       out[(long long)row * out_ld + 3 * HI + lane] = __float2bfloat16((1.f - sg) * dsum[(long long)row * H + lane]);
     }
   }
-  atomicAdd(dgq + 2 * lane, acc[0][0]); atomicAdd(dgq + 2 * lane + 1, acc[0][1]);
-  atomicAdd(dgk + 2 * lane, acc[1][0]); atomicAdd(dgk + 2 * lane + 1, acc[1][1]);
+  // gamma gradients: reduce the 4 head-groups of the warp, then the 8 warps of the block, then one atomic per column per block
+#pragma unroll
+  for (int which = 0; which < 2; ++which)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[which][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (hq == 0) red[wib][which * 64 + sub * 8 + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS_PER_BLOCK; ++w) t += red[w][threadIdx.x];
+    atomicAdd((threadIdx.x < 64 ? dgq : dgk) + (threadIdx.x & 63), t);
+  }
 }
 
 static inline int row_grid(int M, int sms) {
@@ -454,11 +524,12 @@ int tfx_adaln_bwd(const float* du, const float* x, const float* stats, const int
 }
 
 int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, const float* zgate, long long zgate_ld, const float* layerscale,
-                  void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, int M, int D, void* stream) {
+                  void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, float* dbias, int M, int D, void* stream) {
   if (M <= 0) return 0;
   const int tpw = 16;
-  TFX_DISPATCH_NCH(D, (resid_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(dx, (const __nv_bfloat16*)y_bf16, cond_row, zgate, zgate_ld, layerscale,
-                                                                                              (__nv_bfloat16*)dy_bf16, dzgate, dzgate_ld, dlayerscale, M, tpw)));
+  const size_t smem = dbias ? (size_t)WARPS_PER_BLOCK * D * sizeof(float) : 0;
+  TFX_DISPATCH_NCH(D, (resid_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, smem, ST(stream)>>>(dx, (const __nv_bfloat16*)y_bf16, cond_row, zgate, zgate_ld, layerscale,
+                                                                                                 (__nv_bfloat16*)dy_bf16, dzgate, dzgate_ld, dlayerscale, dbias, M, tpw)));
   return check_launch("resid_bwd");
 }
 
@@ -473,13 +544,13 @@ int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const floa
 }
 
 int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          const float* dx_out, float* dgamma, float* dpseudo_query, int M, int D, void* stream) {
+                          const float* dx_out, float* dgamma, float* dpseudo_query, int M, int D, int init, void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
   PtrList pl, dl;
   for (int i = 0; i < n_hiddens; ++i) { pl.p[i] = const_cast<float*>(hiddens[i]); dl.p[i] = dhiddens[i]; }
   const int tpw = 8;
-  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, dgamma, dpseudo_query, M, tpw)));
+  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, dgamma, dpseudo_query, M, tpw, init)));
   return check_launch("attn_residual_bwd");
 }
 
@@ -519,7 +590,7 @@ int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const 
                     float* dq_gamma, float* dk_gamma, int M, int H, void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(H >= 1 && H <= 32, "qk_bwd_pack: heads %d out of range", H);
-  const int tpw = 16;
+  const int tpw = 8;
   qk_bwd_pack_k<<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(dq, dk, (const __nv_bfloat16*)q_bf16, (const __nv_bfloat16*)k_bf16, qk_inv, q_gamma, k_gamma, rope_pos,
                                                                      (const float2*)rope_cs, gates, dsum, (__nv_bfloat16*)dqkvg_bf16, out_ld, dq_gamma, dk_gamma, M, H, tpw);
   return check_launch("qk_bwd_pack");

@@ -81,7 +81,7 @@ class DataParallelTrainer:
                     for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
                         g.copy_(f)
         if cuda:
-            eng.adam_step(grad_scale = 1.0 / self.world, **self.hp)
+            eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, **self.hp)     # next step's zero_grad() is free
         else:
             if self._cpu_opt is None:
                 cls = torch.optim.AdamW if self.hp['decoupled'] else torch.optim.Adam

@@ -167,48 +167,67 @@ class Engine:
                 t.zero_()
         return t[:n].view(shape)
 
-    def pack_weights(self):
-        """fp32 master parameters -> bf16 GEMM operands in kernel layouts (once per optimizer step)."""
-        if not self._dirty and self._packed_version == self.flat._version:
-            return
-        o, D, HI, H, Ip, inner = self.ops, self.D, self.HI, self.H, self.Ip, self.inner
-        pk = self.packed = getattr(self, 'packed', {})
-        def dst(name, rows, cols):
-            t = pk.get(name)
-            if t is None:
-                t = pk[name] = torch.zeros(rows, cols, device = self.device, dtype = BF16)
+    def _build_pack_jobs(self):
+        """Destination buffers + the device-resident job table of `tfx_cast_pack_multi` (built once per attach)."""
+        D, HI, H, Ip, inner = self.D, self.HI, self.H, self.Ip, self.inner
+        pk = self.packed = {}
+        jobs = []
+        def dst(name, rows, cols, dtype = BF16):
+            t = pk[name] = torch.zeros(rows, cols, device = self.device, dtype = dtype) if cols else torch.zeros(rows, device = self.device, dtype = dtype)
             return t
+        def job(src, ld_src, c_src, row_src, d, r_dst, c_dst):
+            jobs.append((src, ld_src, c_src, row_src, d, r_dst, c_dst, 1 if d.dtype == F32 else 0))
         for i in range(self.depth):
             pre = f'transformer.layers.{i}'
             wq = dst(f'qkvg{i}', self.NQ, D)
-            o.cast_pack(self.P(f'{pre}.1.fn.to_qk.0.weight'), D, D, None, wq, 2 * HI, D)
-            o.cast_pack(self.P(f'{pre}.1.fn.to_v.0.weight'), D, D, None, wq[2 * HI:], HI, D)
-            o.cast_pack(self.P(f'{pre}.1.fn.to_gates.0.weight'), D, D, None, wq[3 * HI:], H, D)
-            o.cast_pack(self.P(f'{pre}.1.fn.to_out.1.weight'), HI, HI, None, dst(f'wo{i}', D, HI), D, HI)
-            o.cast_pack(self.P(f'{pre}.2.fn.net.0.weight'), D, D, self.w1_row_src, dst(f'w1{i}', 2 * Ip, D), 2 * Ip, D)
-            o.cast_pack(self.P(f'{pre}.2.fn.net.3.weight'), inner, inner, None, dst(f'w2{i}', D, Ip), D, Ip)
-            b1 = self.P(f'{pre}.2.fn.net.0.bias')
-            pk[f'b1{i}'] = torch.where(self.w1_row_src64 >= 0, b1[self.w1_row_src64.clamp(min = 0)], torch.zeros((), device = self.device))
+            job(self.P(f'{pre}.1.fn.to_qk.0.weight'), D, D, None, wq, 2 * HI, D)
+            job(self.P(f'{pre}.1.fn.to_v.0.weight'), D, D, None, wq[2 * HI:], HI, D)
+            job(self.P(f'{pre}.1.fn.to_gates.0.weight'), D, D, None, wq[3 * HI:], H, D)
+            job(self.P(f'{pre}.1.fn.to_out.1.weight'), HI, HI, None, dst(f'wo{i}', D, HI), D, HI)
+            job(self.P(f'{pre}.2.fn.net.0.weight'), D, D, self.w1_row_src, dst(f'w1{i}', 2 * Ip, D), 2 * Ip, D)
+            job(self.P(f'{pre}.2.fn.net.3.weight'), inner, inner, None, dst(f'w2{i}', D, Ip), D, Ip)
+            job(self.P(f'{pre}.2.fn.net.0.bias'), 1, 1, self.w1_row_src, dst(f'b1{i}', 2 * Ip, 0, F32), 2 * Ip, 1)
             if f'{pre}.0.weight' in self.named:
-                o.cast_pack(self.P(f'{pre}.0.weight'), 2 * D, 2 * D, None, dst(f'wskip{i}', D, 2 * D), D, 2 * D)
-        m = self.model
-        o.cast_pack(self.P('to_text_logits.weight'), D, D, None, dst('wvocab', self.V, D), self.V, D)
+                job(self.P(f'{pre}.0.weight'), 2 * D, 2 * D, None, dst(f'wskip{i}', D, 2 * D), D, 2 * D)
+        job(self.P('to_text_logits.weight'), D, D, None, dst('wvocab', self.V, D), self.V, D)
         for t, (dl, dlp) in enumerate(zip(self.dls, self.dlp)):
-            o.cast_pack(self.P(f'model_to_latent_projs.{t}.weight'), D, D, None, dst(f'wm2l{t}', dl, D), dl, D)
+            job(self.P(f'model_to_latent_projs.{t}.weight'), D, D, None, dst(f'wm2l{t}', dl, D), dl, D)
             if f'latent_to_model_projs.{t}.weight' in self.named:
-                o.cast_pack(self.P(f'latent_to_model_projs.{t}.weight'), dl, dl, None, dst(f'wl2m{t}', D, dlp), D, dlp)
-        o.cast_pack(self.P('transformer.to_time_cond.1.weight'), D + 1, D + 1, None, dst('wt', 4 * D, self.Kt), 4 * D, self.Kt)
+                job(self.P(f'latent_to_model_projs.{t}.weight'), dl, dl, None, dst(f'wl2m{t}', D, dlp), D, dlp)
+        job(self.P('transformer.to_time_cond.1.weight'), D + 1, D + 1, None, dst('wt', 4 * D, self.Kt), 4 * D, self.Kt)
         wfz = dst('wfz', self.W * 3 * D, 4 * D)
-        bfz = pk.get('bfz')
-        if bfz is None:
-            bfz = pk['bfz'] = torch.empty(self.W * 3 * D, device = self.device, dtype = F32)
+        bfz = dst('bfz', self.W * 3 * D, 0, F32)
         for w in range(self.W):
             i, j = divmod(w, 2)
             pre = f'transformer.layers.{i}.{j + 1}'
-            o.cast_pack(self.P(f'{pre}.to_film.weight'), 4 * D, 4 * D, None, wfz[w * 3 * D:], 2 * D, 4 * D)
-            o.cast_pack(self.P(f'{pre}.to_ada_ln_zero.weight'), 4 * D, 4 * D, None, wfz[w * 3 * D + 2 * D:], D, 4 * D)
-            bfz[w * 3 * D: w * 3 * D + 2 * D].copy_(self.P(f'{pre}.to_film.bias'))
-            bfz[w * 3 * D + 2 * D: (w + 1) * 3 * D].copy_(self.P(f'{pre}.to_ada_ln_zero.bias'))
+            job(self.P(f'{pre}.to_film.weight'), 4 * D, 4 * D, None, wfz[w * 3 * D:], 2 * D, 4 * D)
+            job(self.P(f'{pre}.to_ada_ln_zero.weight'), 4 * D, 4 * D, None, wfz[w * 3 * D + 2 * D:], D, 4 * D)
+            job(self.P(f'{pre}.to_film.bias'), 2 * D, 2 * D, None, bfz[w * 3 * D:], 1, 2 * D)
+            job(self.P(f'{pre}.to_ada_ln_zero.bias'), D, D, None, bfz[w * 3 * D + 2 * D:], 1, D)
+        # struct TfxPackJob (include/tfx_b200.h): 56 bytes
+        dt = np.dtype([('src', '<u8'), ('ld_src', '<i8'), ('row_src', '<u8'), ('dst', '<u8'), ('R_dst', '<i8'), ('C_src', '<i4'), ('C_dst', '<i4'),
+                       ('dst_f32', '<i4'), ('pad', '<i4')])
+        assert dt.itemsize == 56
+        tab = np.zeros(len(jobs), dtype = dt)
+        blk_job, blk_first = [], []
+        for j, (src, ld_src, c_src, row_src, d, r_dst, c_dst, f32) in enumerate(jobs):
+            tab[j] = (src.data_ptr(), ld_src, row_src.data_ptr() if row_src is not None else 0, d.data_ptr(), r_dst, c_src, c_dst, f32, 0)
+            nb = (r_dst * c_dst + 2047) // 2048
+            blk_first.append(len(blk_job))
+            blk_job.extend([j] * nb)
+        self._pack_tab = torch.from_numpy(tab.view(np.uint8).copy()).to(self.device)
+        self._pack_blk_job = torch.tensor(blk_job, dtype = I32, device = self.device)
+        self._pack_blk_first = torch.tensor(blk_first, dtype = I32, device = self.device)
+        self._pack_nblocks = len(blk_job)
+        self._pack_ptr = self._first_ptr
+
+    def pack_weights(self):
+        """fp32 master parameters -> bf16 GEMM operands in kernel layouts: ONE launch per optimizer step."""
+        if not self._dirty and self._packed_version == self.flat._version:
+            return
+        if getattr(self, '_pack_ptr', None) != self._first_ptr:
+            self._build_pack_jobs()
+        self.ops.cast_pack_multi(self._pack_tab, self._pack_blk_job, self._pack_blk_first, self._pack_nblocks)
         self._dirty = False
         self._packed_version = self.flat._version
 
@@ -468,6 +487,7 @@ class Engine:
         st = self.state
         assert st['train'], 'backward() needs a train forward'
         self._prepare_grads()
+        self._grads_clean = False
         if gscale is not None:
             gs = gscale.detach().float().reshape(1)
             self.ops.scale_bf16(st['dlogits'], gs, st['dlogits'].numel())
@@ -510,9 +530,7 @@ class Engine:
 
         # ---- block stack, reverse
         hid = st['hid']
-        dH = [self.buf(f'dH{l}', (M, D), F32) for l in range(self.depth + 1)]
-        for t in dH:
-            t.zero_()
+        dH = [self.buf(f'dH{l}', (M, D), F32) for l in range(self.depth + 1)]     # first touched (overwritten) by the last layer's attn_residual_bwd
         dskip = {}
         if nc > 0:
             dtab = self.buf('dtab', (nc, self.W * 3 * D), F32); dtab.zero_()
@@ -525,34 +543,32 @@ class Engine:
             lm = self.layer_maps[i]
             wA, wF = 2 * i, 2 * i + 1
             o.attn_residual_bwd(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
-                                g, self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), M, D)
+                                g, self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), M, D, 1 if i == self.depth - 1 else 0)
             gx = dH[i + 1]                       # complete gradient w.r.t. x_c of this layer; updated in place below
             # -- feed-forward branch
             o.resid_bwd(gx, L['yF'], cond_row, st['zg'][:, wF * D:] if nc > 0 else None, zg_ld, self.P(f'{pre}.2.layerscale'), dy,
-                        dzg[:, wF * D:] if nc > 0 else None, zg_ld, self.G(f'{pre}.2.layerscale'), M, D)
+                        dzg[:, wF * D:] if nc > 0 else None, zg_ld, self.G(f'{pre}.2.layerscale'), self.G(f'{pre}.2.fn.net.3.bias'), M, D)
             dh = self.buf('dh', (M, Ip), BF16)
             o.gemm_store(dy, D, 0, pk[f'w2{i}'], Ip, 1, M, Ip, D, None, 0, dh, Ip, None, None, 1.0, 0, 1)
             o.gemm_store(dy, D, 1, L['h'], Ip, 1, D, inner, M, self.gflat, 0, None, 0, None, lm['w2_rows'], 1.0, 1, ks)
-            o.colsum_bf16(dy, D, M, D, None, self.G(f'{pre}.2.fn.net.3.bias'))
             dvg = self.buf('dvg', (M, 2 * Ip), BF16)
-            o.geglu_bwd(dh, L['vg'], dvg, M, Ip)
+            o.geglu_bwd(dh, L['vg'], dvg, M, Ip, lm['b1_cols'], self.gflat)
             o.gemm_store(dvg, 2 * Ip, 0, pk[f'w1{i}'], D, 1, M, D, 2 * Ip, du, D, None, 0, None, None, 1.0, 0, 1)
             o.gemm_store(dvg, 2 * Ip, 1, L['uF'], D, 1, 2 * Ip, D, M, self.gflat, 0, None, 0, None, lm['w1_rows'], 1.0, 1, ks)
-            o.colsum_bf16(dvg, 2 * Ip, M, 2 * Ip, lm['b1_cols'], self.gflat)
             o.adaln_bwd(du, L['x_b'], L['statsF'], cond_row, st['tab'][:, wF * 3 * D:] if nc > 0 else None, tab_ld, self.P(f'{pre}.2.layernorm_gamma'), gx,
                         dtab[:, wF * 3 * D:] if nc > 0 else None, tab_ld, self.G(f'{pre}.2.layernorm_gamma'), M, D)
             # -- attention branch
             o.resid_bwd(gx, L['yA'], cond_row, st['zg'][:, wA * D:] if nc > 0 else None, zg_ld, self.P(f'{pre}.1.layerscale'), dy,
-                        dzg[:, wA * D:] if nc > 0 else None, zg_ld, self.G(f'{pre}.1.layerscale'), M, D)
+                        dzg[:, wA * D:] if nc > 0 else None, zg_ld, self.G(f'{pre}.1.layerscale'), None, M, D)
             dog = self.buf('dog', (M, HI), BF16)
             o.gemm_store(dy, D, 0, pk[f'wo{i}'], HI, 1, M, HI, D, None, 0, dog, HI, None, None, 1.0, 0, 1)
             wgrad(dy, D, D, L['att'], HI, HI, f'{pre}.1.fn.to_out.1.weight')
             dop = self.buf('dop', (M, HI), BF16); dsum_hm = self.buf('dsum_hm', (H, M), F32); dsum_mh = self.buf('dsum_mh', (M, H), F32)
-            o.attn_bwd_prep(dog, L['att'], L['gates'], dop, dsum_hm, dsum_mh, M, H)
             dq = self.buf('dq', (M, HI), F32); dk = self.buf('dk', (M, HI), F32)
-            dq.zero_()
+            o.attn_bwd_prep(dog, L['att'], L['gates'], dop, dsum_hm, dsum_mh, dq, M, H)
             dqkvg = self.buf('dqkvg', (M, self.NQ), BF16)
-            dqkvg[:, 3 * HI + H:].zero_()
+            if self.ws.get('dqkvg_shape') != (M, self.NQ):          # pad columns are never written by the kernels: clear once per shape
+                dqkvg.zero_(); self.ws['dqkvg_shape'] = (M, self.NQ)
             o.attn_bwd(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['kt_kv0'], dv['kt_kvend'], dv['kt_q0'], dv['kt_qend'],
                        int(rb.kt_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap)
             o.qk_bwd_pack(dq, dk, L['q'], L['k'], L['qk_inv'], self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'), dv['rope_pos'],
@@ -563,7 +579,7 @@ class Engine:
                         dtab[:, wA * 3 * D:] if nc > 0 else None, tab_ld, self.G(f'{pre}.1.layernorm_gamma'), M, D)
             # -- U-Net skip projection: x_a = x_in + W_skip [x_in | skip]
             if L['has_skip']:
-                o.resid_bwd(gx, None, None, None, 0, None, dy, None, 0, None, M, D)
+                o.resid_bwd(gx, None, None, None, 0, None, dy, None, 0, None, None, M, D)
                 wsk = pk[f'wskip{i}']
                 gw = self.G(f'{pre}.0.weight')
                 o.gemm_store(dy, D, 1, L['x_in_b'], D, 1, D, D, M, gw, 2 * D, None, 0, None, None, 1.0, 1, ks)
@@ -611,12 +627,16 @@ class Engine:
 
     # ------------------------------------------------------------------ optimizer
     def zero_grad(self):
-        self.gflat.zero_()
+        if not getattr(self, '_grads_clean', False):
+            self.gflat.zero_()
+        self._grads_clean = False       # whoever asked for clean gradients is about to write them
 
-    def adam_step(self, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled = False, grad_scale = 1.0):
+    def adam_step(self, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled = False, grad_scale = 1.0, zero_grads = False):
+        """zero_grads: clear the flat gradient buffer in the same pass (saves a separate fill); the next `zero_grad()` is then free."""
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.flat); self.exp_avg_sq = torch.zeros_like(self.flat)
         self.opt_step += 1
         self.ops.adam_step(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.flat.numel(), lr, betas[0], betas[1], eps, weight_decay, int(decoupled),
-                           self.opt_step, grad_scale)
+                           self.opt_step, grad_scale, int(zero_grads))
+        self._grads_clean = bool(zero_grads)
         self._dirty = True

@@ -131,10 +131,14 @@ def family_model(name, args_, eng, rb):
         M, K = a[5], a[7]
         return 'gemm(tcgen05)', 2.0 * M * 2 * eng.inner * K, 0
     pairs = float(((rb.kv_limit.astype('int64') - (rb.cu[:-1].repeat(rb.seq_lens))) + 1).sum())
-    if name == 'attn_fwd':
+    if name == 'attn_fwd_tc':
         return 'attention', 4.0 * pairs * 64 * eng.H, 0
-    if name == 'attn_bwd':
+    if name == 'attn_fwd':
+        return 'attention', 0, 0          # general kernel: returns at once when the tcgen05 path is active (flops credited to attn_fwd_tc)
+    if name == 'attn_bwd_tc':
         return 'attention', 10.0 * pairs * 64 * eng.H, 0
+    if name == 'attn_bwd':
+        return 'attention', 0, 0
     return 'hbm-bound rows/elementwise', 0, 0
 
 

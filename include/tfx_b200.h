@@ -60,12 +60,26 @@ int tfx_gemm_geglu(const void* u, long long ldu, const void* W1p, long long ldw,
  * Tile tables (host-built, 64-row tiles that never straddle a sequence): forward per query tile, backward per key tile. */
 int tfx_attn_fwd(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
                  const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
-                 void* o, long long ld_o, float* lse, int M, float scale, float softcap, void* stream);
+                 void* o, long long ld_o, float* lse, int M, float scale, float softcap, const float* skip_if_fast /* optional, see below */, void* stream);
+/* Bounded-logit fast path on tcgen05 / TMEM / TMA (128-row tiles).  q, k are RMS-normalised (T.py:950-952), so the soft-cap argument is
+ * bounded by the two gamma vectors; tfx_attn_fast_params writes params[0] = 1 when |s/cap| <= 0.75 is guaranteed (polynomial tanh on the
+ * FMA pipe, fixed softmax maximum params[1], output accumulator untouched in TMEM).  Host code enqueues BOTH tfx_attn_fwd_tc(params) and
+ * tfx_attn_fwd(skip_if_fast = params); the kernel whose precondition fails returns at once - no host synchronisation. */
+int tfx_attn_fast_params(const float* q_gamma, const float* k_gamma, int dim_head, float scale, float softcap, float* params /* [>=2] device */, void* stream);
+int tfx_attn_fwd_tc(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
+                    const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
+                    void* o, long long ld_o, float* lse, int M, float scale, float softcap, const float* fast_params, void* stream);
 /* dq_zero (optional): fp32 [M][H*64] accumulator of tfx_attn_bwd, cleared here in the same pass */
 int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, float* dq_zero, int M, int H, void* stream);
 int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
                  const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
-                 int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, void* stream);
+                 int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* skip_if_fast /* optional */,
+                 void* stream);
+/* bounded-logit backward on tcgen05: 128-key tiles (k2_* tables), S / dP / dV / dK / dQ accumulators in TMEM, dQ leaves through a TMA reduce-add.
+ * Same dual-launch protocol as the forward (fast_params from tfx_attn_fast_params; dq must be zero on entry, see tfx_attn_bwd_prep). */
+int tfx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
+                    const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
+                    int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* fast_params, void* stream);
 /* backward of the qk-RMSNorm + RoPE epilogue; packs d[q | k | (v written by attn_bwd) | gates] bf16 [M][out_ld] */
 int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const void* k_bf16, const float* qk_inv, const float* q_gamma, const float* k_gamma,
                     const int* rope_pos, const float* rope_cs, const float* gates, const float* dsum_mh, void* dqkvg_bf16, long long out_ld,

@@ -87,7 +87,7 @@ def test_attention_forward_backward_vs_dense(ops, lens, spans):
     dev = lambda a: torch.from_numpy(a).cuda()
     kvl = dev(rb.kv_limit)
     o = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16); lse = torch.zeros(H, M, device = 'cuda')
-    ops.attn_fwd(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, dev(rb.tile_q0), dev(rb.tile_qend), dev(rb.tile_kv0), dev(rb.tile_kvend), len(rb.tile_q0), o, H * 64, lse, M, scale, cap)
+    ops.attn_fwd(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, dev(rb.tile_q0), dev(rb.tile_qend), dev(rb.tile_kv0), dev(rb.tile_kvend), len(rb.tile_q0), o, H * 64, lse, M, scale, cap, None)
     qf, kf, vf, gf = (t.float().requires_grad_(True) for t in (q, k, v, gates))
     ref = dense_attention(qf, kf, vf, gf, kvl.long(), rb.cu.tolist(), scale, cap)
     torch.cuda.synchronize()
@@ -98,7 +98,7 @@ def test_attention_forward_backward_vs_dense(ops, lens, spans):
     ops.attn_bwd_prep(do, o, gates, dop, dsum, dsum2, None, M, H)
     dq = torch.zeros(M, H * 64, device = 'cuda'); dk = torch.zeros(M, H * 64, device = 'cuda'); dv = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
     ops.attn_bwd(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.kt_kv0), dev(rb.kt_kvend), dev(rb.kt_q0), dev(rb.kt_qend), len(rb.kt_kv0), dq, dk, dv, H * 64,
-                 M, H, scale, cap)
+                 M, H, scale, cap, None)
     torch.cuda.synchronize()
     for ours, want, name in ((dq, qf.grad, 'dq'), (dk, kf.grad, 'dk'), (dv.float(), vf.grad, 'dv')):
         err = (ours - want).abs().max().item() / want.abs().max().item()
@@ -106,6 +106,66 @@ def test_attention_forward_backward_vs_dense(ops, lens, spans):
     dgate_ref = gf.grad
     dgate = (1 - torch.sigmoid(gates)) * dsum2
     assert (dgate - dgate_ref).abs().max().item() / dgate_ref.abs().max().item() < 4e-2
+
+
+@pytest.mark.parametrize('lens,spans', [([1024, 1024], [(0, 206, 256), (0, 668, 256), (1, 100, 700)]), ([77, 130, 5, 300], [(0, 10, 40), (1, 64, 64), (1, 128, 2), (3, 120, 150)]), ([64], []),
+                                        ([128, 129, 127], [(1, 0, 129)])])
+def test_attention_tcgen05_fast_path_vs_dense(ops, lens, spans):
+    """bounded-logit tcgen05 forward (attention_sm100.cu): RMS-normalised q/k as the QKVG epilogue produces them"""
+    H, cap, scale = 4, 50., 0.125
+    rb = make_rb(lens, spans)
+    M = rb.M
+    g = torch.Generator(device = 'cuda').manual_seed(1)
+    def unit(x):
+        x = x.reshape(M, H, 64)
+        return (torch.nn.functional.normalize(x, dim = -1) * 8.).reshape(M, H * 64).to(BF16)
+    q, k = (unit(torch.randn(M, H * 64, device = 'cuda', generator = g)) for _ in range(2))
+    q[: M // 2] = k[: M // 2]                       # aligned q/k: logits reach the bound (|s| = 8)
+    v = (torch.randn(M, H * 64, device = 'cuda', generator = g) * 2).to(BF16)
+    gates = torch.randn(M, H, device = 'cuda', generator = g)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    kvl = dev(rb.kv_limit)
+    fp = torch.zeros(8, device = 'cuda')
+    zeros = torch.zeros(64, device = 'cuda')
+    ops.attn_fast_params(zeros, zeros, 64, scale, cap, fp)
+    torch.cuda.synchronize()
+    assert fp[0].item() == 1.0 and 8.0 <= fp[1].item() <= 8.2
+    o = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16); lse = torch.zeros(H, M, device = 'cuda')
+    ops.attn_fwd_tc(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, dev(rb.t2_q0), dev(rb.t2_qend), dev(rb.t2_kv0), dev(rb.t2_kvend), len(rb.t2_q0), o, H * 64, lse, M, scale, cap, fp)
+    ref = dense_attention(q.float(), k.float(), v.float(), gates, kvl.long(), rb.cu.tolist(), scale, cap)
+    # the general kernel must skip when the fast flag is set, and agree when run
+    o2 = torch.zeros_like(o); lse2 = torch.zeros_like(lse)
+    ops.attn_fwd(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, dev(rb.tile_q0), dev(rb.tile_qend), dev(rb.tile_kv0), dev(rb.tile_kvend), len(rb.tile_q0), o2, H * 64, lse2, M, scale, cap, fp)
+    torch.cuda.synchronize()
+    assert (o2 == 0).all()
+    ops.attn_fwd(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, dev(rb.tile_q0), dev(rb.tile_qend), dev(rb.tile_kv0), dev(rb.tile_kvend), len(rb.tile_q0), o2, H * 64, lse2, M, scale, cap, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(o.float(), ref, atol = 3e-2, rtol = 3e-2)
+    assert torch.allclose(lse, lse2, atol = 2e-3, rtol = 1e-4)
+    assert torch.allclose(o.float(), o2.float(), atol = 2e-2, rtol = 2e-2)
+    # ---- backward: tcgen05 kernel vs autograd of the dense reference and vs the general kernel
+    qf, kf, vf, gf = (t.float().requires_grad_(True) for t in (q, k, v, gates))
+    ref = dense_attention(qf, kf, vf, gf, kvl.long(), rb.cu.tolist(), scale, cap)
+    do = torch.randn(M, H * 64, device = 'cuda', generator = g).to(BF16)
+    ref.backward(do.float())
+    dop = torch.zeros_like(do); dsum = torch.zeros(H, M, device = 'cuda'); dsum2 = torch.zeros(M, H, device = 'cuda')
+    dq = torch.full((M, H * 64), 7., device = 'cuda')              # cleared by the prep kernel
+    ops.attn_bwd_prep(do, o, gates, dop, dsum, dsum2, dq, M, H)
+    dk = torch.zeros(M, H * 64, device = 'cuda'); dv = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
+    ops.attn_bwd_tc(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.k2_kv0), dev(rb.k2_kvend), dev(rb.k2_q0), dev(rb.k2_qend), len(rb.k2_kv0), dq, dk, dv, H * 64,
+                    M, H, scale, cap, fp)
+    dq2 = torch.zeros(M, H * 64, device = 'cuda'); dk2 = torch.zeros(M, H * 64, device = 'cuda'); dv2 = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
+    ops.attn_bwd(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.kt_kv0), dev(rb.kt_kvend), dev(rb.kt_q0), dev(rb.kt_qend), len(rb.kt_kv0), dq2, dk2, dv2, H * 64,
+                 M, H, scale, cap, None)
+    torch.cuda.synchronize()
+    for ours, gen, want, name in ((dq, dq2, qf.grad, 'dq'), (dk, dk2, kf.grad, 'dk'), (dv.float(), dv2.float(), vf.grad, 'dv')):
+        err = (ours - want).abs().max().item() / want.abs().max().item()
+        err2 = (ours - gen).abs().max().item() / want.abs().max().item()
+        assert err < 4e-2 and err2 < 4e-2, (name, err, err2)
+    # large gammas: the fast path must decline
+    ops.attn_fast_params(zeros + 2.0, zeros + 2.0, 64, scale, cap, fp)
+    torch.cuda.synchronize()
+    assert fp[0].item() == 0.0
 
 
 def test_rowops_vs_torch(ops):

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_k(const __nv_bfloat16* _
                                                          long long ld_q, long long ld_k, long long ld_v, const float* __restrict__ gates, int H,
                                                          const int* __restrict__ kv_limit, const int* __restrict__ tile_q0, const int* __restrict__ tile_qend,
                                                          const int* __restrict__ tile_kv0, const int* __restrict__ tile_kvend, __nv_bfloat16* __restrict__ o,
-                                                         long long ld_o, float* __restrict__ lse, int M, float scale, float cap) {
+                                                         long long ld_o, float* __restrict__ lse, int M, float scale, float cap, const float* __restrict__ skip_if_fast) {
+  if (skip_if_fast && skip_if_fast[0] != 0.f) return;     // the bounded-logit tcgen05 kernel (attention_sm100.cu) handles this layer
   __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64];
   __shared__ __align__(128) __nv_bfloat16 sK[2][64 * 64];
   __shared__ __align__(128) __nv_bfloat16 sV[2][64 * 64];
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_k(const __nv_bfloat16* _
                                                          const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_limit,
                                                          const int* __restrict__ kt_kv0, const int* __restrict__ kt_kvend, const int* __restrict__ kt_q0,
                                                          const int* __restrict__ kt_qend, float* __restrict__ dq, float* __restrict__ dk,
-                                                         __nv_bfloat16* __restrict__ dv, long long ld_dv, int M, int H, float scale, float cap) {
+                                                         __nv_bfloat16* __restrict__ dv, long long ld_dv, int M, int H, float scale, float cap, const float* __restrict__ skip_if_fast) {
+  if (skip_if_fast && skip_if_fast[0] != 0.f) return;     // the bounded-logit tcgen05 kernel (attention_sm100.cu) handles this layer
   extern __shared__ __align__(128) uint8_t att_smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
   __nv_bfloat16* sV = sK + 64 * 64;
@@ -420,11 +422,11 @@ extern "C" {
 
 int tfx_attn_fwd(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
                  const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
-                 void* o, long long ld_o, float* lse, int M, float scale, float softcap, void* stream) {
+                 void* o, long long ld_o, float* lse, int M, float scale, float softcap, const float* skip_if_fast, void* stream) {
   if (n_tiles <= 0) return 0;
   TFX_REQUIRE(softcap > 0.f, "attn_fwd: softcap must be > 0 (got %f)", softcap);
   attn_fwd_k<<<dim3(n_tiles, H), ATT_THREADS, 0, ST(stream)>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ld_q, ld_k, ld_v, gates, H, kv_limit,
-                                                               tile_q0, tile_qend, tile_kv0, tile_kvend, (__nv_bfloat16*)o, ld_o, lse, M, scale, softcap);
+                                                               tile_q0, tile_qend, tile_kv0, tile_kvend, (__nv_bfloat16*)o, ld_o, lse, M, scale, softcap, skip_if_fast);
   return check_launch("attn_fwd");
 }
 
@@ -439,7 +441,7 @@ int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* ga
 
 int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
                  const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
-                 int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, void* stream) {
+                 int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* skip_if_fast, void* stream) {
   if (n_kv_tiles <= 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -448,7 +450,7 @@ int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre
   }
   attn_bwd_k<<<dim3(n_kv_tiles, H), ATT_THREADS, ATT_BWD_SMEM, ST(stream)>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)do_pre, ld_q, ld_k,
                                                                   ld_v, ld_do, lse, dsum_hm, kv_limit, kt_kv0, kt_kvend, kt_q0, kt_qend, dq, dk, (__nv_bfloat16*)dv, ld_dv, M, H,
-                                                                  scale, softcap);
+                                                                  scale, softcap, skip_if_fast);
   return check_launch("attn_bwd");
 }
 

@@ -1,0 +1,576 @@
+// tcgen05 / TMEM / TMA attention for sm_100a: the "bounded-logit" fast path of the span-masked, soft-capped
+// attention (semantics: attention.cu; reference transfusion.py:998-1027, mask :452-470).
+//
+// Why a separate path.  q and k are RMS-normalised per head (T.py:950-952), so |q.k| * dh^-1/2 <= 8 * max|gq+1| * max|gk+1|
+// is known from the two 64-element gamma vectors before the kernel runs.  When that bound keeps the soft-cap argument
+// y = s/cap inside |y| <= 0.75 (true for any gamma product <= 4.6; gamma is 0 at init) two things follow:
+//   * tanh(y) is a degree-9 odd polynomial to 2.6e-7 absolute - same accuracy as the MUFU ex2+rcp formulation of the
+//     general kernel, but on the FMA pipe (the MUFU pipe, 16/clk/SM, is what bounds the general kernel);
+//   * the soft-capped logits are bounded by m = cap * y_max <= 37.5, so softmax can use the FIXED maximum m: no running max,
+//     no rescaling of the output accumulator - O accumulates untouched in TMEM across all KV tiles.
+// `tfx_attn_fast_params` evaluates the bound on the device; both this kernel and the general one are launched and the one
+// whose precondition fails returns immediately (no host synchronisation).
+//
+// Schedule (one CTA = 128 query rows x one head, 2 CTAs / SM so that one CTA's softmax overlaps the other's MMA latency):
+//   warp 0   : TMA producer (Q once, K_j / V_j single-buffered - each is consumed by one MMA batch long before its refill is needed)
+//   warp 1   : tcgen05.mma issuer + TMEM owner.  S = Q K_j^T (128x128x64, SS) -> TMEM[0,128);  O += P V_j (128x64x128, SS) -> TMEM[128,192)
+//   warps 2-5: softmax, thread <-> query row (tcgen05.ld 32x32b): p = 2^(x*poly(x^2) - m2), row sum, P -> smem (bf16, 128B-swizzled
+//              K-major tile, the A operand of the PV MMA).  The span mask is one integer compare per score against kv_limit[row],
+//              skipped for tiles that are entirely visible.
+#include "sm100_ptx.cuh"
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "../../include/tfx_b200.h"
+#include <limits.h>
+
+namespace tfx {
+
+int num_sms();
+
+constexpr int FA_BM = 128, FA_BN = 128;
+constexpr int FA_THREADS = 192;
+constexpr int FA_SMEM = 16384 * 3 + 32768 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr float FA_YMAX = 0.75f;
+
+// tanh(y) ~= y * (C0 + C1 u + C2 u^2 + C3 u^3 + C4 u^4), u = y^2, |y| <= 0.75, abs err 2.6e-7 (minimax fit, fp32 Horner)
+#define FA_C0 9.9999722832e-01f
+#define FA_C1 -3.3323076483e-01f
+#define FA_C2 1.3226091649e-01f
+#define FA_C3 -4.9280448379e-02f
+#define FA_C4 1.2318833231e-02f
+
+// params[0] = 1 if the fast path is valid for this layer, params[1] = m (upper bound of the soft-capped logits, natural units)
+__global__ void attn_fast_params_k(const float* __restrict__ gq, const float* __restrict__ gk, int n, float scale, float cap, float* __restrict__ params) {
+  const int lane = threadIdx.x;
+  float a = 0.f, b = 0.f;
+  for (int i = lane; i < n; i += 32) { a = fmaxf(a, fabsf(gq[i] + 1.f)); b = fmaxf(b, fabsf(gk[i] + 1.f)); }
+  a = warp_max(a); b = warp_max(b);
+  if (lane == 0) {
+    // |q| <= sqrt(n) * a, |k| <= sqrt(n) * b (RMSNorm scale sqrt(n), rotation preserves norms); 1.01 covers the bf16 rounding of q, k
+    const float xmax = 1.01f * (float)n * a * b * scale;
+    const float ymax = xmax / cap;
+    params[0] = (ymax <= FA_YMAX && isfinite(ymax)) ? 1.f : 0.f;
+    params[1] = xmax;
+  }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+attn_fwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+              const float* __restrict__ gates, int H, const int* __restrict__ kv_limit, const int* __restrict__ tile_q0, const int* __restrict__ tile_qend,
+              const int* __restrict__ tile_kv0, const int* __restrict__ tile_kvend, __nv_bfloat16* __restrict__ o, long long ld_o, float* __restrict__ lse,
+              int M, float scale, float cap, const float* __restrict__ fast) {
+  if (fast[0] == 0.f) return;                       // precondition of this path does not hold: the general kernel does the work
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint8_t* sP = smem + 49152;                        // two K-blocks (keys 0-63 | 64-127), each [128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4, *s_full = bars + 5, *s_empty = bars + 6,
+           *p_full = bars + 7, *p_empty = bars + 8, *o_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  int* s_minlim = reinterpret_cast<int*>(bars + 11);
+
+  const int tile = gridDim.x - 1 - blockIdx.x;      // heavy (late) tiles first
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = tile_q0[tile], q_end = tile_qend[tile], kv0 = tile_kv0[tile], kv_end = tile_kvend[tile];
+  const int n_kv = (kv_end - kv0 + FA_BN - 1) / FA_BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    *s_minlim = INT_MAX;
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  // softmax threads: row metadata + the tile-wide minimum of the visibility limits (tiles below it need no mask)
+  const int quad = warp & 3;
+  const int row = quad * 32 + lane;
+  const int grow = q0 + row;
+  const bool valid = warp >= 2 && grow < q_end;
+  const int lim = valid ? kv_limit[grow] : -1;
+  if (warp >= 2 && valid) atomicMin(s_minlim, lim);
+  __syncthreads();
+  const int min_lim = *s_minlim;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 16384);
+      tma_load_2d(&tmQ, q_full, sQ, head * 64, q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int key0 = kv0 + j * FA_BN;
+        mbar_wait(k_empty, (j & 1) ^ 1);
+        mbar_expect_tx(k_full, 16384);
+        tma_load_2d(&tmK, k_full, sK, head * 64, key0);
+        mbar_wait(v_empty, (j & 1) ^ 1);
+        mbar_expect_tx(v_full, 16384);
+        tma_load_2d(&tmV, v_full, sV, head * 64, key0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idO = umma_idesc_bf16(128, 64, 0, 1);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      auto issue_S = [&]() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tS, umma_smem_desc_sw128(aQ + k * 32, 0, 1024), umma_smem_desc_sw128(aK + k * 32, 0, 1024), idS, k > 0 ? 1u : 0u);
+        umma_commit(k_empty);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full, 0);
+      tc_fence_after();
+      issue_S();
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait(k_full, (j + 1) & 1);
+          mbar_wait(s_empty, j & 1);               // softmax has pulled S_j out of TMEM
+          tc_fence_after();
+          issue_S();
+        }
+        mbar_wait(p_full, j & 1);
+        mbar_wait(v_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ss(tO, umma_smem_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024), umma_smem_desc_sw128(aV + kk * 2048, 8192, 1024), idO,
+                       (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(v_empty);
+        umma_commit(p_empty);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ===================================================== softmax warps (thread <-> query row)
+    const float k1 = scale / cap;                    // y = x * k1
+    const float KL = cap * 1.4426950408889634f;      // exponent (base 2) = KL * tanh(y) - m2
+    const float m2 = fast[1] * 1.4426950408889634f;
+    const float k2 = k1 * k1;
+    // e2 = x * (a0 + a1 X + a2 X^2 + a3 X^3 + a4 X^4) - m2,  X = x^2
+    const float a0 = KL * k1 * FA_C0, a1 = KL * k1 * k2 * FA_C1, a2 = KL * k1 * k2 * k2 * FA_C2, a3 = KL * k1 * k2 * k2 * k2 * FA_C3,
+                a4 = KL * k1 * k2 * k2 * k2 * k2 * FA_C4;
+    const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), A3 = make_float2(a3, a3), A4 = make_float2(a4, a4),
+                 NM2 = make_float2(-m2, -m2);
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    uint8_t* prow = sP + (row >> 3) * 1024 + (row & 7) * 128;
+    float2 l2 = make_float2(0.f, 0.f);
+    for (int j = 0; j < n_kv; ++j) {
+      const int key0 = kv0 + j * FA_BN;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);    // PV_{j-1} has consumed the P tile
+      const bool all_visible = key0 + FA_BN - 1 <= min_lim;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        if (c == 3) {                                 // S_j is now entirely in registers / smem: release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);
+        }
+        uint32_t w[16];
+        const int kbase = key0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {           // packed fp32x2 FMAs (FFMA2): two scores per instruction
+          const float2 x = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          const float2 X = __fmul2_rn(x, x);
+          float2 g = __ffma2_rn(A4, X, A3);
+          g = __ffma2_rn(g, X, A2);
+          g = __ffma2_rn(g, X, A1);
+          g = __ffma2_rn(g, X, A0);
+          const float2 e = __ffma2_rn(x, g, NM2);
+          float p0 = ex2_approx(e.x), p1 = ex2_approx(e.y);
+          if (!all_visible) { p0 = (kbase + i <= lim) ? p0 : 0.f; p1 = (kbase + i + 1 <= lim) ? p1 : 0.f; }
+          l2 = __fadd2_rn(l2, make_float2(p0, p1));
+          w[i >> 1] = pack_bf16(p0, p1);
+        }
+        uint8_t* pb = prow + (c >> 1) * 16384;
+        const int ch0 = (c & 1) * 4;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          *reinterpret_cast<uint4*>(pb + (((ch0 + qd) ^ (row & 7)) << 4)) = make_uint4(w[4 * qd], w[4 * qd + 1], w[4 * qd + 2], w[4 * qd + 3]);
+      }
+      fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l * sigmoid(gate) -> bf16
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float l = l2.x + l2.y;
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    float gsc = inv;
+    if (valid && gates) gsc *= 1.f / (1.f + __expf(-gates[(long long)grow * H + head]));
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tO + lane_addr + hf * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+        __nv_bfloat16* dst = o + (long long)grow * ld_o + head * 64 + hf * 32;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(r[qd * 8 + 2 * e]) * gsc, __uint_as_float(r[qd * 8 + 2 * e + 1]) * gsc);
+          *reinterpret_cast<uint4*>(dst + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    if (valid && lse) lse[(long long)head * M + grow] = fast[1] + logf(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+
+// ================================================================================================ backward (bounded-logit path)
+// One CTA = one 128-key tile x one head; it sweeps the 128-row query tiles that can see those keys.  Per query tile:
+//   S  = Q K^T, dP = dO V^T                       (2 x 128x128x64, SS)             -> TMEM [0,128), [128,256)
+//   softmax warps (thread <-> query row, two warps per TMEM lane quadrant, 64 key columns each):
+//        p  = 2^(x poly(x^2) - lse2)     (mask: key <= kv_limit[row], skipped for fully visible tiles)
+//        ds = p (dp - D) (1 - tanh^2) scale        P, dS -> smem (bf16, 128B-swizzled [query][key] tiles)
+//   dV += P^T dO, dK += dS^T Q                     (2 x 128x64x128, A MN-major from the P / dS tiles)    -> TMEM [256,320), [320,384)
+//   dQ  = dS K                                     (128x64x128)                                           -> TMEM [384,448)
+//   dQ leaves through shared memory and ONE TMA reduce-add per 32-column half (cp.reduce.async.bulk.tensor): no LSU atomics.
+// The dQ read-out of tile i-1 is software-pipelined behind the softmax of tile i, and S/dP of tile i+1 are issued as soon as
+// the softmax warps have pulled tile i out of TMEM, so the CUDA cores (the bound of this kernel) never wait for the tensor core.
+constexpr int FB_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
+constexpr int FB_SMEM = 16384 * 2 /*K,V*/ + 32768 * 2 /*Q,dO x2*/ + 32768 * 3 /*P, dS, dQ*/ + 1024 + 256;
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+              const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
+              const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_limit,
+              const int* __restrict__ kt_kv0, const int* __restrict__ kt_kvend, const int* __restrict__ kt_q0, const int* __restrict__ kt_qend,
+              float* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long ld_dv, int M, int H, float scale, float cap, const float* __restrict__ fast) {
+  if (fast[0] == 0.f) return;
+  extern __shared__ uint8_t fb_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fb_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = smem + 32768;                        // [2][16 KB]
+  uint8_t* sDO = smem + 65536;                       // [2][16 KB]
+  uint8_t* sP = smem + 98304;                        // [2 key blocks][128 rows][128 B]
+  uint8_t* sDS = smem + 131072;
+  uint8_t* sDQ = smem + 163840;                      // [2 column halves][128 rows][128 B] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 196608);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *sdp_full = bars + 5, *s_free = bars + 6, *pds_full = bars + 7,
+           *pds_empty = bars + 8, *dq_full = bars + 9, *dq_free = bars + 10, *dkv_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tile = blockIdx.x, head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = kt_kv0[tile], kv_end = kt_kvend[tile], q_begin = kt_q0[tile], q_end = kt_qend[tile];
+  const int n_q = (q_end - q_begin + FA_BM - 1) / FA_BM;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
+    mbar_init(kv_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&qdo_full[b], 1); mbar_init(&qdo_empty[b], 1); }
+    mbar_init(sdp_full, 1); mbar_init(s_free, 8); mbar_init(pds_full, 8); mbar_init(pds_empty, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 8); mbar_init(dkv_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 32768);
+      tma_load_2d(&tmK, kv_full, sK, head * 64, kv0);
+      tma_load_2d(&tmV, kv_full, sV, head * 64, kv0);
+      for (int it = 0; it < n_q; ++it) {
+        const int b = it & 1;
+        mbar_wait(&qdo_empty[b], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[b], 32768);
+        tma_load_2d(&tmQ, &qdo_full[b], sQ + b * 16384, head * 64, q_begin + it * FA_BM);
+        tma_load_2d(&tmDO, &qdo_full[b], sDO + b * 16384, head * 64, q_begin + it * FA_BM);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);       // S, dP: A, B K-major
+      constexpr uint32_t idT = umma_idesc_bf16(128, 64, 1, 1);        // dV, dK: A (P^T / dS^T) MN-major, B (dO / Q) MN-major
+      constexpr uint32_t idQ = umma_idesc_bf16(128, 64, 0, 1);        // dQ: A (dS) K-major, B (K) MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
+      auto issue_S_dP = [&](int b) {
+        const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tS, umma_smem_desc_sw128(aQ + k * 32, 0, 1024), umma_smem_desc_sw128(aK + k * 32, 0, 1024), idS, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tDP, umma_smem_desc_sw128(aDO + k * 32, 0, 1024), umma_smem_desc_sw128(aV + k * 32, 0, 1024), idS, k > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      tc_fence_after();
+      issue_S_dP(0);
+      for (int it = 0; it < n_q; ++it) {
+        const int b = it & 1;
+        if (it + 1 < n_q) {
+          mbar_wait(&qdo_full[b ^ 1], ((it + 1) >> 1) & 1);
+          mbar_wait(s_free, it & 1);                 // softmax warps have pulled S / dP of tile `it` out of TMEM
+          tc_fence_after();
+          issue_S_dP(b ^ 1);
+        }
+        mbar_wait(pds_full, it & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384);
+#pragma unroll
+        for (int kq = 0; kq < 8; ++kq)               // dV += P^T dO : contraction over the 128 queries
+          umma_bf16_ss(tDV, umma_smem_desc_sw128(aP + kq * 2048, 16384, 1024), umma_smem_desc_sw128(aDO + kq * 2048, 8192, 1024), idT, (it > 0 || kq > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kq = 0; kq < 8; ++kq)               // dK += dS^T Q
+          umma_bf16_ss(tDK, umma_smem_desc_sw128(aDS + kq * 2048, 16384, 1024), umma_smem_desc_sw128(aQ + kq * 2048, 8192, 1024), idT, (it > 0 || kq > 0) ? 1u : 0u);
+        if (it > 0) { mbar_wait(dq_free, (it - 1) & 1); tc_fence_after(); }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)               // dQ = dS K : contraction over the 128 keys
+          umma_bf16_ss(tDQ, umma_smem_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024), umma_smem_desc_sw128(aK + kk * 2048, 8192, 1024), idQ, kk > 0 ? 1u : 0u);
+        umma_commit(&qdo_empty[b]);
+        umma_commit(pds_empty);
+        umma_commit(dq_full);
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    // ===================================================== softmax / gradient warps
+    const int quad = warp & 3;
+    const int hf = (warp - 2) >> 2;                  // key-column half (S, dP) / dQ column half handled by this warp
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const float k1 = scale / cap;
+    const float KL = cap * 1.4426950408889634f;
+    const float k2 = k1 * k1;
+    const float a0 = KL * k1 * FA_C0, a1 = KL * k1 * k2 * FA_C1, a2 = KL * k1 * k2 * k2 * FA_C2, a3 = KL * k1 * k2 * k2 * k2 * FA_C3,
+                a4 = KL * k1 * k2 * k2 * k2 * k2 * FA_C4;
+    const float oms_c = -scale / (KL * KL);          // scale * (1 - tanh^2) = fma(e2^2, oms_c, scale)
+    const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), A3 = make_float2(a3, a3), A4 = make_float2(a4, a4),
+                 OC = make_float2(oms_c, oms_c), SC = make_float2(scale, scale);
+    const float* lse_h = lse + (long long)head * M;
+    const float* ds_h = dsum + (long long)head * M;
+    const int swz_row = (row >> 3) * 1024 + (row & 7) * 128;
+    const bool elected = (warp == 2 && lane == 0);
+
+    auto dq_readout = [&](int it_done) {             // dQ of query tile `it_done`: TMEM -> smem -> TMA reduce-add into global
+      mbar_wait(dq_full, it_done & 1);
+      tc_fence_after();
+      if (elected) bulk_wait_read0();                // the previous reduce has finished reading sDQ
+      softmax_bar();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tDQ + lane_addr + hf * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      uint8_t* dst = sDQ + hf * 16384 + swz_row;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+      fence_proxy_async_smem();
+      softmax_bar();
+      if (elected) {
+        const int qrow0 = q_begin + it_done * FA_BM;
+        tma_reduce_add_2d(&tmDQ, sDQ, head * 64, qrow0);
+        tma_reduce_add_2d(&tmDQ, sDQ + 16384, head * 64 + 32, qrow0);
+        bulk_commit();
+      }
+    };
+
+    for (int it = 0; it < n_q; ++it) {
+      const int grow = q_begin + it * FA_BM + row;
+      const bool valid = grow < q_end;
+      const int lim = valid ? kv_limit[grow] : -1;
+      const float lse2 = valid ? lse_h[grow] * 1.4426950408889634f : 0.f;
+      const float Dr = valid ? ds_h[grow] : 0.f;
+      const bool all_visible = __all_sync(0xffffffffu, kv0 + FA_BN - 1 <= lim);
+      const float2 NL = make_float2(-lse2, -lse2), ND = make_float2(-Dr, -Dr);
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      if (it > 0) mbar_wait(pds_empty, (it - 1) & 1);     // dV / dK / dQ MMAs of the previous tile have consumed P, dS
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32b_x32(tS + lane_addr + hf * 64 + c * 32, rs);
+        tmem_ld_32x32b_x32(tDP + lane_addr + hf * 64 + c * 32, rp);
+        tmem_ld_wait();
+        if (c == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
+        }
+        uint32_t wp[16], wd[16];
+        const int kbase = kv0 + hf * 64 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {           // packed fp32x2 FMAs (FFMA2): two scores per instruction
+          const float2 x = make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1]));
+          const float2 X = __fmul2_rn(x, x);
+          float2 g = __ffma2_rn(A4, X, A3);
+          g = __ffma2_rn(g, X, A2);
+          g = __ffma2_rn(g, X, A1);
+          g = __ffma2_rn(g, X, A0);
+          const float2 e = __fmul2_rn(x, g);                        // cap * log2e * tanh(y)
+          const float2 pe = __fadd2_rn(e, NL);
+          float p0 = ex2_approx(pe.x), p1 = ex2_approx(pe.y);
+          if (!all_visible) { p0 = (kbase + i <= lim) ? p0 : 0.f; p1 = (kbase + i + 1 <= lim) ? p1 : 0.f; }
+          const float2 oms = __ffma2_rn(__fmul2_rn(e, e), OC, SC);  // scale * (1 - tanh^2)
+          const float2 dpd = __fadd2_rn(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), ND);
+          const float2 d = __fmul2_rn(__fmul2_rn(make_float2(p0, p1), dpd), oms);
+          wp[i >> 1] = pack_bf16(p0, p1);
+          wd[i >> 1] = pack_bf16(d.x, d.y);
+        }
+        uint8_t* pb = sP + hf * 16384 + swz_row;
+        uint8_t* db = sDS + hf * 16384 + swz_row;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int sw = ((c * 4 + qd) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(pb + sw) = make_uint4(wp[4 * qd], wp[4 * qd + 1], wp[4 * qd + 2], wp[4 * qd + 3]);
+          *reinterpret_cast<uint4*>(db + sw) = make_uint4(wd[4 * qd], wd[4 * qd + 1], wd[4 * qd + 2], wd[4 * qd + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (it > 0) dq_readout(it - 1);
+    }
+    dq_readout(n_q - 1);
+    // ---- dK (fp32) and dV (bf16) of this key tile
+    mbar_wait(dkv_full, 0);
+    tc_fence_after();
+    const int key = kv0 + row;
+    {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tDK + lane_addr + hf * 32, r);
+      tmem_ld_wait();
+      if (key < kv_end) {
+        float* dst = dk + (long long)key * H * 64 + head * 64 + hf * 32;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * 4) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+      }
+      tmem_ld_32x32b_x32(tDV + lane_addr + hf * 32, r);
+      tmem_ld_wait();
+      if (key < kv_end) {
+        __nv_bfloat16* dst = dv + (long long)key * ld_dv + head * 64 + hf * 32;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(r[qd * 8 + 2 * e]), __uint_as_float(r[qd * 8 + 2 * e + 1]));
+          *reinterpret_cast<uint4*>(dst + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    if (elected) bulk_wait0();                       // all dQ reductions have been performed before the CTA retires
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// fp32 2-D tensor map with a 32-float (128 B, swizzled) x box_rows box - the destination of the dQ TMA reduce-add
+static int make_tmap_f32_sw128(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+}  // namespace tfx
+
+using namespace tfx;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int tfx_attn_fast_params(const float* q_gamma, const float* k_gamma, int dim_head, float scale, float softcap, float* params, void* stream) {
+  TFX_REQUIRE(dim_head > 0 && softcap > 0.f, "attn_fast_params: bad arguments");
+  attn_fast_params_k<<<1, 32, 0, ST(stream)>>>(q_gamma, k_gamma, dim_head, scale, softcap, params);
+  return check_launch("attn_fast_params");
+}
+
+int tfx_attn_fwd_tc(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
+                    const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
+                    void* o, long long ld_o, float* lse, int M, float scale, float softcap, const float* fast_params, void* stream) {
+  if (n_tiles <= 0) return 0;
+  TFX_REQUIRE(fast_params != nullptr, "attn_fwd_tc: fast_params (from tfx_attn_fast_params) is required");
+  TFX_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 8 == 0, "attn_fwd_tc: row pitches must be multiples of 8 bf16");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bf16(&tq, q, (long long)H * 64, M, ld_q, FA_BM)) || (rc = make_tmap_bf16(&tk, k, (long long)H * 64, M, ld_k, FA_BN)) ||
+      (rc = make_tmap_bf16(&tv, v, (long long)H * 64, M, ld_v, FA_BN))) {
+    set_error("attn_fwd_tc: cuTensorMapEncodeTiled failed (%d)", rc);
+    return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_fwd_tc_k, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess) { set_error("attn_fwd_tc: cannot raise dynamic smem"); return -2; }
+    attr_set = true;
+  }
+  attn_fwd_tc_k<<<dim3(n_tiles, H), FA_THREADS, FA_SMEM, ST(stream)>>>(tq, tk, tv, gates, H, kv_limit, tile_q0, tile_qend, tile_kv0, tile_kvend, (__nv_bfloat16*)o, ld_o, lse, M,
+                                                                      scale, softcap, fast_params);
+  return check_launch("attn_fwd_tc");
+}
+
+int tfx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
+                    const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
+                    int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* fast_params, void* stream) {
+  if (n_kv_tiles <= 0) return 0;
+  TFX_REQUIRE(fast_params != nullptr, "attn_bwd_tc: fast_params (from tfx_attn_fast_params) is required");
+  TFX_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_do % 8 == 0 && ld_dv % 8 == 0, "attn_bwd_tc: row pitches must be multiples of 8 bf16");
+  CUtensorMap tq, tk, tv, tdo, tdq;
+  int rc;
+  if ((rc = make_tmap_bf16(&tq, q, (long long)H * 64, M, ld_q, FA_BM)) || (rc = make_tmap_bf16(&tk, k, (long long)H * 64, M, ld_k, FA_BN)) ||
+      (rc = make_tmap_bf16(&tv, v, (long long)H * 64, M, ld_v, FA_BN)) || (rc = make_tmap_bf16(&tdo, do_pre, (long long)H * 64, M, ld_do, FA_BM)) ||
+      (rc = make_tmap_f32_sw128(&tdq, dq, (long long)H * 64, M, (long long)H * 64, FA_BM))) {
+    set_error("attn_bwd_tc: cuTensorMapEncodeTiled failed (%d)", rc);
+    return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_k, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM) != cudaSuccess) { set_error("attn_bwd_tc: cannot raise dynamic smem"); return -2; }
+    attr_set = true;
+  }
+  attn_bwd_tc_k<<<dim3(n_kv_tiles, H), FB_THREADS, FB_SMEM, ST(stream)>>>(tq, tk, tv, tdo, tdq, lse, dsum_hm, kv_limit, kt_kv0, kt_kvend, kt_q0, kt_qend, dk, (__nv_bfloat16*)dv,
+                                                                         ld_dv, M, H, scale, softcap, fast_params);
+  return check_launch("attn_bwd_tc");
+}
+
+}  // extern "C"

@@ -60,20 +60,45 @@ struct GemmParams {
   __nv_bfloat16* h;            // [M][N/2] gelu(gate)*value
 };
 
-template <int BN> struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+constexpr int GEMM_XRES = 8 * 8192;      // EPI_RESID: per-warp prefetch of the residual slab (32 rows x 64 fp32), filled by cp.async
+template <int BN, int EPI = 0> struct GemmCfg {
+  static constexpr int STAGES = (BN == 256 || EPI == 2) ? 4 : 6;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING + (EPI == 2 ? GEMM_XRES : 0) + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator (power of two: 256 / 512)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Phi(g) and phi(g) of the exact-erf GELU (T.py:831-834, F.gelu default) from ONE exponential: Abramowitz-Stegun 7.1.26,
+// erf(x) = 1 - (a1 t + .. + a5 t^5) e^{-x^2}, t = 1/(1 + p x), |err| <= 1.5e-7 - far below the bf16 rounding of the outputs.
+// ~14 FMA-pipe instructions + 2 MUFU instead of the ~50 of erff + expf: the GEGLU epilogues are instruction-bound.
+__device__ __forceinline__ void gelu_parts(float g, float& cdf, float& pdf) {
+  const float ax = fabsf(g) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  const float E = __expf(-ax * ax);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float h = 0.5f * poly * t * E;          // 0.5 * (1 - erf(|g|/sqrt 2))
+  cdf = g >= 0.f ? 1.f - h : h;
+  pdf = 0.3989422804014327f * E;
+}
+__device__ __forceinline__ float gelu_erf(float x) { float c, d; gelu_parts(x, c, d); return x * c; }
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack2_bf16_(uint32_t w) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&w);
+  return __bfloat1622float2(t);
 }
 
 // ---- per-warp staging tile: 32 rows x 128 B, 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
@@ -118,12 +143,13 @@ __device__ __forceinline__ void stg_load(uint8_t* sw, int lane, const uint8_t* g
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING);
+  uint8_t* xres_smem = staging + GEMM_STAGING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING + (EPI == EPI_RESID ? GEMM_XRES : 0));
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
@@ -230,14 +256,34 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
-      mbar_wait(&tfull_bar[buf], bphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + buf * BN;
       const int wrow0 = m_blk * GEMM_BM + quad * 32;          // first row of this warp's 32-row slab
       const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
       const int rows_valid = min(32, p.M - wrow0);            // may be <= 0
       const int col0 = n_blk * BN;
+      uint8_t* xr = xres_smem + (warp - 2) * 8192;
+      int qk_pos = 0;
+      if constexpr (EPI == EPI_RESID) {
+        // residual slab of this tile -> smem while the MMAs of the tile are still running (cp.async: no register staging, no stall)
+#pragma unroll
+        for (int cc = 0; cc < BN / 64; ++cc) {
+          const int cbase = col0 + (half * (BN / 64) + cc) * 32;
+          if (cbase < p.N) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+              const bool ok = rr < rows_valid;
+              cp_async16_zfill(xr + cc * 4096 + rr * 128 + ((ch ^ (rr & 7)) << 4), p.x_res + (long long)(wrow0 + (ok ? rr : 0)) * p.N + cbase + ch * 4, ok);
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      if constexpr (EPI == EPI_QKVG) { qk_pos = row_ok ? p.rope_pos[row] : 0; }
+      mbar_wait(&tfull_bar[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + buf * BN;
+      if constexpr (EPI == EPI_RESID) { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); }
 
       if constexpr (EPI == EPI_STORE) {
         const bool f32_staged = p.out_f32 && (p.row_off || (p.ld_f32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
@@ -323,8 +369,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (kind <= 1) {
           const float* gamma = kind == 0 ? p.q_gamma : p.k_gamma;
           __nv_bfloat16* dstm = kind == 0 ? p.q : p.k;
-          const int pos = row_ok ? p.rope_pos[row] : 0;
-          const float2* cs = p.rope_cs + (long long)pos * 32;
+          const float2* cs = p.rope_cs + (long long)qk_pos * 32;
           {
             const int hh = half;
             uint32_t r0[32], r1[32];
@@ -391,12 +436,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
           const int cbase = col0 + c * 32;
           if (cbase >= p.N) break;                    // N is a multiple of 32 for every RESID use
-          uint32_t r[32], xr[32];
+          uint32_t r[32], xrv[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
-          stg_load<8>(sw, lane, reinterpret_cast<const uint8_t*>(p.x_res + (long long)wrow0 * p.N + cbase), (long long)p.N * 4, rows_valid);
-          __syncwarp();
-          stg_get<8>(sw, lane, xr);
-          __syncwarp();
+          stg_get<8>(xr + (c - half * (BN / 64)) * 4096, lane, xrv);
           tmem_ld_wait();
           float y[32], o[32];
 #pragma unroll
@@ -409,19 +451,19 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 s4 = *reinterpret_cast<const float4*>(zrow + cbase + j);
-              o[j] = __uint_as_float(xr[j]) + y[j] * s4.x; o[j + 1] = __uint_as_float(xr[j + 1]) + y[j + 1] * s4.y;
-              o[j + 2] = __uint_as_float(xr[j + 2]) + y[j + 2] * s4.z; o[j + 3] = __uint_as_float(xr[j + 3]) + y[j + 3] * s4.w;
+              o[j] = __uint_as_float(xrv[j]) + y[j] * s4.x; o[j + 1] = __uint_as_float(xrv[j + 1]) + y[j + 1] * s4.y;
+              o[j + 2] = __uint_as_float(xrv[j + 2]) + y[j + 2] * s4.z; o[j + 3] = __uint_as_float(xrv[j + 3]) + y[j + 3] * s4.w;
             }
           } else if (p.ls) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 s4 = *reinterpret_cast<const float4*>(p.ls + cbase + j);
-              o[j] = __uint_as_float(xr[j]) + y[j] * (s4.x + 1.f); o[j + 1] = __uint_as_float(xr[j + 1]) + y[j + 1] * (s4.y + 1.f);
-              o[j + 2] = __uint_as_float(xr[j + 2]) + y[j + 2] * (s4.z + 1.f); o[j + 3] = __uint_as_float(xr[j + 3]) + y[j + 3] * (s4.w + 1.f);
+              o[j] = __uint_as_float(xrv[j]) + y[j] * (s4.x + 1.f); o[j + 1] = __uint_as_float(xrv[j + 1]) + y[j + 1] * (s4.y + 1.f);
+              o[j + 2] = __uint_as_float(xrv[j + 2]) + y[j + 2] * (s4.z + 1.f); o[j + 3] = __uint_as_float(xrv[j + 3]) + y[j + 3] * (s4.w + 1.f);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(xr[j]) + y[j];
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(xrv[j]) + y[j];
           }
           if (p.y_bf16) {
             uint32_t w[16];
@@ -526,7 +568,7 @@ struct GemmOperand {
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& p_in, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   GemmParams p = p_in;
   CUtensorMap tmA, tmA2, tmB;
   int rc;

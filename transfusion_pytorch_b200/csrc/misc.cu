@@ -11,6 +11,21 @@ namespace tfx {
 
 int num_sms();
 
+// Phi(g), phi(g) of the exact-erf GELU from one exponential (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7); same routine as the
+// forward GEGLU epilogue (gemm_sm100.cuh).
+__device__ __forceinline__ void gelu_parts(float g, float& cdf, float& pdf) {
+  const float ax = fabsf(g) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  const float E = __expf(-ax * ax);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float h = 0.5f * poly * t * E;
+  cdf = g >= 0.f ? 1.f - h : h;
+  pdf = 0.3989422804014327f * E;
+}
+
 static inline int ew_grid(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)num_sms() * 16;
@@ -97,8 +112,8 @@ __global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfl
       const float dd[2] = {d.x, d.y}, vv[2] = {v.x, v.y}, gg[2] = {g.x, g.y};
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float cdf = 0.5f * (1.f + erff(gg[e] * 0.70710678118654752f));
-        const float pdf = 0.3989422804014327f * __expf(-0.5f * gg[e] * gg[e]);
+        float cdf, pdf;
+        gelu_parts(gg[e], cdf, pdf);
         o_v[e] = dd[e] * gg[e] * cdf;                       // d value = dh * gelu(g)
         o_g[e] = dd[e] * vv[e] * (cdf + gg[e] * pdf);       // d gate  = dh * value * gelu'(g)
         sv[2 * k + e] += o_v[e]; sg[2 * k + e] += o_g[e];
@@ -345,7 +360,7 @@ int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long
   if (M <= 0) return 0;
   TFX_REQUIRE(inner_pad % 64 == 0 && inner_pad <= 8192, "geglu_bwd: inner_pad %d must be a multiple of 64 and <= 8192", inner_pad);
   const int threads = ((inner_pad / 8) + 31) / 32 * 32;
-  const int rpb = 64;
+  const int rpb = 32;
   geglu_bwd_k<<<(unsigned)((M + rpb - 1) / rpb), threads, 0, ST(stream)>>>((const __nv_bfloat16*)dh_bf16, (const __nv_bfloat16*)vg_bf16, (__nv_bfloat16*)dvg_bf16, M, inner_pad,
                                                                          col_map, dbias, rpb);
   return check_launch("geglu_bwd");

@@ -228,6 +228,12 @@ class Engine:
         if getattr(self, '_pack_ptr', None) != self._first_ptr:
             self._build_pack_jobs()
         self.ops.cast_pack_multi(self._pack_tab, self._pack_blk_job, self._pack_blk_first, self._pack_nblocks)
+        # per layer: is the bounded-logit (tcgen05) attention path valid for the current q/k norm gammas?  (device-side decision)
+        if getattr(self, 'fastp', None) is None or self.fastp.device != self.device:
+            self.fastp = torch.zeros(self.depth, 8, device = self.device, dtype = F32)
+        for i in range(self.depth):
+            pre = f'transformer.layers.{i}.1.fn'
+            self.ops.attn_fast_params(self.P(f'{pre}.q_norm.gamma'), self.P(f'{pre}.k_norm.gamma'), 64, self.scale, self.softcap, self.fastp[i])
         self._dirty = False
         self._packed_version = self.flat._version
 
@@ -237,9 +243,9 @@ class Engine:
         if rb.dev:
             return rb.dev
         ints = [rb.text_id, rb.label, rb.kv_limit, rb.rope_pos, rb.cond_row, rb.slot, rb.tile_q0, rb.tile_qend, rb.tile_kv0, rb.tile_kvend,
-                rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend, rb.row_token]
+                rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend, rb.row_token, rb.t2_q0, rb.t2_qend, rb.t2_kv0, rb.t2_kvend, rb.k2_kv0, rb.k2_kvend, rb.k2_q0, rb.k2_qend]
         names = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
-                 'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token']
+                 'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend']
         sizes = [_round_up(a.shape[0], 4) for a in ints]
         host = torch.empty(sum(sizes), dtype = I32).pin_memory()
         hv = host.numpy()
@@ -375,8 +381,12 @@ class Engine:
             o.gemm_qkvg(uA, D, pk[f'qkvg{i}'], D, M, H, D, q, k, v, gates, qk_inv, self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'),
                         dv['rope_pos'], rope)
             att = self.buf(f'{lt}o', (M, HI), BF16); lse = self.buf(f'{lt}lse', (H, M), F32)
+            fp = self.fastp[i]
+            # both kernels are enqueued; the one whose precondition (read from `fp` on the device) fails returns immediately
+            o.attn_fwd_tc(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['t2_q0'], dv['t2_qend'], dv['t2_kv0'], dv['t2_kvend'], int(rb.t2_q0.shape[0]),
+                          att, HI, lse, M, self.scale, self.softcap, fp)
             o.attn_fwd(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_qend'], dv['tile_kv0'], dv['tile_kvend'], n_tiles,
-                       att, HI, lse, M, self.scale, self.softcap)
+                       att, HI, lse, M, self.scale, self.softcap, fp)
             x_b = self.buf(f'{lt}xb', (M, D), F32); yA = self.buf(f'{lt}yA', (M, D), BF16) if train else None
             o.gemm_resid(att, HI, None, 0, 0, pk[f'wo{i}'], HI, M, D, HI, None, x_a, x_b, None, yA, cond_row, zgA, zg_ld, self.P(f'{pre}.1.layerscale'))
             uF = self.buf(f'{lt}uF', (M, D), BF16); statsF = self.buf(f'{lt}sF', (M, 2), F32)
@@ -569,8 +579,11 @@ class Engine:
             dqkvg = self.buf('dqkvg', (M, self.NQ), BF16)
             if self.ws.get('dqkvg_shape') != (M, self.NQ):          # pad columns are never written by the kernels: clear once per shape
                 dqkvg.zero_(); self.ws['dqkvg_shape'] = (M, self.NQ)
+            fp = self.fastp[i]
+            o.attn_bwd_tc(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['k2_kv0'], dv['k2_kvend'], dv['k2_q0'], dv['k2_qend'],
+                          int(rb.k2_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
             o.attn_bwd(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['kt_kv0'], dv['kt_kvend'], dv['kt_q0'], dv['kt_qend'],
-                       int(rb.kt_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap)
+                       int(rb.kt_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
             o.qk_bwd_pack(dq, dk, L['q'], L['k'], L['qk_inv'], self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'), dv['rope_pos'],
                           self.ws['rope_cs'], L['gates'], dsum_mh, dqkvg, self.NQ, self.G(f'{pre}.1.fn.q_norm.gamma'), self.G(f'{pre}.1.fn.k_norm.gamma'), M, H)
             o.gemm_store(dqkvg, self.NQ, 0, pk[f'qkvg{i}'], D, 1, M, D, self.NQ, du, D, None, 0, None, None, 1.0, 0, 1)

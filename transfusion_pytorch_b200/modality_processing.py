@@ -81,6 +81,15 @@ class RaggedBatch:
     kt_kvend: np.ndarray = None
     kt_q0: np.ndarray = None
     kt_qend: np.ndarray = None
+    # same tables with 128-row tiles (tcgen05 attention: UMMA M = 128)
+    t2_q0: np.ndarray = None
+    t2_qend: np.ndarray = None
+    t2_kv0: np.ndarray = None
+    t2_kvend: np.ndarray = None
+    k2_kv0: np.ndarray = None
+    k2_kvend: np.ndarray = None
+    k2_q0: np.ndarray = None
+    k2_qend: np.ndarray = None
     max_rope_pos: int = 0
     has_labels: bool = False
     n_valid: int = 0
@@ -102,21 +111,25 @@ def _meta_ids(model, shape_str: str, modality_type: int):
 
 
 def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
-    """64-row tile tables; tiles never straddle a sequence."""
-    tq0, tqe, tk0, tke = [], [], [], []
-    kk0, kke, kq0, kqe = [], [], [], []
-    for b in range(rb.B):
-        s, n = int(rb.cu[b]), int(rb.seq_lens[b])
-        for t0 in range(0, n, ATT_TILE):
-            q0, qe = s + t0, s + min(t0 + ATT_TILE, n)
-            tq0.append(q0); tqe.append(qe); tk0.append(s)
-            tke.append(int(rb.kv_limit[q0:qe].max()) + 1)
-            kk0.append(q0); kke.append(qe)
-            qf = int(qfirst[q0]) - s
-            kq0.append(s + (qf // ATT_TILE) * ATT_TILE); kqe.append(s + n)
+    """Attention tile tables; tiles never straddle a sequence.  Forward: per query tile the key range [kv0, kv_end) it can see;
+    backward: per key tile the query range [q0, q_end) that can see it.  Built for 64-row tiles (general mma.sync kernels) and
+    128-row tiles (tcgen05 kernels)."""
     as32 = lambda a: np.asarray(a, dtype = np.int32)
-    rb.tile_q0, rb.tile_qend, rb.tile_kv0, rb.tile_kvend = as32(tq0), as32(tqe), as32(tk0), as32(tke)
-    rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend = as32(kk0), as32(kke), as32(kq0), as32(kqe)
+    for T, pre_q, pre_k in ((ATT_TILE, 'tile', 'kt'), (2 * ATT_TILE, 't2', 'k2')):
+        tq0, tqe, tk0, tke = [], [], [], []
+        kk0, kke, kq0, kqe = [], [], [], []
+        for b in range(rb.B):
+            s, n = int(rb.cu[b]), int(rb.seq_lens[b])
+            for t0 in range(0, n, T):
+                q0, qe = s + t0, s + min(t0 + T, n)
+                tq0.append(q0); tqe.append(qe); tk0.append(s)
+                tke.append(int(rb.kv_limit[q0:qe].max()) + 1)
+                kk0.append(q0); kke.append(qe)
+                qf = int(qfirst[q0]) - s
+                kq0.append(s + (qf // T) * T); kqe.append(s + n)
+        for name, arr in ((f'{pre_q}_q0', tq0), (f'{pre_q}_qend', tqe), (f'{pre_q}_kv0', tk0), (f'{pre_q}_kvend', tke),
+                          (f'{pre_k}_kv0', kk0), (f'{pre_k}_kvend', kke), (f'{pre_k}_q0', kq0), (f'{pre_k}_qend', kqe)):
+            setattr(rb, name, as32(arr))
 
 
 def pack_batch(

@@ -228,8 +228,10 @@ def run_b200_arm(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
         e0.record()
+        t_host = time.perf_counter()
         for i in range(steps):
             fn(i)
+        timed.host_ms = 1e3 * (time.perf_counter() - t_host) / steps      # CPU time to enqueue one step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device = dev)
@@ -244,6 +246,7 @@ def run_b200_arm(args):
     if sampler: sampler.start()
     l0 = eng.ops.launches
     ms_total = timed(step_resident, args.steps)
+    host_enqueue_ms = timed.host_ms
     launches = eng.ops.launches - l0
     if sampler:
         sampler.stop_flag = True
@@ -304,7 +307,7 @@ def run_b200_arm(args):
                     config = dict(workload = 'configs[1]: single-modality text+latent d=512 depth=8 dim_latent=384 seq=1024', global_batch = world * B, per_gpu_batch = B,
                                   seq_len = SEQ, parallelism = f'dp{world}', optimizer = 'fused Adam', l2 = 'per-step working set (>10 GB of activations) is far larger than the 126 MB L2; 4 rotating input batches'),
                     e2e = dict(value = e2e_value, unit = 'tokens/s', ms_per_step = ms_e2e, h2d_bytes_per_step = int(h2d[0]), d2h_bytes_per_step = 4),
-                    gpu_launches = int(launches), clocks = clocks, roofline = roof, cpu_baseline = cpu)
+                    gpu_launches = int(launches), host_enqueue_ms_per_step = round(host_enqueue_ms, 3), clocks = clocks, roofline = roof, cpu_baseline = cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

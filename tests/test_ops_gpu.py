@@ -188,7 +188,7 @@ def test_rowops_vs_torch(ops):
     import ctypes
     arr = (ctypes.c_void_p * 5)(*[h.data_ptr() for h in hid])
     xo = torch.zeros(M, D, device = 'cuda')
-    ops.attn_residual_fwd(ctypes.cast(arr, ctypes.c_void_p), 5, gam, pq, xo, None, M, D)
+    ops.attn_residual_fwd(ctypes.cast(arr, ctypes.c_void_p), 5, gam, pq, xo, None, None, M, D)
     vals = torch.stack(hid)
     keys = torch.nn.functional.normalize(vals, dim = -1) * D ** 0.5 * (gam + 1)
     sim = torch.einsum('lnd,d->nl', keys, pq) * D ** -0.5

@@ -33,8 +33,8 @@ SIGNATURES = {
     'tfx_adaln_fwd': [VP, VP, VP, LL, VP, VP, VP, I, I, VP],
     'tfx_adaln_bwd': [VP, VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, I, I, VP],
     'tfx_resid_bwd': [VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, VP, I, I, VP],
-    'tfx_attn_residual_fwd': [VP, I, VP, VP, VP, VP, I, I, VP],
-    'tfx_attn_residual_bwd': [VP, VP, I, VP, VP, VP, VP, VP, I, I, I, VP],
+    'tfx_attn_residual_fwd': [VP, I, VP, VP, VP, VP, VP, I, I, VP],
+    'tfx_attn_residual_bwd': [VP, VP, I, VP, VP, VP, VP, VP, VP, VP, I, I, I, VP],
     'tfx_rmsnorm_fwd': [VP, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_rmsnorm_bwd': [VP, VP, VP, VP, VP, I, I, VP],
     'tfx_embed_assemble': [VP, VP, VP, VP, VP, VP, I, I, VP],

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restri
 // x = sum_l softmax_l(sim) h_l           (T.py:803-829)   single pass, online softmax over depth.
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
-                                                             float* __restrict__ xo, __nv_bfloat16* __restrict__ xb, int M) {
+                                                             float* __restrict__ xo, __nv_bfloat16* __restrict__ xb, float* __restrict__ lse_out, int M) {
   constexpr int D = NCH * 128;
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -216,65 +216,74 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
     for (int i = 0; i < NCH * 4; ++i) acc[i] *= inv;
     store_row_f32<NCH>(xo + (long long)row * D, lane, acc);
     if (xb) store_row_bf16<NCH>(xb + (long long)row * D, lane, acc);
+    if (lse_out && lane == 0) lse_out[row] = m + __logf(l);
   }
 }
 
 // ------------------------------------------------------------------------------------ AttentionResidual backward
 // dh_l += alpha_l*dx + dsim_l*(w/|h| - <h,w> h/|h|^3);   dw += dsim_l*h/|h|   (dw -> d gamma, d pq)
+// Single pass over the hiddens: alpha_l = exp(sim_l - lse) uses the log-sum-exp saved by the forward, and the softmax-backward
+// mean  sum_k alpha_k <h_k, dx>  equals <x_out, dx> (x_out is the saved forward output) - so every h_l is read exactly once.
 template <int NCH>
-__global__ void __launch_bounds__(ROW_THREADS) attn_res_bwd_k(PtrList hid, PtrList dhid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
-                                                             const float* __restrict__ dxo, float* __restrict__ dgamma, float* __restrict__ dpq, int M, int tpw, int init) {
+__global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd_k(PtrList hid, PtrList dhid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
+                                                                const float* __restrict__ dxo, const float* __restrict__ xo, const float* __restrict__ lse,
+                                                                float* __restrict__ dgamma, float* __restrict__ dpq, int M, int tpw, int init) {
   constexpr int D = NCH * 128;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
-  if (r0 >= M) return;
-  float w[NCH * 4], gv[NCH * 4], pv[NCH * 4], accw[NCH * 4];
-  load_row_f32<NCH>(gamma, lane, gv);
-  load_row_f32<NCH>(pq, lane, pv);
+  const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);
+  __shared__ __align__(16) float w_s[D];             // w = (gamma+1) * pq, shared by the block (keeps 16 registers free)
+  for (int c = threadIdx.x; c < D; c += ROW_THREADS) w_s[c] = (gamma[c] + 1.f) * pq[c];
+  __syncthreads();
+  float accw[NCH * 4];
 #pragma unroll
-  for (int i = 0; i < NCH * 4; ++i) { w[i] = (gv[i] + 1.f) * pv[i]; accw[i] = 0.f; }
+  for (int i = 0; i < NCH * 4; ++i) accw[i] = 0.f;
   for (int row = r0; row < r1; ++row) {
-    float dxv[NCH * 4];
+    float dxv[NCH * 4], h[NCH * 4];
     load_row_f32<NCH>(dxo + (long long)row * D, lane, dxv);
-    // pass 1: lane k keeps the scalars of hidden k
-    float my_sim = -INFINITY, my_da = 0.f, my_nrm = 1.f, my_dot = 0.f;
-    for (int k = 0; k < L1; ++k) {
-      float h[NCH * 4];
-      load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
-      float ss = 0.f, dot = 0.f, da = 0.f;
+    load_row_f32<NCH>(xo + (long long)row * D, lane, h);
+    float mean_da = 0.f;
 #pragma unroll
-      for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; da += h[i] * dxv[i]; }
-      ss = warp_sum(ss); dot = warp_sum(dot); da = warp_sum(da);
-      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-      if (lane == k) { my_sim = dot / nrm; my_da = da; my_nrm = nrm; my_dot = dot; }
-    }
-    const float mx = warp_max(my_sim);
-    const float e = lane < L1 ? __expf(my_sim - mx) : 0.f;
-    const float alpha = e / warp_sum(e);
-    const float mean_da = warp_sum(alpha * my_da);
-    const float dsim = alpha * (my_da - mean_da);
-    // pass 2
+    for (int i = 0; i < NCH * 4; ++i) mean_da += h[i] * dxv[i];
+    mean_da = warp_sum(mean_da);
+    const float lse_r = lse[row];
+    load_row_f32<NCH>(hid.p[0] + (long long)row * D, lane, h);
     for (int k = 0; k < L1; ++k) {
-      const float a = __shfl_sync(0xffffffffu, alpha, k), ds = __shfl_sync(0xffffffffu, dsim, k);
-      const float nrm = __shfl_sync(0xffffffffu, my_nrm, k), dot = __shfl_sync(0xffffffffu, my_dot, k);
-      const float rn = 1.f / nrm, c2 = ds * dot * rn * rn * rn, c1 = ds * rn;
-      float h[NCH * 4], g[NCH * 4];
-      load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
+      float hn[NCH * 4], g[NCH * 4];
+      if (k + 1 < L1) load_row_f32<NCH>(hid.p[k + 1] + (long long)row * D, lane, hn);      // prefetch the next hidden
       if (!init) load_row_f32<NCH>(dhid.p[k] + (long long)row * D, lane, g);
       else {
 #pragma unroll
         for (int i = 0; i < NCH * 4; ++i) g[i] = 0.f;
       }
+      float w[NCH * 4];
+      load_row_f32<NCH>(w_s, lane, w);
+      float ss = 0.f, dot = 0.f, da = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; da += h[i] * dxv[i]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); da += __shfl_xor_sync(0xffffffffu, da, o);
+      }
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f), rn = 1.f / nrm;
+      const float a = __expf(dot * rn - lse_r);
+      const float ds = a * (da - mean_da);
+      const float c1 = ds * rn, c2 = ds * dot * rn * rn * rn;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) {
         g[i] += a * dxv[i] + c1 * w[i] - c2 * h[i];
         accw[i] += c1 * h[i];
       }
       store_row_f32<NCH>(dhid.p[k] + (long long)row * D, lane, g);
+      if (k + 1 < L1) {
+#pragma unroll
+        for (int i = 0; i < NCH * 4; ++i) h[i] = hn[i];
+      }
     }
   }
-  float t[NCH * 4];
+  float gv[NCH * 4], pv[NCH * 4], t[NCH * 4];
+  load_row_f32<NCH>(gamma, lane, gv);
+  load_row_f32<NCH>(pq, lane, pv);
 #pragma unroll
   for (int i = 0; i < NCH * 4; ++i) t[i] = accw[i] * pv[i];
   red_row_f32<NCH>(dgamma, lane, t);
@@ -534,23 +543,23 @@ int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, cons
 }
 
 int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          float* x_out, void* x_out_bf16, int M, int D, void* stream) {
+                          float* x_out, void* x_out_bf16, float* lse_out, int M, int D, void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
   PtrList pl;
   for (int i = 0; i < n_hiddens; ++i) pl.p[i] = const_cast<float*>(hiddens[i]);
-  TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, M)));
+  TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, lse_out, M)));
   return check_launch("attn_residual_fwd");
 }
 
 int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          const float* dx_out, float* dgamma, float* dpseudo_query, int M, int D, int init, void* stream) {
+                          const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, int M, int D, int init, void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
   PtrList pl, dl;
   for (int i = 0; i < n_hiddens; ++i) { pl.p[i] = const_cast<float*>(hiddens[i]); dl.p[i] = dhiddens[i]; }
-  const int tpw = 8;
-  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, dgamma, dpseudo_query, M, tpw, init)));
+  const int tpw = 4;
+  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, dgamma, dpseudo_query, M, tpw, init)));
   return check_launch("attn_residual_bwd");
 }
 

@@ -27,6 +27,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
+from ._pinned import POOL
 from .modality_processing import RaggedBatch
 
 BF16, F32, I32, I64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
@@ -247,23 +248,24 @@ class Engine:
         names = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend']
         sizes = [_round_up(a.shape[0], 4) for a in ints]
-        host = torch.empty(sum(sizes), dtype = I32).pin_memory()
+        fl = np.concatenate([rb.cond_times, rb.row_time]).astype(np.float32)
+        n_int, n_fl = sum(sizes), _round_up(fl.shape[0], 4)
+        raw = POOL.take((n_int + n_fl) * 4)                       # pooled pinned staging: no per-step cudaHostAlloc
+        host = raw[:(n_int + n_fl) * 4].view(I32)
         hv = host.numpy()
         off = 0
         for a, s in zip(ints, sizes):
             hv[off:off + a.shape[0]] = a; off += s
+        hv[n_int:n_int + fl.shape[0]] = fl.view(np.int32)
         devbuf = host.to(self.device, non_blocking = True)
+        POOL.give(raw)
         d, off = {}, 0
         for n, a, s in zip(names, ints, sizes):
             d[n] = devbuf[off:off + a.shape[0]]; off += s
-        fl = np.concatenate([rb.cond_times, rb.row_time]).astype(np.float32)
-        if fl.shape[0]:
-            fdev = torch.from_numpy(fl).pin_memory().to(self.device, non_blocking = True)
-            d['cond_times'], d['row_time'] = fdev[:rb.n_cond], fdev[rb.n_cond:]
-        else:
-            d['cond_times'] = d['row_time'] = torch.zeros(0, device = self.device)
-        d['h2d_bytes'] = host.numel() * 4 + fl.shape[0] * 4
-        d['_keep'] = (host, devbuf)
+        fdev = devbuf[n_int:n_int + fl.shape[0]].view(F32)
+        d['cond_times'], d['row_time'] = fdev[:rb.n_cond], fdev[rb.n_cond:]
+        d['h2d_bytes'] = host.numel() * 4
+        d['_keep'] = devbuf
         rb.dev = d
         return d
 
@@ -398,7 +400,9 @@ class Engine:
                          self.P(f'{pre}.2.layerscale'))
             hid.append(x_c)
             xr = self.buf(f'{tag}xr{i}', (M, D), F32); xrb = self.buf(f'{tag}xrb{i}', (M, D), BF16)
-            o.attn_residual_fwd(self._ptr_array(hid), len(hid), self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'), xr, xrb, M, D)
+            rlse = self.buf(f'{tag}rlse{i}', (M,), F32) if train else None
+            o.attn_residual_fwd(self._ptr_array(hid), len(hid), self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'), xr, xrb, rlse, M, D)
+            L.update(xr = xr, rlse = rlse)
             L.update(x_a = x_a, uA = uA, statsA = statsA, q = q, k = k, v = v, gates = gates, qk_inv = qk_inv, att = att, lse = lse, yA = yA, x_b = x_b,
                      uF = uF, statsF = statsF, vg = vg, h = h, yF = yF, x_in = x_in, x_in_b = x_in_b, has_skip = has_skip, first_half = first_half)
             st['layers'].append(L)
@@ -553,7 +557,7 @@ class Engine:
             lm = self.layer_maps[i]
             wA, wF = 2 * i, 2 * i + 1
             o.attn_residual_bwd(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
-                                g, self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), M, D, 1 if i == self.depth - 1 else 0)
+                                g, L['xr'], L['rlse'], self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), M, D, 1 if i == self.depth - 1 else 0)
             gx = dH[i + 1]                       # complete gradient w.r.t. x_c of this layer; updated in place below
             # -- feed-forward branch
             o.resid_bwd(gx, L['yF'], cond_row, st['zg'][:, wF * D:] if nc > 0 else None, zg_ld, self.P(f'{pre}.2.layerscale'), dy,

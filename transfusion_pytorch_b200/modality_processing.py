@@ -113,22 +113,29 @@ def _meta_ids(model, shape_str: str, modality_type: int):
 def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
     """Attention tile tables; tiles never straddle a sequence.  Forward: per query tile the key range [kv0, kv_end) it can see;
     backward: per key tile the query range [q0, q_end) that can see it.  Built for 64-row tiles (general mma.sync kernels) and
-    128-row tiles (tcgen05 kernels)."""
-    as32 = lambda a: np.asarray(a, dtype = np.int32)
+    128-row tiles (tcgen05 kernels).  Vectorised: no per-tile Python work."""
+    cu, lens = rb.cu.astype(np.int64), rb.seq_lens.astype(np.int64)
+    kv_limit = np.asarray(rb.kv_limit)
+    qfirst = np.asarray(qfirst)
     for T, pre_q, pre_k in ((ATT_TILE, 'tile', 'kt'), (2 * ATT_TILE, 't2', 'k2')):
-        tq0, tqe, tk0, tke = [], [], [], []
-        kk0, kke, kq0, kqe = [], [], [], []
-        for b in range(rb.B):
-            s, n = int(rb.cu[b]), int(rb.seq_lens[b])
-            for t0 in range(0, n, T):
-                q0, qe = s + t0, s + min(t0 + T, n)
-                tq0.append(q0); tqe.append(qe); tk0.append(s)
-                tke.append(int(rb.kv_limit[q0:qe].max()) + 1)
-                kk0.append(q0); kke.append(qe)
-                qf = int(qfirst[q0]) - s
-                kq0.append(s + (qf // T) * T); kqe.append(s + n)
-        for name, arr in ((f'{pre_q}_q0', tq0), (f'{pre_q}_qend', tqe), (f'{pre_q}_kv0', tk0), (f'{pre_q}_kvend', tke),
-                          (f'{pre_k}_kv0', kk0), (f'{pre_k}_kvend', kke), (f'{pre_k}_q0', kq0), (f'{pre_k}_qend', kqe)):
+        ntiles = (lens + T - 1) // T                                     # tiles per sequence
+        total = int(ntiles.sum())
+        if total == 0:
+            z = np.zeros(0, dtype = np.int32)
+            for name in (f'{pre_q}_q0', f'{pre_q}_qend', f'{pre_q}_kv0', f'{pre_q}_kvend', f'{pre_k}_kv0', f'{pre_k}_kvend', f'{pre_k}_q0', f'{pre_k}_qend'):
+                setattr(rb, name, z)
+            continue
+        seq = np.repeat(np.arange(rb.B), ntiles)                         # sequence of every tile
+        first = np.cumsum(ntiles) - ntiles                               # index of the first tile of each sequence
+        tin = np.arange(total) - first[seq]                              # tile index inside its sequence
+        s = cu[:-1][seq]
+        q0 = s + tin * T
+        qe = np.minimum(q0 + T, s + lens[seq])
+        kve = np.maximum.reduceat(kv_limit, q0) + 1                      # tiles are contiguous and cover every token
+        kq0 = s + ((qfirst[q0] - s) // T) * T
+        as32 = lambda a: np.ascontiguousarray(a, dtype = np.int32)
+        for name, arr in ((f'{pre_q}_q0', q0), (f'{pre_q}_qend', qe), (f'{pre_q}_kv0', s), (f'{pre_q}_kvend', kve),
+                          (f'{pre_k}_kv0', q0), (f'{pre_k}_kvend', qe), (f'{pre_k}_q0', kq0), (f'{pre_k}_qend', s + lens[seq])):
             setattr(rb, name, as32(arr))
 
 

@@ -22,6 +22,7 @@ from torch import nn, Tensor, tensor, is_tensor, cat
 from torch.nn import Module, ModuleList
 
 from .sampling import SamplingMixin
+from ._pinned import POOL
 from .modality_processing import (
     ModalitySample, RaggedBatch, pack_batch, pack_text_only, get_processing_strategy, DEFAULT_PROCESSING_STRATEGY, is_int_tensor)
 
@@ -356,19 +357,39 @@ class Transfusion(SamplingMixin, Module):
 
     # ------------------------------------------------------------------ engine glue
     def _latents_to_device(self, rb: RaggedBatch):
+        """Per modality type: the instances' latents concatenated into one fp32 [S_t, dim_latent] device matrix.
+        Host tensors that are already pinned are DMA'd straight into their slice (no host-side copy); pageable ones go
+        through a persistent pinned staging buffer (one memcpy, no per-step cudaHostAlloc)."""
         dev = self.device
         out, nbytes = [], 0
         for t, lst in enumerate(rb.latents):
             if not lst:
                 out.append(None); continue
-            if any(x.is_cuda for x in lst):
-                out.append(cat([x.detach().to(dev).float() for x in lst]).contiguous())
-            else:
-                host = cat([x.detach().float().cpu() for x in lst]).contiguous()
-                if dev.type == 'cuda':
-                    host = host.pin_memory()
-                nbytes += host.numel() * 4
-                out.append(host.to(dev, non_blocking = True))
+            if dev.type != 'cuda':
+                out.append(cat([x.detach().float() for x in lst]).contiguous()); continue
+            dl = lst[0].shape[-1]
+            rows = [x.shape[0] for x in lst]
+            dst = torch.empty(sum(rows), dl, device = dev, dtype = torch.float32)
+            stage, stage_raw, off, soff = None, None, 0, 0
+            for x, n in zip(lst, rows):
+                x = x.detach()
+                if x.is_cuda:
+                    dst[off:off + n].copy_(x)
+                elif x.dtype == torch.float32 and x.is_contiguous() and x.is_pinned():
+                    dst[off:off + n].copy_(x, non_blocking = True); nbytes += x.numel() * 4
+                else:
+                    if stage is None:
+                        need = sum(r for r, y in zip(rows, lst) if not y.is_cuda) * dl
+                        stage_raw = POOL.take(need * 4)
+                        stage = stage_raw[:need * 4].view(torch.float32)
+                    view = stage[soff:soff + n * dl].view(n, dl)
+                    view.copy_(x)
+                    dst[off:off + n].copy_(view, non_blocking = True)
+                    soff += n * dl; nbytes += n * dl * 4
+                off += n
+            if stage is not None:
+                POOL.give(stage_raw)
+            out.append(dst)
         rb.latent_h2d_bytes = nbytes
         return out
 

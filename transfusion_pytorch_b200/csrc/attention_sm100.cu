@@ -171,7 +171,6 @@ attn_fwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int key0 = kv0 + j * FA_BN;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      if (j > 0) mbar_wait(p_empty, (j - 1) & 1);    // PV_{j-1} has consumed the P tile
       const bool all_visible = key0 + FA_BN - 1 <= min_lim;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -199,6 +198,7 @@ attn_fwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           l2 = __fadd2_rn(l2, make_float2(p0, p1));
           w[i >> 1] = pack_bf16(p0, p1);
         }
+        if (c == 0 && j > 0) mbar_wait(p_empty, (j - 1) & 1);    // PV_{j-1} has consumed the P tile (waited for as late as possible)
         uint8_t* pb = prow + (c >> 1) * 16384;
         const int ch0 = (c & 1) * 4;
 #pragma unroll
@@ -409,17 +409,25 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     };
 
+    // per-row metadata of the NEXT query tile is fetched while the current one is processed (global-load latency off the critical path)
+    int lim_n = -1; float lse_n = 0.f, D_n = 0.f;
+    auto fetch_row_meta = [&](int it) {
+      const int gr = q_begin + it * FA_BM + row;
+      const bool ok = it < n_q && gr < q_end;
+      lim_n = ok ? kv_limit[gr] : -1;
+      lse_n = ok ? lse_h[gr] : 0.f;
+      D_n = ok ? ds_h[gr] : 0.f;
+    };
+    fetch_row_meta(0);
     for (int it = 0; it < n_q; ++it) {
-      const int grow = q_begin + it * FA_BM + row;
-      const bool valid = grow < q_end;
-      const int lim = valid ? kv_limit[grow] : -1;
-      const float lse2 = valid ? lse_h[grow] * 1.4426950408889634f : 0.f;
-      const float Dr = valid ? ds_h[grow] : 0.f;
+      const int lim = lim_n;
+      const float lse2 = lse_n * 1.4426950408889634f;
+      const float Dr = D_n;
+      fetch_row_meta(it + 1);
       const bool all_visible = __all_sync(0xffffffffu, kv0 + FA_BN - 1 <= lim);
       const float2 NL = make_float2(-lse2, -lse2), ND = make_float2(-Dr, -Dr);
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
-      if (it > 0) mbar_wait(pds_empty, (it - 1) & 1);     // dV / dK / dQ MMAs of the previous tile have consumed P, dS
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t rs[32], rp[32];
@@ -451,6 +459,7 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           wp[i >> 1] = pack_bf16(p0, p1);
           wd[i >> 1] = pack_bf16(d.x, d.y);
         }
+        if (c == 0 && it > 0) mbar_wait(pds_empty, (it - 1) & 1);     // dV / dK / dQ MMAs of the previous tile have consumed P, dS
         uint8_t* pb = sP + hf * 16384 + swz_row;
         uint8_t* db = sDS + hf * 16384 + swz_row;
 #pragma unroll

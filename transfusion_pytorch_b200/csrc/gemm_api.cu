@@ -60,6 +60,8 @@ int tfx_gemm_qkvg(const void* u, long long ldu, const void* W, long long ldw, in
   p.q = (__nv_bfloat16*)q; p.k = (__nv_bfloat16*)k; p.v = (__nv_bfloat16*)v; p.gates = gates; p.qk_inv = qk_inv;
   p.q_gamma = q_gamma; p.k_gamma = k_gamma; p.rope_pos = rope_pos; p.rope_cs = (const float2*)rope_cs;
   GemmOperand a{u, ldu, false}, b{W, ldw, false};
+  // 256-wide tiles (4 heads per tile, 16 epilogue warps) whenever the head count allows it; 2 heads per 128-wide tile otherwise
+  if (H % 4 == 0) return finish(launch_gemm_t<256, false, false, EPI_QKVG>(a, b, p, num_sms(), ST(stream)), "gemm_qkvg");
   return finish(launch_gemm_t<128, false, false, EPI_QKVG>(a, b, p, num_sms(), ST(stream)), "gemm_qkvg");
 }
 
@@ -83,7 +85,7 @@ int tfx_gemm_geglu(const void* u, long long ldu, const void* W1p, long long ldw,
   GemmParams p; memset(&p, 0, sizeof(p));
   p.M = M; p.N = Np; p.K = K; p.k_splits = 1; p.bias = b1p; p.vg = (__nv_bfloat16*)vg; p.h = (__nv_bfloat16*)h;
   GemmOperand a{u, ldu, false}, b{W1p, ldw, false};
-  return finish(launch_gemm_t<128, false, false, EPI_GEGLU>(a, b, p, num_sms(), ST(stream)), "gemm_geglu");
+  return finish(launch_gemm_t<256, false, false, EPI_GEGLU>(a, b, p, num_sms(), ST(stream)), "gemm_geglu");
 }
 
 }  // extern "C"

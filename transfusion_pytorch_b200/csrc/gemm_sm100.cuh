@@ -24,8 +24,6 @@ namespace tfx {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;     // 64 bf16 = 128 B = one swizzle atom row
 constexpr int GEMM_UK = 16;     // UMMA K for 16-bit inputs
-constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps (two per TMEM lane quadrant)
-constexpr int GEMM_STAGING = 8 * 4096;   // 8 epilogue warps x (32 rows x 128 B)
 
 enum : int { EPI_STORE = 0, EPI_QKVG = 1, EPI_RESID = 2, EPI_GEGLU = 3 };
 
@@ -60,13 +58,22 @@ struct GemmParams {
   __nv_bfloat16* h;            // [M][N/2] gelu(gate)*value
 };
 
-constexpr int GEMM_XRES = 8 * 8192;      // EPI_RESID: per-warp prefetch of the residual slab (32 rows x 64 fp32), filled by cp.async
+// Epilogue organisation.  A tcgen05.ld gives a thread one accumulator ROW, and a warp may only touch the TMEM lane quadrant warp%4,
+// so parallelism in the epilogue comes from several warps per quadrant splitting the tile's COLUMNS.  The fused epilogues (QKVG,
+// RESID, GEGLU) are latency-bound with 8 warps (profiles/r01_ncu_gemm_epi_v2.txt: 10-45 % issue utilisation, 1 block / SM), so they
+// run 16 epilogue warps (4 per quadrant, <= 112 registers / thread); the plain STORE epilogue (dgrad / wgrad) keeps 8.
 template <int BN, int EPI = 0> struct GemmCfg {
+  static constexpr int EW = (EPI == 0 || (EPI == 1 && BN == 128)) ? 8 : 16;                   // epilogue warps
+  static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int STAGES = (BN == 256 || EPI == 2) ? 4 : 6;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING + (EPI == 2 ? GEMM_XRES : 0) + 1024 /*align slack*/ + 256 /*barriers*/;
+  // per-warp staging: 32 rows x 128 B (swizzled) for 8-warp kernels and RESID (fp32 rows; doubles as the residual prefetch buffer),
+  // 32 rows x 64 B for the 16-warp bf16 epilogues of the 256-wide kernels (smem is needed for the 4-stage operand ring there)
+  static constexpr int STG_WARP = EW == 8 ? 4096 : (EPI == 2 ? 4096 + 2048 : 2048);   // RESID: residual / fp32 tile (4 KB) + bf16 tile (2 KB)
+  static constexpr int STAGING = EW * STG_WARP;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator (power of two: 256 / 512)
 };
 
@@ -140,16 +147,44 @@ __device__ __forceinline__ void stg_load(uint8_t* sw, int lane, const uint8_t* g
   }
 }
 
+// 32 fp32 values of the lane's row -> bf16 -> staging tile (128 B pitch, 4 chunks), packed chunk by chunk
+__device__ __forceinline__ void stg_put_pack(uint8_t* sw, int lane, const float* y) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(sw + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+        make_uint4(pack_bf16(y[8 * c], y[8 * c + 1]), pack_bf16(y[8 * c + 2], y[8 * c + 3]), pack_bf16(y[8 * c + 4], y[8 * c + 5]), pack_bf16(y[8 * c + 6], y[8 * c + 7]));
+}
+// compact variant for 32 bf16 per row: 32 rows x 64 B, chunk c of row r at r*64 + ((c ^ ((r >> 1) & 3)) << 4)  (conflict-free both ways)
+__device__ __forceinline__ void stg64_put(uint8_t* sw, int lane, const uint32_t* w) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(sw + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+__device__ __forceinline__ void stg64_put_pack(uint8_t* sw, int lane, const float* y) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(sw + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(pack_bf16(y[8 * c], y[8 * c + 1]), pack_bf16(y[8 * c + 2], y[8 * c + 3]), pack_bf16(y[8 * c + 4], y[8 * c + 5]), pack_bf16(y[8 * c + 6], y[8 * c + 7]));
+}
+__device__ __forceinline__ void stg64_store(const uint8_t* sw, int lane, uint8_t* g, long long pitch, int rows_valid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), ch = lane & 3;
+    if (row < rows_valid)
+      *reinterpret_cast<uint4*>(g + row * pitch + ch * 16) = *reinterpret_cast<const uint4*>(sw + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI>::THREADS), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int EW = Cfg::EW;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
-  uint8_t* xres_smem = staging + GEMM_STAGING;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING + (EPI == EPI_RESID ? GEMM_XRES : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING);
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
@@ -167,7 +202,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EW); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -247,8 +282,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================================================== epilogue warps (2..9)
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;        // column half of the tile handled by this warp
-    uint8_t* sw = staging + (warp - 2) * 4096;
+    const int part = (warp - 2) >> 2;        // column slice of the tile handled by this warp (EW / 4 slices)
+    const int half = part;                   // 8-warp kernels: two column halves
+    uint8_t* sw = staging + (warp - 2) * Cfg::STG_WARP;
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int split = item / (m_tiles * n_tiles);
@@ -261,20 +297,16 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = row < p.M;
       const int rows_valid = min(32, p.M - wrow0);            // may be <= 0
       const int col0 = n_blk * BN;
-      uint8_t* xr = xres_smem + (warp - 2) * 8192;
       int qk_pos = 0;
       if constexpr (EPI == EPI_RESID) {
-        // residual slab of this tile -> smem while the MMAs of the tile are still running (cp.async: no register staging, no stall)
+        // residual slab of this tile (32 rows x 32 fp32) -> smem while the MMAs of the tile are still running (cp.async: no stall)
+        const int cbase = col0 + part * 32;
+        if (cbase < p.N) {
 #pragma unroll
-        for (int cc = 0; cc < BN / 64; ++cc) {
-          const int cbase = col0 + (half * (BN / 64) + cc) * 32;
-          if (cbase < p.N) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3), ch = lane & 7;
-              const bool ok = rr < rows_valid;
-              cp_async16_zfill(xr + cc * 4096 + rr * 128 + ((ch ^ (rr & 7)) << 4), p.x_res + (long long)(wrow0 + (ok ? rr : 0)) * p.N + cbase + ch * 4, ok);
-            }
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+            const bool ok = rr < rows_valid;
+            cp_async16_zfill(sw + rr * 128 + ((ch ^ (rr & 7)) << 4), p.x_res + (long long)(wrow0 + (ok ? rr : 0)) * p.N + cbase + ch * 4, ok);
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -360,8 +392,73 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
+      } else if constexpr (EPI == EPI_QKVG && BN == 256) {
+        // 256-wide tile = 4 heads, one head (64 accumulator columns) per warp of the quadrant
+        const int tps = p.H >> 2;             // tiles per section (H % 4 == 0)
+        const int kind = n_blk / tps;         // 0 q, 1 k, 2 v, 3 gates
+        const int tis = n_blk - kind * tps;
+        const long long HI = (long long)p.H * 64;
+        const uint32_t tcol = taddr + part * 64;
+        if (kind <= 1) {
+          const float* gamma = kind == 0 ? p.q_gamma : p.k_gamma;
+          __nv_bfloat16* dstm = kind == 0 ? p.q : p.k;
+          const float2* cs = p.rope_cs + (long long)qk_pos * 32;
+          const int head = tis * 4 + part;
+          float ss = 0.f;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {    // pass 1: |x|^2 over the head (TMEM reads are cheap: the row is re-read in pass 2)
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tcol + hf * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float a = __uint_as_float(r[j]); ss += a * a; }
+          }
+          const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+          if (row_ok) p.qk_inv[(long long)row * 2 * p.H + kind * p.H + head] = inv;
+          const float sc = inv * 8.f;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {    // pass 2: normalise, gamma, RoPE, bf16
+            uint32_t r[32], outw[16];
+            tmem_ld_32x32b_x32(tcol + hf * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 gm = *reinterpret_cast<const float2*>(gamma + hf * 32 + 2 * i);
+              const float y0 = __uint_as_float(r[2 * i]) * sc * (gm.x + 1.f);
+              const float y1 = __uint_as_float(r[2 * i + 1]) * sc * (gm.y + 1.f);
+              const float2 cc = cs[hf * 16 + i];
+              outw[i] = pack_bf16(y0 * cc.x - y1 * cc.y, y1 * cc.x + y0 * cc.y);
+            }
+            stg64_put(sw, lane, outw);
+            __syncwarp();
+            stg64_store(sw, lane, reinterpret_cast<uint8_t*>(dstm + (long long)wrow0 * HI + head * 64 + hf * 32), HI * 2, rows_valid);
+            __syncwarp();
+          }
+        } else if (kind == 2) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32], w[16];
+            tmem_ld_32x32b_x32(tcol + hf * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            stg64_put(sw, lane, w);
+            __syncwarp();
+            stg64_store(sw, lane, reinterpret_cast<uint8_t*>(p.v + (long long)wrow0 * HI + tis * 256 + part * 64 + hf * 32), HI * 2, rows_valid);
+            __syncwarp();
+          }
+        } else if (part == 0) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* dst = p.gates + (long long)row * p.H;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < p.H) dst[j] = __uint_as_float(r[j]);
+          }
+        }
       } else if constexpr (EPI == EPI_QKVG) {
-        static_assert(EPI != EPI_QKVG || BN == 128, "QKVG epilogue expects 128-wide N tiles");
+        static_assert(EPI != EPI_QKVG || BN == 128 || BN == 256, "QKVG epilogue expects 128- or 256-wide N tiles");
         const int tps = p.H >> 1;             // tiles per section
         const int kind = n_blk / tps;         // 0 q, 1 k, 2 v, 3 gates
         const int tis = n_blk - kind * tps;   // tile in section
@@ -430,89 +527,104 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       } else if constexpr (EPI == EPI_RESID) {
+        static_assert(EPI != EPI_RESID || BN == 128, "RESID epilogue expects 128-wide N tiles (4 x 32-column slices)");
         const int crow = (row_ok && p.cond_row) ? p.cond_row[row] : -1;
         const float* zrow = (p.zgate && crow >= 0) ? p.zgate + (long long)crow * p.zgate_ld : nullptr;
-#pragma unroll 1
-        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-          const int cbase = col0 + c * 32;
-          if (cbase >= p.N) break;                    // N is a multiple of 32 for every RESID use
-          uint32_t r[32], xrv[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          stg_get<8>(xr + (c - half * (BN / 64)) * 4096, lane, xrv);
+        const int cbase = col0 + part * 32;
+        if (cbase < p.N) {                              // N is a multiple of 32 for every RESID use
+          uint32_t r[32];
+          uint8_t* swb = sw + 4096;                     // 64-byte-pitch tile for the bf16 outputs
+          tmem_ld_32x32b_x32(taddr + part * 32, r);
           tmem_ld_wait();
-          float y[32], o[32];
+          float y[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]);
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) { const float4 b = *reinterpret_cast<const float4*>(p.bias + cbase + j); y[j] += b.x; y[j + 1] += b.y; y[j + 2] += b.z; y[j + 3] += b.w; }
           }
-          if (zrow) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(zrow + cbase + j);
-              o[j] = __uint_as_float(xrv[j]) + y[j] * s4.x; o[j + 1] = __uint_as_float(xrv[j + 1]) + y[j + 1] * s4.y;
-              o[j + 2] = __uint_as_float(xrv[j + 2]) + y[j + 2] * s4.z; o[j + 3] = __uint_as_float(xrv[j + 3]) + y[j + 3] * s4.w;
-            }
-          } else if (p.ls) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(p.ls + cbase + j);
-              o[j] = __uint_as_float(xrv[j]) + y[j] * (s4.x + 1.f); o[j + 1] = __uint_as_float(xrv[j + 1]) + y[j + 1] * (s4.y + 1.f);
-              o[j + 2] = __uint_as_float(xrv[j + 2]) + y[j + 2] * (s4.z + 1.f); o[j + 3] = __uint_as_float(xrv[j + 3]) + y[j + 3] * (s4.w + 1.f);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(xrv[j]) + y[j];
-          }
           if (p.y_bf16) {
-            uint32_t w[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(y[2 * j], y[2 * j + 1]);
-            stg_put<4>(sw, lane, w);
+            stg64_put_pack(swb, lane, y);
             __syncwarp();
-            stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.y_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
+            stg64_store(swb, lane, reinterpret_cast<uint8_t*>(p.y_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
             __syncwarp();
           }
+          {
+            uint32_t xrv[32];
+            stg_get<8>(sw, lane, xrv);                  // residual row (prefetched by cp.async before the accumulator wait)
+            if (zrow) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(o[j]);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(zrow + cbase + j);
+                y[j] = __uint_as_float(xrv[j]) + y[j] * s4.x; y[j + 1] = __uint_as_float(xrv[j + 1]) + y[j + 1] * s4.y;
+                y[j + 2] = __uint_as_float(xrv[j + 2]) + y[j + 2] * s4.z; y[j + 3] = __uint_as_float(xrv[j + 3]) + y[j + 3] * s4.w;
+              }
+            } else if (p.ls) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(p.ls + cbase + j);
+                y[j] = __uint_as_float(xrv[j]) + y[j] * (s4.x + 1.f); y[j + 1] = __uint_as_float(xrv[j + 1]) + y[j + 1] * (s4.y + 1.f);
+                y[j + 2] = __uint_as_float(xrv[j + 2]) + y[j + 2] * (s4.z + 1.f); y[j + 3] = __uint_as_float(xrv[j + 3]) + y[j + 3] * (s4.w + 1.f);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(xrv[j]);
+            }
+          }
+          __syncwarp();                                 // every lane has consumed its residual row: the 4 KB tile now stages x_out
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(y[j]);
           stg_put<8>(sw, lane, r);
           __syncwarp();
           stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(p.x_out + (long long)wrow0 * p.N + cbase), (long long)p.N * 4, rows_valid);
-          __syncwarp();
           if (p.x_out_bf16) {
-            uint32_t w[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(o[2 * j], o[2 * j + 1]);
-            stg_put<4>(sw, lane, w);
+            stg64_put_pack(swb, lane, y);
             __syncwarp();
-            stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.x_out_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
-            __syncwarp();
+            stg64_store(swb, lane, reinterpret_cast<uint8_t*>(p.x_out_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
           }
+          __syncwarp();
         }
       } else if constexpr (EPI == EPI_GEGLU) {
-        static_assert(EPI != EPI_GEGLU || BN == 128, "GEGLU epilogue expects 128-wide N tiles");
-        {
-          const int c = half;
-          uint32_t rv[32], rg[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, rv);
-          tmem_ld_32x32b_x32(taddr + 64 + c * 32, rg);
+        static_assert(EPI != EPI_GEGLU || BN == 256, "GEGLU epilogue expects 256-wide N tiles (2 x [64 value | 64 gate])");
+        const int pair = part >> 1, c = part & 1;
+        const int cv = col0 + pair * 128 + c * 32, cg = cv + 64;
+        if (cv < p.N) {                                 // N is a multiple of 128: a pair is either complete or absent
+          // Three short passes (value -> vg, gate -> vg, value x gelu(gate) -> h): re-reading the accumulator from TMEM is cheaper
+          // than keeping 64 fp32 + 48 packed words live in a 96-register budget.
+          const uint32_t tv = taddr + pair * 128 + c * 32, tg = tv + 64;
+          uint32_t r[32];
+          float g[32];
+          tmem_ld_32x32b_x32(tv, r);
           tmem_ld_wait();
-          const int cv = col0 + c * 32, cg = col0 + 64 + c * 32;
-          uint32_t wv[16], wg[16], wh[16];
+          {
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float v0 = __uint_as_float(rv[2 * j]) + p.bias[cv + 2 * j], v1 = __uint_as_float(rv[2 * j + 1]) + p.bias[cv + 2 * j + 1];
-            const float g0 = __uint_as_float(rg[2 * j]) + p.bias[cg + 2 * j], g1 = __uint_as_float(rg[2 * j + 1]) + p.bias[cg + 2 * j + 1];
-            wv[j] = pack_bf16(v0, v1); wg[j] = pack_bf16(g0, g1);
-            wh[j] = pack_bf16(gelu_erf(g0) * v0, gelu_erf(g1) * v1);
+            for (int j = 0; j < 32; j += 2) { const float2 bv = *reinterpret_cast<const float2*>(p.bias + cv + j); v[j] = __uint_as_float(r[j]) + bv.x; v[j + 1] = __uint_as_float(r[j + 1]) + bv.y; }
+            stg64_put_pack(sw, lane, v);
           }
-          stg_put<4>(sw, lane, wv); __syncwarp();
-          stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.vg + (long long)wrow0 * p.N + cv), (long long)p.N * 2, rows_valid); __syncwarp();
-          stg_put<4>(sw, lane, wg); __syncwarp();
-          stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.vg + (long long)wrow0 * p.N + cg), (long long)p.N * 2, rows_valid); __syncwarp();
-          stg_put<4>(sw, lane, wh); __syncwarp();
-          stg_store<4>(sw, lane, reinterpret_cast<uint8_t*>(p.h + (long long)wrow0 * (p.N / 2) + n_blk * 64 + c * 32), (long long)p.N, rows_valid); __syncwarp();
+          __syncwarp();
+          stg64_store(sw, lane, reinterpret_cast<uint8_t*>(p.vg + (long long)wrow0 * p.N + cv), (long long)p.N * 2, rows_valid);
+          tmem_ld_32x32b_x32(tg, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) { const float2 bg = *reinterpret_cast<const float2*>(p.bias + cg + j); g[j] = __uint_as_float(r[j]) + bg.x; g[j + 1] = __uint_as_float(r[j + 1]) + bg.y; }
+          __syncwarp();
+          stg64_put_pack(sw, lane, g);
+          __syncwarp();
+          stg64_store(sw, lane, reinterpret_cast<uint8_t*>(p.vg + (long long)wrow0 * p.N + cg), (long long)p.N * 2, rows_valid);
+          tmem_ld_32x32b_x32(tv, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 bv = *reinterpret_cast<const float2*>(p.bias + cv + j);
+            g[j] = gelu_erf(g[j]) * (__uint_as_float(r[j]) + bv.x);
+            g[j + 1] = gelu_erf(g[j + 1]) * (__uint_as_float(r[j + 1]) + bv.y);
+          }
+          __syncwarp();
+          stg64_put_pack(sw, lane, g);
+          __syncwarp();
+          stg64_store(sw, lane, reinterpret_cast<uint8_t*>(p.h + (long long)wrow0 * (p.N / 2) + (n_blk * 2 + pair) * 64 + c * 32), (long long)p.N, rows_valid);
+          __syncwarp();
         }
       }
       // release this accumulator buffer back to the MMA warp
@@ -596,7 +708,7 @@ int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& 
   const int items = m_tiles * n_tiles * p.k_splits;
   if (items <= 0) return 0;
   const int grid = items < num_sms ? items : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -97,7 +97,7 @@ __global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfl
   float sv[8], sg[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sv[e] = 0.f; sg[e] = 0.f; }
-#pragma unroll 2
+#pragma unroll 4
   for (long long r = r0; r < r1; ++r) {
     const uint4 d4 = *reinterpret_cast<const uint4*>(dh + r * Ip + c8);
     const __nv_bfloat16* vrow = vg + r * 2 * Ip + tile * 128;

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(ROW_THREADS) adaln_fwd_k(const float* __restri
 // ------------------------------------------------------------------------------------ adaLN backward
 // dx += LN'(du * scale);  d(gamma_c) += du*xhat, d(beta_c) += du   (per cond row)   d(g) += du*xhat (text)
 template <int NCH>
-__global__ void __launch_bounds__(ROW_THREADS) adaln_bwd_k(const float* __restrict__ du, const float* __restrict__ x,
+__global__ void __launch_bounds__(ROW_THREADS, 2) adaln_bwd_k(const float* __restrict__ du, const float* __restrict__ x,
                                                           const float* __restrict__ stats, const int* __restrict__ cond_row,
                                                           const float* __restrict__ film, long long film_ld, const float* __restrict__ g,
                                                           float* __restrict__ dx, float* __restrict__ dfilm, long long dfilm_ld,
@@ -499,10 +499,17 @@ __global__ void __launch_bounds__(ROW_THREADS) qk_bwd_pack_k(const float* __rest
   }
 }
 
+int num_sms();
 static inline int row_grid(int M, int sms) {
   long long blocks = ((long long)M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   long long cap = (long long)sms * 8;
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+// rows per warp such that the grid is (just under) one full wave of `blocks_per_sm` resident blocks on every SM
+static inline int balanced_tpw(int M, int sms, int blocks_per_sm, int min_tpw) {
+  const long long warps = (long long)sms * blocks_per_sm * WARPS_PER_BLOCK;
+  const int tpw = (int)((M + warps - 1) / warps);
+  return tpw < min_tpw ? min_tpw : tpw;
 }
 static inline int chunk_grid(int M, int tpw) {
   long long warps = ((long long)M + tpw - 1) / tpw;
@@ -527,7 +534,7 @@ int tfx_adaln_fwd(const float* x, const int* cond_row, const float* film, long l
 int tfx_adaln_bwd(const float* du, const float* x, const float* stats, const int* cond_row, const float* film, long long film_ld,
                   const float* ln_gamma, float* dx_accum, float* dfilm, long long dfilm_ld, float* dln_gamma, int M, int D, void* stream) {
   if (M <= 0) return 0;
-  const int tpw = 16;
+  const int tpw = balanced_tpw(M, num_sms(), 2, 4);
   TFX_DISPATCH_NCH(D, (adaln_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(du, x, stats, cond_row, film, film_ld, ln_gamma, dx_accum, dfilm, dfilm_ld, dln_gamma, M, tpw)));
   return check_launch("adaln_bwd");
 }
@@ -535,7 +542,7 @@ int tfx_adaln_bwd(const float* du, const float* x, const float* stats, const int
 int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, const float* zgate, long long zgate_ld, const float* layerscale,
                   void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, float* dbias, int M, int D, void* stream) {
   if (M <= 0) return 0;
-  const int tpw = 16;
+  const int tpw = balanced_tpw(M, num_sms(), 2, 4);
   const size_t smem = dbias ? (size_t)WARPS_PER_BLOCK * D * sizeof(float) : 0;
   TFX_DISPATCH_NCH(D, (resid_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, smem, ST(stream)>>>(dx, (const __nv_bfloat16*)y_bf16, cond_row, zgate, zgate_ld, layerscale,
                                                                                                  (__nv_bfloat16*)dy_bf16, dzgate, dzgate_ld, dlayerscale, dbias, M, tpw)));

@@ -41,7 +41,8 @@ int tfx_gemm_store(const void* A, long long lda, int a_mn_major, const void* B, 
  * (q_norm, k_norm), 964-965 (apply_rotary_emb), 1027 (to_gates).  Outputs q,k (post-RoPE), v: bf16 [M][H*64];
  * gates fp32 [M][H] (logits); qk_inv fp32 [M][2H] (saved 1/|x| for backward).                     */
 int tfx_gemm_qkvg(const void* u, long long ldu, const void* W, long long ldw, int M, int H, int D, void* q, void* k, void* v, float* gates, float* qk_inv,
-                  const float* q_gamma, const float* k_gamma, const int* rope_pos, const float* rope_cs, void* stream);
+                  const float* q_gamma, const float* k_gamma, const int* rope_pos, const float* rope_cs_t /* [32][rope_len][2], see tfx_rope_table */, int rope_len,
+                  void* stream);
 
 /* branch output projection + AdaptiveWrapper output gate + residual:
  *   y = [A | A2] W^T + bias ;  x_out = x_res + y * (cond_row[m] >= 0 ? zgate[cond_row[m]] : layerscale + 1)
@@ -139,7 +140,8 @@ int tfx_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int tfx_scale_f32(float* p, const float* scale_ptr, float scale, long long n, void* stream);
 int tfx_scale_bf16(void* p_bf16, const float* scale_ptr, long long n, void* stream);          /* p *= *scale_ptr (device scalar) */
 int tfx_axpy_f32(float* y, const float* x, float a, long long n, void* stream);   /* y += a*x */
-int tfx_rope_table(const float* freqs, float* cos_sin, int max_pos, int n_freqs, void* stream);
+/* cos_sin [max_pos][n_freqs][2]; cos_sin_t (optional) the same table stored [n_freqs][max_pos][2] (coalesced reads for thread-per-row epilogues) */
+int tfx_rope_table(const float* freqs, float* cos_sin, float* cos_sin_t, int max_pos, int n_freqs, void* stream);
 /* fused Adam / AdamW over the flat parameter buffer (the optimizer the reference's examples use, train_latent_with_text.py:142-153) */
 int tfx_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int decoupled_wd, int step, float grad_scale, int zero_grads /* 1: clear grads in the same pass */, void* stream);

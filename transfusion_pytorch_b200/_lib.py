@@ -20,7 +20,7 @@ VP, I, LL, F = c_void_p, c_int, c_longlong, c_float
 SIGNATURES = {
     'tfx_init': [I],
     'tfx_gemm_store': [VP, LL, I, VP, LL, I, I, I, I, VP, LL, VP, LL, VP, VP, F, I, I, VP],
-    'tfx_gemm_qkvg': [VP, LL, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP],
+    'tfx_gemm_qkvg': [VP, LL, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, I, VP],
     'tfx_gemm_resid': [VP, LL, VP, LL, I, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, LL, VP, VP],
     'tfx_gemm_geglu': [VP, LL, VP, LL, VP, I, I, I, VP, VP, VP],
     'tfx_attn_fwd': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, LL, VP, I, F, F, VP, VP],
@@ -54,7 +54,7 @@ SIGNATURES = {
     'tfx_scale_f32': [VP, VP, F, LL, VP],
     'tfx_scale_bf16': [VP, VP, LL, VP],
     'tfx_axpy_f32': [VP, VP, F, LL, VP],
-    'tfx_rope_table': [VP, VP, I, I, VP],
+    'tfx_rope_table': [VP, VP, VP, I, I, VP],
     'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP],
 }
 

@@ -45,7 +45,8 @@ struct GemmParams {
   float* qk_inv;               // [M][2H]  1/max(|x|,eps) for q heads then k heads
   const float *q_gamma, *k_gamma;   // [64]
   const int* rope_pos;         // [M]
-  const float2* rope_cs;       // [max_pos][32] (cos, sin)
+  const float2* rope_cs;       // [32][rope_len] (cos, sin): transposed table, consecutive positions are contiguous
+  int rope_len;
   // ---- EPI_RESID: y = acc + bias; y_bf16 = y; x_out = x_res + y * scale(row, col)
   const float* x_res; float* x_out; __nv_bfloat16* x_out_bf16;     // [M][N]
   __nv_bfloat16* y_bf16;       // [M][N] optional (pre-scale branch output, saved for backward)
@@ -312,6 +313,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
       if constexpr (EPI == EPI_QKVG) { qk_pos = row_ok ? p.rope_pos[row] : 0; }
+      if constexpr (EPI == EPI_RESID) { qk_pos = (row_ok && p.cond_row) ? p.cond_row[row] : -1; }      // (reused as the condition row)
       mbar_wait(&tfull_bar[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + buf * BN;
@@ -402,7 +404,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (kind <= 1) {
           const float* gamma = kind == 0 ? p.q_gamma : p.k_gamma;
           __nv_bfloat16* dstm = kind == 0 ? p.q : p.k;
-          const float2* cs = p.rope_cs + (long long)qk_pos * 32;
+          const float2* cs = p.rope_cs + qk_pos;        // entry i of this row's position: cs[i * rope_len]
           const int head = tis * 4 + part;
           float ss = 0.f;
 #pragma unroll
@@ -426,7 +428,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const float2 gm = *reinterpret_cast<const float2*>(gamma + hf * 32 + 2 * i);
               const float y0 = __uint_as_float(r[2 * i]) * sc * (gm.x + 1.f);
               const float y1 = __uint_as_float(r[2 * i + 1]) * sc * (gm.y + 1.f);
-              const float2 cc = cs[hf * 16 + i];
+              const float2 cc = cs[(long long)(hf * 16 + i) * p.rope_len];
               outw[i] = pack_bf16(y0 * cc.x - y1 * cc.y, y1 * cc.x + y0 * cc.y);
             }
             stg64_put(sw, lane, outw);
@@ -466,7 +468,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (kind <= 1) {
           const float* gamma = kind == 0 ? p.q_gamma : p.k_gamma;
           __nv_bfloat16* dstm = kind == 0 ? p.q : p.k;
-          const float2* cs = p.rope_cs + (long long)qk_pos * 32;
+          const float2* cs = p.rope_cs + qk_pos;        // entry i of this row's position: cs[i * rope_len]
           {
             const int hh = half;
             uint32_t r0[32], r1[32];
@@ -490,7 +492,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const float2 gm = *reinterpret_cast<const float2*>(gamma + d0);
                 const float y0 = __uint_as_float(rr[2 * i]) * sc * (gm.x + 1.f);
                 const float y1 = __uint_as_float(rr[2 * i + 1]) * sc * (gm.y + 1.f);
-                const float2 cc = cs[half * 16 + i];
+                const float2 cc = cs[(long long)(half * 16 + i) * p.rope_len];
                 outw[half * 16 + i] = pack_bf16(y0 * cc.x - y1 * cc.y, y1 * cc.x + y0 * cc.y);
               }
             }
@@ -528,7 +530,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else if constexpr (EPI == EPI_RESID) {
         static_assert(EPI != EPI_RESID || BN == 128, "RESID epilogue expects 128-wide N tiles (4 x 32-column slices)");
-        const int crow = (row_ok && p.cond_row) ? p.cond_row[row] : -1;
+        const int crow = qk_pos;                        // fetched before the accumulator wait
         const float* zrow = (p.zgate && crow >= 0) ? p.zgate + (long long)crow * p.zgate_ld : nullptr;
         const int cbase = col0 + part * 32;
         if (cbase < p.N) {                              // N is a multiple of 32 for every RESID use

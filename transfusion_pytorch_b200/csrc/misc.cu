@@ -305,12 +305,16 @@ __global__ void axpy_f32_k(float* __restrict__ y, const float* __restrict__ x, f
 }
 
 // cos/sin table for RoPE: cs[p][i] = (cos(p*f_i), sin(p*f_i))   (rotary_embedding_torch; T.py:3223)
-__global__ void rope_table_k(const float* __restrict__ freqs, float2* __restrict__ cs, int max_pos, int nf) {
+// cs_t (optional) is the same table stored [i][p]: consecutive tokens (consecutive positions) then read consecutive addresses, which is
+// what the thread-per-row QKVG epilogue needs (with [p][i] every lane of a warp load hits a different 256-byte row).
+__global__ void rope_table_k(const float* __restrict__ freqs, float2* __restrict__ cs, float2* __restrict__ cs_t, int max_pos, int nf) {
   const int n = max_pos * nf;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int p = i / nf, f = i - p * nf;
     const float a = (float)p * freqs[f];
-    cs[i] = make_float2(cosf(a), sinf(a));
+    const float2 v = make_float2(cosf(a), sinf(a));
+    cs[i] = v;
+    if (cs_t) cs_t[(long long)f * max_pos + p] = v;
   }
 }
 
@@ -433,9 +437,9 @@ int tfx_axpy_f32(float* y, const float* x, float a, long long n, void* stream) {
   return check_launch("axpy_f32");
 }
 
-int tfx_rope_table(const float* freqs, float* cos_sin, int max_pos, int n_freqs, void* stream) {
+int tfx_rope_table(const float* freqs, float* cos_sin, float* cos_sin_t, int max_pos, int n_freqs, void* stream) {
   if (max_pos <= 0) return 0;
-  rope_table_k<<<ew_grid((long long)max_pos * n_freqs, 256), 256, 0, ST(stream)>>>(freqs, (float2*)cos_sin, max_pos, n_freqs);
+  rope_table_k<<<ew_grid((long long)max_pos * n_freqs, 256), 256, 0, ST(stream)>>>(freqs, (float2*)cos_sin, (float2*)cos_sin_t, max_pos, n_freqs);
   return check_launch("rope_table");
 }
 

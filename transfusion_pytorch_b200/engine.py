@@ -270,12 +270,14 @@ class Engine:
         return d
 
     def rope_table(self, max_pos: int):
+        """cos/sin tables: [pos][32] (row kernels) and its transpose [32][pos] (thread-per-row QKVG epilogue)"""
         n = _round_up(max_pos + 1, 1024)
         t = self.ws.get('rope_cs')
         if t is None or t.shape[0] < n:
             t = torch.empty(n, 32, 2, device = self.device, dtype = F32)
-            self.ops.rope_table(self.model.rotary_emb.freqs.detach().float().contiguous(), t, n, 32)
-            self.ws['rope_cs'] = t
+            tt = torch.empty(32, n, 2, device = self.device, dtype = F32)
+            self.ops.rope_table(self.model.rotary_emb.freqs.detach().float().contiguous(), t, tt, n, 32)
+            self.ws['rope_cs'], self.ws['rope_cs_t'] = t, tt
         return t
 
     def _ptr_array(self, tensors):
@@ -381,7 +383,7 @@ class Engine:
             q = self.buf(f'{lt}q', (M, HI), BF16); k = self.buf(f'{lt}k', (M, HI), BF16); v = self.buf(f'{lt}v', (M, HI), BF16)
             gates = self.buf(f'{lt}g', (M, H), F32); qk_inv = self.buf(f'{lt}qi', (M, 2 * H), F32)
             o.gemm_qkvg(uA, D, pk[f'qkvg{i}'], D, M, H, D, q, k, v, gates, qk_inv, self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'),
-                        dv['rope_pos'], rope)
+                        dv['rope_pos'], self.ws['rope_cs_t'], int(self.ws['rope_cs_t'].shape[1]))
             att = self.buf(f'{lt}o', (M, HI), BF16); lse = self.buf(f'{lt}lse', (H, M), F32)
             fp = self.fastp[i]
             # both kernels are enqueued; the one whose precondition (read from `fp` on the device) fails returns immediately

@@ -120,15 +120,19 @@ int tfx_time_features(const float* times, const float* fourier_w, void* feats_bf
 /* small table ops of the conditioning path: op 0 sigmoid(a), 1 silu(a), 2 a*b*(1-b), 3 a*silu'(b), 4 copy */
 int tfx_table_op(const float* a, long long ld_a, const float* b, long long ld_b, float* out_f32, long long ld_of, void* out_bf16, long long ld_ob, long long rows, int cols,
                  int op, void* stream);
-/* dbias (optional) [col_map ? mapped : 2*inner_pad] += column sums of dvg (gradient of the FFN-in bias, T.py:845) */
-int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, const int* col_map, float* dbias, void* stream);
+/* GEGLU backward on the tile-interleaved layout.  Bias gradient (column sums of dvg, T.py:845): either `partials`
+ * [ceil(M / tfx_geglu_bwd_rows_per_block())][2*inner_pad] fp32 receives per-block partial sums (reduce with tfx_colsum_f32 + col_map -
+ * preferred: ~1000 blocks adding to the same addresses serialise in the L2 atomic units), or, if partials is NULL, dbias[col_map[c]] is
+ * updated with atomics directly. */
+int tfx_geglu_bwd_rows_per_block(void);
+int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, const int* col_map, float* dbias, float* partials, void* stream);
 /* text cross-entropy fwd+bwd (T.py:3320-3331; text-only 2653-2659 with vlimit = num_text_tokens) */
 int tfx_ce_fwd_bwd(const float* logits, long long ld_logits, const int* labels, int V, int vlimit, float gscale, void* dlogits_bf16, long long ld_dlogits,
                    double* loss_sum, int* n_valid, int M, void* stream);
 /* flow MSE fwd+bwd (T.py:3354-3362) */
 int tfx_mse_fwd_bwd(const float* pred, long long ld_pred, const float* flow, void* dpred_bf16, long long ld_dpred, float gscale, double* sumsq, long long S, int dl, void* stream);
 int tfx_colsum_bf16(const void* in_bf16, long long ld, long long M, int N, const int* col_map, float* out, void* stream);
-int tfx_colsum_f32(const float* in, long long ld, long long M, int N, float* out, void* stream);
+int tfx_colsum_f32(const float* in, long long ld, long long M, int N, const int* col_map /* optional */, float* out, void* stream);
 int tfx_cast_pack(const float* src, long long ld_src, int C_src, const int* row_src, void* dst_bf16, long long R_dst, int C_dst, void* stream);
 /* all per-optimizer-step weight repacks in one launch; jobs / block tables live in device memory (built once by the host) */
 typedef struct TfxPackJob {

@@ -43,11 +43,11 @@ SIGNATURES = {
     'tfx_flow_noise': [VP, VP, VP, VP, LL, VP, VP, LL, I, VP],
     'tfx_time_features': [VP, VP, VP, I, I, I, VP],
     'tfx_table_op': [VP, LL, VP, LL, VP, LL, VP, LL, LL, I, I, VP],
-    'tfx_geglu_bwd': [VP, VP, VP, LL, I, VP, VP, VP],
+    'tfx_geglu_bwd': [VP, VP, VP, LL, I, VP, VP, VP, VP],
     'tfx_ce_fwd_bwd': [VP, LL, VP, I, I, F, VP, LL, VP, VP, I, VP],
     'tfx_mse_fwd_bwd': [VP, LL, VP, VP, LL, F, VP, LL, I, VP],
     'tfx_colsum_bf16': [VP, LL, LL, I, VP, VP, VP],
-    'tfx_colsum_f32': [VP, LL, LL, I, VP, VP],
+    'tfx_colsum_f32': [VP, LL, LL, I, VP, VP, VP],
     'tfx_cast_pack': [VP, LL, I, VP, VP, LL, I, VP],
     'tfx_cast_pack_multi': [VP, VP, VP, I, VP],
     'tfx_cast_bf16': [VP, VP, LL, VP],
@@ -58,7 +58,7 @@ SIGNATURES = {
     'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP],
 }
 
-EXPORTED = ['tfx_last_error', 'tfx_version'] + list(SIGNATURES)
+EXPORTED = ['tfx_last_error', 'tfx_version', 'tfx_geglu_bwd_rows_per_block'] + list(SIGNATURES)
 
 
 class TfxError(RuntimeError):
@@ -84,6 +84,8 @@ def load():
     lib.tfx_last_error.argtypes = []
     lib.tfx_version.restype = c_int
     lib.tfx_version.argtypes = []
+    lib.tfx_geglu_bwd_rows_per_block.restype = c_int
+    lib.tfx_geglu_bwd_rows_per_block.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -87,7 +87,7 @@ __global__ void table_op_k(const float* __restrict__ a, const float* __restrict_
 // d(vg) (= gradient of the FFN-in bias).  A thread owns one 8-column chunk of h (and the matching value / gate chunks)
 // and walks `rpb` rows; its 16 column sums stay in registers and are flushed with one atomicAdd each per block.
 __global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ vg, __nv_bfloat16* __restrict__ dvg, long long M, int Ip,
-                            const int* __restrict__ col_map, float* __restrict__ dbias, int rpb) {
+                            const int* __restrict__ col_map, float* __restrict__ dbias, float* __restrict__ partials, int rpb) {
   const int cpr = Ip / 8;                 // 16-byte chunks per row of dh
   const int ch = threadIdx.x;
   if (ch >= cpr) return;
@@ -97,7 +97,7 @@ __global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfl
   float sv[8], sg[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sv[e] = 0.f; sg[e] = 0.f; }
-#pragma unroll 4
+#pragma unroll 2
   for (long long r = r0; r < r1; ++r) {
     const uint4 d4 = *reinterpret_cast<const uint4*>(dh + r * Ip + c8);
     const __nv_bfloat16* vrow = vg + r * 2 * Ip + tile * 128;
@@ -108,23 +108,25 @@ __global__ void geglu_bwd_k(const __nv_bfloat16* __restrict__ dh, const __nv_bfl
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 d = unpack2_bf16(dw[k]), v = unpack2_bf16(vw[k]), g = unpack2_bf16(gw[k]);
-      float o_v[2], o_g[2];
-      const float dd[2] = {d.x, d.y}, vv[2] = {v.x, v.y}, gg[2] = {g.x, g.y};
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float cdf, pdf;
-        gelu_parts(gg[e], cdf, pdf);
-        o_v[e] = dd[e] * gg[e] * cdf;                       // d value = dh * gelu(g)
-        o_g[e] = dd[e] * vv[e] * (cdf + gg[e] * pdf);       // d gate  = dh * value * gelu'(g)
-        sv[2 * k + e] += o_v[e]; sg[2 * k + e] += o_g[e];
-      }
-      ov[k] = pack2_bf16(o_v[0], o_v[1]); og[k] = pack2_bf16(o_g[0], o_g[1]);
+      float cdf0, pdf0, cdf1, pdf1;
+      gelu_parts(g.x, cdf0, pdf0); gelu_parts(g.y, cdf1, pdf1);
+      const float ov0 = d.x * g.x * cdf0, ov1 = d.y * g.y * cdf1;                       // d value = dh * gelu(g)
+      const float og0 = d.x * v.x * fmaf(g.x, pdf0, cdf0), og1 = d.y * v.y * fmaf(g.y, pdf1, cdf1);   // d gate = dh * value * gelu'(g)
+      sv[2 * k] += ov0; sv[2 * k + 1] += ov1; sg[2 * k] += og0; sg[2 * k + 1] += og1;
+      ov[k] = pack2_bf16(ov0, ov1); og[k] = pack2_bf16(og0, og1);
     }
     __nv_bfloat16* orow = dvg + r * 2 * Ip + tile * 128;
     *reinterpret_cast<uint4*>(orow + j) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
     *reinterpret_cast<uint4*>(orow + 64 + j) = make_uint4(og[0], og[1], og[2], og[3]);
   }
-  if (dbias) {
+  if (partials) {
+    // per-block partial column sums, reduced afterwards by tfx_colsum_f32 (same-address atomics from ~1000 blocks serialise in L2)
+    float* prow = partials + (long long)blockIdx.x * 2 * Ip + tile * 128 + j;
+    *reinterpret_cast<float4*>(prow) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+    *reinterpret_cast<float4*>(prow + 4) = make_float4(sv[4], sv[5], sv[6], sv[7]);
+    *reinterpret_cast<float4*>(prow + 64) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+    *reinterpret_cast<float4*>(prow + 68) = make_float4(sg[4], sg[5], sg[6], sg[7]);
+  } else if (dbias) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int cv = tile * 128 + j + e, cg = cv + 64;
@@ -218,13 +220,14 @@ __global__ void colsum_bf16_k(const __nv_bfloat16* __restrict__ in, long long ld
     if (c + 1 < N) { const int o1 = col_map ? col_map[c + 1] : c + 1; if (o1 >= 0) atomicAdd(out + o1, a1); }
   }
 }
-__global__ void colsum_f32_k(const float* __restrict__ in, long long ld, long long M, int N, float* __restrict__ out, int rows_per_block) {
+__global__ void colsum_f32_k(const float* __restrict__ in, long long ld, long long M, int N, const int* __restrict__ col_map, float* __restrict__ out, int rows_per_block) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float a = 0.f;
   for (long long r = r0; r < r1; ++r) a += in[r * ld + c];
-  atomicAdd(out + c, a);
+  const int o = col_map ? col_map[c] : c;
+  if (o >= 0) atomicAdd(out + o, a);
 }
 
 // dst[r][c] (bf16, R_dst x C_dst) = (row_src[r] >= 0 && c < C_src) ? src[row_src[r]*ld_src + c] : 0
@@ -360,13 +363,15 @@ int tfx_table_op(const float* a, long long ld_a, const float* b, long long ld_b,
   return check_launch("table_op");
 }
 
-int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, const int* col_map, float* dbias, void* stream) {
+int tfx_geglu_bwd_rows_per_block(void) { return 32; }
+
+int tfx_geglu_bwd(const void* dh_bf16, const void* vg_bf16, void* dvg_bf16, long long M, int inner_pad, const int* col_map, float* dbias, float* partials, void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(inner_pad % 64 == 0 && inner_pad <= 8192, "geglu_bwd: inner_pad %d must be a multiple of 64 and <= 8192", inner_pad);
   const int threads = ((inner_pad / 8) + 31) / 32 * 32;
-  const int rpb = 32;
+  const int rpb = tfx_geglu_bwd_rows_per_block();
   geglu_bwd_k<<<(unsigned)((M + rpb - 1) / rpb), threads, 0, ST(stream)>>>((const __nv_bfloat16*)dh_bf16, (const __nv_bfloat16*)vg_bf16, (__nv_bfloat16*)dvg_bf16, M, inner_pad,
-                                                                         col_map, dbias, rpb);
+                                                                         col_map, dbias, partials, rpb);
   return check_launch("geglu_bwd");
 }
 
@@ -393,10 +398,10 @@ int tfx_colsum_bf16(const void* in_bf16, long long ld, long long M, int N, const
   return check_launch("colsum_bf16");
 }
 
-int tfx_colsum_f32(const float* in, long long ld, long long M, int N, float* out, void* stream) {
+int tfx_colsum_f32(const float* in, long long ld, long long M, int N, const int* col_map, float* out, void* stream) {
   if (M <= 0 || N <= 0) return 0;
-  const int rpb = 256;
-  colsum_f32_k<<<dim3((N + 127) / 128, (unsigned)((M + rpb - 1) / rpb)), 128, 0, ST(stream)>>>(in, ld, M, N, out, rpb);
+  const int rpb = 64;
+  colsum_f32_k<<<dim3((N + 127) / 128, (unsigned)((M + rpb - 1) / rpb)), 128, 0, ST(stream)>>>(in, ld, M, N, col_map, out, rpb);
   return check_launch("colsum_f32");
 }
 

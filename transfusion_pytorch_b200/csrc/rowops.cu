@@ -436,23 +436,21 @@ __global__ void __launch_bounds__(ROW_THREADS) qk_bwd_pack_k(const float* __rest
       const float4 c0 = cp[0], c1 = cp[1];
       cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
     }
+    for (int h0 = 0; h0 < H; h0 += 4) {
+      const int h = h0 + hq;
+      const bool act = h < H;
+      const long long off = (long long)row * HI + (act ? h : 0) * 64 + sub * 8;
+      // all loads of this head group (q and k, gradient and value) are issued before any arithmetic
+      const float4 da[2] = {*reinterpret_cast<const float4*>(dq + off), *reinterpret_cast<const float4*>(dk + off)};
+      const float4 db[2] = {*reinterpret_cast<const float4*>(dq + off + 4), *reinterpret_cast<const float4*>(dk + off + 4)};
+      const uint4 tv[2] = {*reinterpret_cast<const uint4*>(q + off), *reinterpret_cast<const uint4*>(k + off)};
+      const float invs[2] = {act ? qk_inv[(long long)row * 2 * H + h] : 0.f, act ? qk_inv[(long long)row * 2 * H + H + h] : 0.f};
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const float* dsrc = which == 0 ? dq : dk;
-      const __nv_bfloat16* src = which == 0 ? q : k;
-      for (int h0 = 0; h0 < H; h0 += 4) {
-        const int h = h0 + hq;
-        const bool act = h < H;
-        const long long off = (long long)row * HI + (act ? h : 0) * 64 + sub * 8;
-        float dr[8], r[8];
-        {
-          const float4 a = *reinterpret_cast<const float4*>(dsrc + off), b = *reinterpret_cast<const float4*>(dsrc + off + 4);
-          dr[0] = a.x; dr[1] = a.y; dr[2] = a.z; dr[3] = a.w; dr[4] = b.x; dr[5] = b.y; dr[6] = b.z; dr[7] = b.w;
-          const uint4 t = *reinterpret_cast<const uint4*>(src + off);
-          const float2 p0 = unpack2_bf16(t.x), p1 = unpack2_bf16(t.y), p2 = unpack2_bf16(t.z), p3 = unpack2_bf16(t.w);
-          r[0] = p0.x; r[1] = p0.y; r[2] = p1.x; r[3] = p1.y; r[4] = p2.x; r[5] = p2.y; r[6] = p3.x; r[7] = p3.y;
-        }
-        const float inv = act ? qk_inv[(long long)row * 2 * H + which * H + h] : 0.f;
+      for (int which = 0; which < 2; ++which) {
+        const float dr[8] = {da[which].x, da[which].y, da[which].z, da[which].w, db[which].x, db[which].y, db[which].z, db[which].w};
+        const float2 p0 = unpack2_bf16(tv[which].x), p1 = unpack2_bf16(tv[which].y), p2 = unpack2_bf16(tv[which].z), p3 = unpack2_bf16(tv[which].w);
+        const float r[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+        const float inv = invs[which];
         float xh[8], dxh[8], dot = 0.f;
 #pragma unroll
         for (int pr = 0; pr < 4; ++pr) {

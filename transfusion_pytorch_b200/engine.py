@@ -568,7 +568,11 @@ class Engine:
             o.gemm_store(dy, D, 0, pk[f'w2{i}'], Ip, 1, M, Ip, D, None, 0, dh, Ip, None, None, 1.0, 0, 1)
             o.gemm_store(dy, D, 1, L['h'], Ip, 1, D, inner, M, self.gflat, 0, None, 0, None, lm['w2_rows'], 1.0, 1, ks)
             dvg = self.buf('dvg', (M, 2 * Ip), BF16)
-            o.geglu_bwd(dh, L['vg'], dvg, M, Ip, lm['b1_cols'], self.gflat)
+            rpb = self.ops.lib.tfx_geglu_bwd_rows_per_block()
+            nblk = (M + rpb - 1) // rpb
+            part = self.buf('geglu_part', (nblk, 2 * Ip), F32)
+            o.geglu_bwd(dh, L['vg'], dvg, M, Ip, None, None, part)
+            o.colsum_f32(part, 2 * Ip, nblk, 2 * Ip, lm['b1_cols'], self.gflat)
             o.gemm_store(dvg, 2 * Ip, 0, pk[f'w1{i}'], D, 1, M, D, 2 * Ip, du, D, None, 0, None, None, 1.0, 0, 1)
             o.gemm_store(dvg, 2 * Ip, 1, L['uF'], D, 1, 2 * Ip, D, M, self.gflat, 0, None, 0, None, lm['w1_rows'], 1.0, 1, ks)
             o.adaln_bwd(du, L['x_b'], L['statsF'], cond_row, st['tab'][:, wF * 3 * D:] if nc > 0 else None, tab_ld, self.P(f'{pre}.2.layernorm_gamma'), gx,
@@ -637,7 +641,7 @@ class Engine:
             o.gemm_store(dtabb, W3, 0, pk['wfz'], 4 * D, 1, nc, 4 * D, W3, dcond, 4 * D, None, 0, None, None, 1.0, 0, 1)
             o.gemm_store(dtabb, W3, 1, st['cond'], 4 * D, 1, W3, 4 * D, nc, self.gflat, 0, None, 0, None, self.fz_rows, 1.0, 1, 1)
             bsum = self.buf('bsum', (W3,), F32); bsum.zero_()
-            o.colsum_f32(dtab, W3, nc, W3, bsum)
+            o.colsum_f32(dtab, W3, nc, W3, None, bsum)
             self.gflat.index_add_(0, self.fz_bias_idx, bsum)
             dcpre = self.buf('dcpre', (nc, 4 * D), BF16)
             o.table_op(dcond, 4 * D, st['cpre'], 4 * D, None, 0, dcpre, 4 * D, nc, 4 * D, 3)

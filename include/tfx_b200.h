@@ -101,8 +101,9 @@ int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, cons
  * depth softmax, consumed by the backward together with the forward output x_out so that every hidden is read exactly once */
 int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
                           float* x_out, void* x_out_bf16, float* lse_out, int M, int D, void* stream);
+long long tfx_attn_residual_bwd_workspace_floats(int M, int D);   /* fp32 scratch for the per-block parameter-gradient partial sums */
 int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, int M, int D,
+                          const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D,
                           int init /* 1: dhiddens are overwritten, not accumulated */, void* stream);
 /* final RMSNorm (T.py:1250, 785-786) (+ compaction of modality rows for the flow head) */
 int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream);

@@ -34,7 +34,7 @@ SIGNATURES = {
     'tfx_adaln_bwd': [VP, VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, I, I, VP],
     'tfx_resid_bwd': [VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, VP, I, I, VP],
     'tfx_attn_residual_fwd': [VP, I, VP, VP, VP, VP, VP, I, I, VP],
-    'tfx_attn_residual_bwd': [VP, VP, I, VP, VP, VP, VP, VP, VP, VP, I, I, I, VP],
+    'tfx_attn_residual_bwd': [VP, VP, I, VP, VP, VP, VP, VP, VP, VP, VP, I, I, I, VP],
     'tfx_rmsnorm_fwd': [VP, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_rmsnorm_bwd': [VP, VP, VP, VP, VP, I, I, VP],
     'tfx_embed_assemble': [VP, VP, VP, VP, VP, VP, I, I, VP],
@@ -58,7 +58,7 @@ SIGNATURES = {
     'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP],
 }
 
-EXPORTED = ['tfx_last_error', 'tfx_version', 'tfx_geglu_bwd_rows_per_block'] + list(SIGNATURES)
+EXPORTED = ['tfx_last_error', 'tfx_version', 'tfx_geglu_bwd_rows_per_block', 'tfx_attn_residual_bwd_workspace_floats'] + list(SIGNATURES)
 
 
 class TfxError(RuntimeError):
@@ -86,6 +86,8 @@ def load():
     lib.tfx_version.argtypes = []
     lib.tfx_geglu_bwd_rows_per_block.restype = c_int
     lib.tfx_geglu_bwd_rows_per_block.argtypes = []
+    lib.tfx_attn_residual_bwd_workspace_floats.restype = c_longlong
+    lib.tfx_attn_residual_bwd_workspace_floats.argtypes = [c_int, c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

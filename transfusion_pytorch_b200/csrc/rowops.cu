@@ -61,8 +61,17 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) adaln_bwd_k(const float* __res
   constexpr int D = NCH * 128;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int r0 = warp * tpw, r1 = min(M, r0 + tpw);
-  if (r0 >= M) return;
+  const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);      // (no early return: block-wide barrier below)
+  // text rows all update the same [D] vector: per-warp smem rows + one block-level reduction instead of one global atomic per warp
+  // (thousands of same-address atomics serialise in the L2 atomic units).  Condition rows are shared by only a few warps: direct red.
+  __shared__ __align__(16) float red_g[WARPS_PER_BLOCK][D];
+  float* my_g = red_g[threadIdx.x >> 5];
+  {
+    float z[NCH * 4];
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) z[i] = 0.f;
+    store_row_f32<NCH>(my_g, lane, z);
+  }
   float gv[NCH * 4];
   load_row_f32<NCH>(g, lane, gv);
   float accA[NCH * 4], accB[NCH * 4];
@@ -70,7 +79,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) adaln_bwd_k(const float* __res
   auto flush = [&]() {
     if (cur == -2) return;
     if (cur >= 0) { red_row_f32<NCH>(dfilm + cur * dfilm_ld, lane, accA); red_row_f32<NCH>(dfilm + cur * dfilm_ld + D, lane, accB); }
-    else red_row_f32<NCH>(dg, lane, accA);
+    else {
+      float t[NCH * 4];
+      load_row_f32<NCH>(my_g, lane, t);
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) t[i] += accA[i];
+      store_row_f32<NCH>(my_g, lane, t);
+    }
   };
   for (int row = r0; row < r1; ++row) {
     const int cr = cond_row ? cond_row[row] : -1;
@@ -108,6 +123,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) adaln_bwd_k(const float* __res
     store_row_f32<NCH>(dx + (long long)row * D, lane, o);
   }
   flush();
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += ROW_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS_PER_BLOCK; ++w) t += red_g[w][c];
+    if (t != 0.f) atomicAdd(dg + c, t);
+  }
 }
 
 // ------------------------------------------------------------------------------------ branch-output gate backward
@@ -142,13 +164,17 @@ __global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restri
   const bool has_scale = ls != nullptr;
   float lsv[NCH * 4];
   if (has_scale) load_row_f32<NCH>(ls, lane, lsv);
-  float acc[NCH * 4], accb[NCH * 4];
+  float acc[NCH * 4], accb[NCH * 4], accl[NCH * 4];      // per cond row / bias / layerscale (text rows) accumulators
 #pragma unroll
-  for (int i = 0; i < NCH * 4; ++i) accb[i] = 0.f;
+  for (int i = 0; i < NCH * 4; ++i) { accb[i] = 0.f; accl[i] = 0.f; }
   int cur = -2;
   auto flush = [&]() {
     if (cur == -2 || !has_scale) return;
-    if (cur >= 0) red_row_f32<NCH>(dzgate + cur * dzgate_ld, lane, acc); else red_row_f32<NCH>(dls, lane, acc);
+    if (cur >= 0) red_row_f32<NCH>(dzgate + cur * dzgate_ld, lane, acc);
+    else {
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) accl[i] += acc[i];
+    }
   };
   for (int row = r0; row < r1; ++row) {
     const int cr = (cond_row && zgate) ? cond_row[row] : -1;
@@ -176,6 +202,7 @@ __global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restri
   }
   flush();
   if (dbias) block_red_cols<NCH>(red_smem, accb, dbias);     // uniform branch: every thread of the block reaches the barrier
+  if (has_scale) { __syncthreads(); block_red_cols<NCH>(red_smem, accl, dls); }   // layerscale gradient: one atomic per column per block
 }
 
 // ------------------------------------------------------------------------------------ AttentionResidual forward
@@ -227,11 +254,11 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd_k(PtrList hid, PtrList dhid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
                                                                 const float* __restrict__ dxo, const float* __restrict__ xo, const float* __restrict__ lse,
-                                                                float* __restrict__ dgamma, float* __restrict__ dpq, int M, int tpw, int init) {
+                                                                float* __restrict__ partials, int M, int tpw, int init) {
   constexpr int D = NCH * 128;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);
+  const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);    // (no early return: block-wide barriers below)
   __shared__ __align__(16) float w_s[D];             // w = (gamma+1) * pq, shared by the block (keeps 16 registers free)
   for (int c = threadIdx.x; c < D; c += ROW_THREADS) w_s[c] = (gamma[c] + 1.f) * pq[c];
   __syncthreads();
@@ -281,15 +308,29 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd_k(PtrList hid, Pt
       }
     }
   }
-  float gv[NCH * 4], pv[NCH * 4], t[NCH * 4];
-  load_row_f32<NCH>(gamma, lane, gv);
-  load_row_f32<NCH>(pq, lane, pv);
+  // d w = sum over tokens of c1 * h: block-level reduction, then ONE row of partial sums per block (no same-address atomics from
+  // thousands of warps); attn_res_bwd_finish_k folds the partials into d gamma = dw * pq and d pq = dw * (gamma + 1)
+  __shared__ float red[WARPS_PER_BLOCK][D];
+  store_row_f32<NCH>(red[threadIdx.x >> 5], lane, accw);
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += ROW_THREADS) {
+    float t = 0.f;
 #pragma unroll
-  for (int i = 0; i < NCH * 4; ++i) t[i] = accw[i] * pv[i];
-  red_row_f32<NCH>(dgamma, lane, t);
-#pragma unroll
-  for (int i = 0; i < NCH * 4; ++i) t[i] = accw[i] * (gv[i] + 1.f);
-  red_row_f32<NCH>(dpq, lane, t);
+    for (int w = 0; w < WARPS_PER_BLOCK; ++w) t += red[w][c];
+    partials[(long long)blockIdx.x * D + c] = t;
+  }
+}
+
+// dgamma[c] += pq[c] * sum_b partials[b][c];  dpq[c] += (gamma[c] + 1) * sum_b partials[b][c]
+__global__ void attn_res_bwd_finish_k(const float* __restrict__ partials, int n_blocks, int D, const float* __restrict__ gamma, const float* __restrict__ pq,
+                                      float* __restrict__ dgamma, float* __restrict__ dpq, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const int b0 = blockIdx.y * rows_per_block, b1 = min(n_blocks, b0 + rows_per_block);
+  float a = 0.f;
+  for (int b = b0; b < b1; ++b) a += partials[(long long)b * D + c];
+  atomicAdd(dgamma + c, a * pq[c]);
+  atomicAdd(dpq + c, a * (gamma[c] + 1.f));
 }
 
 // ------------------------------------------------------------------------------------ final RMSNorm
@@ -541,7 +582,7 @@ int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, cons
                   void* dy_bf16, float* dzgate, long long dzgate_ld, float* dlayerscale, float* dbias, int M, int D, void* stream) {
   if (M <= 0) return 0;
   const int tpw = balanced_tpw(M, num_sms(), 2, 4);
-  const size_t smem = dbias ? (size_t)WARPS_PER_BLOCK * D * sizeof(float) : 0;
+  const size_t smem = (dbias || layerscale) ? (size_t)WARPS_PER_BLOCK * D * sizeof(float) : 0;
   TFX_DISPATCH_NCH(D, (resid_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, smem, ST(stream)>>>(dx, (const __nv_bfloat16*)y_bf16, cond_row, zgate, zgate_ld, layerscale,
                                                                                                  (__nv_bfloat16*)dy_bf16, dzgate, dzgate_ld, dlayerscale, dbias, M, tpw)));
   return check_launch("resid_bwd");
@@ -557,15 +598,24 @@ int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const floa
   return check_launch("attn_residual_fwd");
 }
 
+static const int ATTN_RES_BWD_TPW = 4;
+long long tfx_attn_residual_bwd_workspace_floats(int M, int D) { return (long long)chunk_grid(M, ATTN_RES_BWD_TPW) * D; }
+
 int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, int M, int D, int init, void* stream) {
+                          const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, int init,
+                          void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
+  TFX_REQUIRE(workspace != nullptr, "attn_residual_bwd: workspace of tfx_attn_residual_bwd_workspace_floats(M, D) floats is required");
   PtrList pl, dl;
   for (int i = 0; i < n_hiddens; ++i) { pl.p[i] = const_cast<float*>(hiddens[i]); dl.p[i] = dhiddens[i]; }
-  const int tpw = 4;
-  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<chunk_grid(M, tpw), ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, dgamma, dpseudo_query, M, tpw, init)));
-  return check_launch("attn_residual_bwd");
+  const int tpw = ATTN_RES_BWD_TPW;
+  const int blocks = chunk_grid(M, tpw);
+  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<blocks, ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, workspace, M, tpw, init)));
+  if (int rc = check_launch("attn_residual_bwd")) return rc;
+  const int rpb = 16;
+  attn_res_bwd_finish_k<<<dim3((D + 127) / 128, (blocks + rpb - 1) / rpb), 128, 0, ST(stream)>>>(workspace, blocks, D, gamma, pseudo_query, dgamma, dpseudo_query, rpb);
+  return check_launch("attn_residual_bwd_finish");
 }
 
 int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream) {

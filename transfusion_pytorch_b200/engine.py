@@ -553,13 +553,14 @@ class Engine:
             dzg = self.buf('dzg', (nc, self.W * D), F32); dzg.zero_()
         dy = self.buf('dy', (M, D), BF16)
         du = self.buf('du', (M, D), F32)
+        arws = self.buf('attn_res_ws', (int(o.lib.tfx_attn_residual_bwd_workspace_floats(M, D)),), F32)
         for i in reversed(range(self.depth)):
             L = st['layers'][i]
             pre = f'transformer.layers.{i}'
             lm = self.layer_maps[i]
             wA, wF = 2 * i, 2 * i + 1
             o.attn_residual_bwd(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
-                                g, L['xr'], L['rlse'], self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), M, D, 1 if i == self.depth - 1 else 0)
+                                g, L['xr'], L['rlse'], self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), arws, M, D, 1 if i == self.depth - 1 else 0)
             gx = dH[i + 1]                       # complete gradient w.r.t. x_c of this layer; updated in place below
             # -- feed-forward branch
             o.resid_bwd(gx, L['yF'], cond_row, st['zg'][:, wF * D:] if nc > 0 else None, zg_ld, self.P(f'{pre}.2.layerscale'), dy,

@@ -515,10 +515,24 @@ class Engine:
         pk, nc, S = self.packed, rb.n_cond, rb.S
         cond_row = dv['cond_row'] if nc > 0 else None
         tab_ld, zg_ld = self.W * 3 * D, self.W * D
-        ks = max(1, min(64, M // 2048))           # split-K factor of the wgrad GEMMs (K = tokens)
+        ks = max(1, min(64, M // 2048))           # default split-K factor of the wgrad GEMMs (K = tokens)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        def ksplit(n_out, n_in, K = M):
+            # split-K factor of a wgrad GEMM: tiles x splits should fill whole waves of the persistent grid (one CTA per SM);
+            # e.g. the [1408 x 512] FFN-out gradient has 22 tiles: 16 splits = 2.4 waves (80 % busy), 20 splits = 2.97 waves
+            tiles = ((n_out + 127) // 128) * ((n_in + 255) // 256 if (n_in % 256 == 0 or n_in >= 1024) else (n_in + 127) // 128)
+            best, best_eff = 1, 0.0
+            for s in range(1, 65):
+                if K // s < 1024 and s > 1:
+                    break
+                items = tiles * s
+                eff = items / (-(-items // sms) * sms)
+                if eff > best_eff + 0.02 or (abs(eff - best_eff) <= 0.02 and s <= ks and s > best):
+                    best, best_eff = s, eff
+            return best
         def wgrad(dy, ld_dy, n_out, act, ld_act, n_in, gname, K = M):
             # dW[n_out, n_in] += dy^T act : both operands MN-major over the token (K) dimension, split-K atomics
-            o.gemm_store(dy, ld_dy, 1, act, ld_act, 1, n_out, n_in, K, self.G(gname), n_in, None, 0, None, None, 1.0, 1, max(1, min(ks, K // 128)))
+            o.gemm_store(dy, ld_dy, 1, act, ld_act, 1, n_out, n_in, K, self.G(gname), n_in, None, 0, None, None, 1.0, 1, ksplit(n_out, n_in, K))
 
         # ---- heads
         dlog = st['dlogits']
@@ -567,7 +581,7 @@ class Engine:
                         dzg[:, wF * D:] if nc > 0 else None, zg_ld, self.G(f'{pre}.2.layerscale'), self.G(f'{pre}.2.fn.net.3.bias'), M, D)
             dh = self.buf('dh', (M, Ip), BF16)
             o.gemm_store(dy, D, 0, pk[f'w2{i}'], Ip, 1, M, Ip, D, None, 0, dh, Ip, None, None, 1.0, 0, 1)
-            o.gemm_store(dy, D, 1, L['h'], Ip, 1, D, inner, M, self.gflat, 0, None, 0, None, lm['w2_rows'], 1.0, 1, ks)
+            o.gemm_store(dy, D, 1, L['h'], Ip, 1, D, inner, M, self.gflat, 0, None, 0, None, lm['w2_rows'], 1.0, 1, ksplit(D, inner))
             dvg = self.buf('dvg', (M, 2 * Ip), BF16)
             rpb = self.ops.lib.tfx_geglu_bwd_rows_per_block()
             nblk = (M + rpb - 1) // rpb
@@ -575,7 +589,7 @@ class Engine:
             o.geglu_bwd(dh, L['vg'], dvg, M, Ip, None, None, part)
             o.colsum_f32(part, 2 * Ip, nblk, 2 * Ip, lm['b1_cols'], self.gflat)
             o.gemm_store(dvg, 2 * Ip, 0, pk[f'w1{i}'], D, 1, M, D, 2 * Ip, du, D, None, 0, None, None, 1.0, 0, 1)
-            o.gemm_store(dvg, 2 * Ip, 1, L['uF'], D, 1, 2 * Ip, D, M, self.gflat, 0, None, 0, None, lm['w1_rows'], 1.0, 1, ks)
+            o.gemm_store(dvg, 2 * Ip, 1, L['uF'], D, 1, 2 * Ip, D, M, self.gflat, 0, None, 0, None, lm['w1_rows'], 1.0, 1, ksplit(2 * Ip, D))
             o.adaln_bwd(du, L['x_b'], L['statsF'], cond_row, st['tab'][:, wF * 3 * D:] if nc > 0 else None, tab_ld, self.P(f'{pre}.2.layernorm_gamma'), gx,
                         dtab[:, wF * 3 * D:] if nc > 0 else None, tab_ld, self.G(f'{pre}.2.layernorm_gamma'), M, D)
             # -- attention branch
@@ -598,7 +612,7 @@ class Engine:
             o.qk_bwd_pack(dq, dk, L['q'], L['k'], L['qk_inv'], self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'), dv['rope_pos'],
                           self.ws['rope_cs'], L['gates'], dsum_mh, dqkvg, self.NQ, self.G(f'{pre}.1.fn.q_norm.gamma'), self.G(f'{pre}.1.fn.k_norm.gamma'), M, H)
             o.gemm_store(dqkvg, self.NQ, 0, pk[f'qkvg{i}'], D, 1, M, D, self.NQ, du, D, None, 0, None, None, 1.0, 0, 1)
-            o.gemm_store(dqkvg, self.NQ, 1, L['uA'], D, 1, self.NQ, D, M, self.gflat, 0, None, 0, None, lm['qkvg_rows'], 1.0, 1, ks)
+            o.gemm_store(dqkvg, self.NQ, 1, L['uA'], D, 1, self.NQ, D, M, self.gflat, 0, None, 0, None, lm['qkvg_rows'], 1.0, 1, ksplit(self.NQ, D))
             o.adaln_bwd(du, L['x_a'], L['statsA'], cond_row, st['tab'][:, wA * 3 * D:] if nc > 0 else None, tab_ld, self.P(f'{pre}.1.layernorm_gamma'), gx,
                         dtab[:, wA * 3 * D:] if nc > 0 else None, tab_ld, self.G(f'{pre}.1.layernorm_gamma'), M, D)
             # -- U-Net skip projection: x_a = x_in + W_skip [x_in | skip]
@@ -606,12 +620,12 @@ class Engine:
                 o.resid_bwd(gx, None, None, None, 0, None, dy, None, 0, None, None, M, D)
                 wsk = pk[f'wskip{i}']
                 gw = self.G(f'{pre}.0.weight')
-                o.gemm_store(dy, D, 1, L['x_in_b'], D, 1, D, D, M, gw, 2 * D, None, 0, None, None, 1.0, 1, ks)
-                o.gemm_store(dy, D, 1, L['skip_b'], D, 1, D, D, M, gw.view(-1)[D:], 2 * D, None, 0, None, None, 1.0, 1, ks)
+                o.gemm_store(dy, D, 1, L['x_in_b'], D, 1, D, D, M, gw, 2 * D, None, 0, None, None, 1.0, 1, ksplit(D, D))
+                o.gemm_store(dy, D, 1, L['skip_b'], D, 1, D, D, M, gw.view(-1)[D:], 2 * D, None, 0, None, None, 1.0, 1, ksplit(D, D))
                 src = L['skip_src']
-                if src not in dskip:
-                    dskip[src] = self.buf(f'dskip{src}', (M, D), F32); dskip[src].zero_()
-                o.gemm_store(dy, D, 0, wsk[:, D:], 2 * D, 1, M, D, D, dskip[src], D, None, 0, None, None, 1.0, 1, 1)
+                assert src not in dskip                   # every skip source feeds exactly one skip projection: plain store, no zero fill
+                dskip[src] = self.buf(f'dskip{src}', (M, D), F32)
+                o.gemm_store(dy, D, 0, wsk[:, D:], 2 * D, 1, M, D, D, dskip[src], D, None, 0, None, None, 1.0, 0, 1)
                 o.gemm_store(dy, D, 0, wsk, 2 * D, 1, M, D, D, gx, D, None, 0, None, None, 1.0, 1, 1)
             if i in dskip:
                 o.axpy_f32(gx, dskip[i], 1.0, M * D)

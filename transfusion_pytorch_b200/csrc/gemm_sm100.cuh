@@ -286,6 +286,25 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int part = (warp - 2) >> 2;        // column slice of the tile handled by this warp (EW / 4 slices)
     const int half = part;                   // 8-warp kernels: two column halves
     uint8_t* sw = staging + (warp - 2) * Cfg::STG_WARP;
+    // EPI_RESID: the 32 x 32 fp32 residual slab of a tile is fetched into the warp's 4 KB tile by cp.async one tile AHEAD (issued as soon
+    // as the current slab has been pulled into registers), so its DRAM latency hides behind the current tile's math and stores
+    auto resid_prefetch = [&](int it_) {
+      if constexpr (EPI == EPI_RESID) {
+        const int rem_ = it_ % (m_tiles * n_tiles);
+        const int mb_ = rem_ / n_tiles, nb_ = rem_ - mb_ * n_tiles;
+        const int wrow_ = mb_ * GEMM_BM + quad * 32, cb_ = nb_ * BN + part * 32;
+        const int rv_ = min(32, p.M - wrow_);
+        if (cb_ < p.N) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+            const bool ok = rr < rv_;
+            cp_async16_zfill(sw + rr * 128 + ((ch ^ (rr & 7)) << 4), p.x_res + (long long)(wrow_ + (ok ? rr : 0)) * p.N + cb_ + ch * 4, ok);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int split = item / (m_tiles * n_tiles);
@@ -300,17 +319,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int col0 = n_blk * BN;
       int qk_pos = 0;
       if constexpr (EPI == EPI_RESID) {
-        // residual slab of this tile (32 rows x 32 fp32) -> smem while the MMAs of the tile are still running (cp.async: no stall)
-        const int cbase = col0 + part * 32;
-        if (cbase < p.N) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + (lane >> 3), ch = lane & 7;
-            const bool ok = rr < rows_valid;
-            cp_async16_zfill(sw + rr * 128 + ((ch ^ (rr & 7)) << 4), p.x_res + (long long)(wrow0 + (ok ? rr : 0)) * p.N + cbase + ch * 4, ok);
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (local == 0) resid_prefetch(item);         // later tiles were prefetched while the previous tile was being processed
       }
       if constexpr (EPI == EPI_QKVG) { qk_pos = row_ok ? p.rope_pos[row] : 0; }
       if constexpr (EPI == EPI_RESID) { qk_pos = (row_ok && p.cond_row) ? p.cond_row[row] : -1; }      // (reused as the condition row)
@@ -553,7 +562,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           {
             uint32_t xrv[32];
-            stg_get<8>(sw, lane, xrv);                  // residual row (prefetched by cp.async before the accumulator wait)
+            stg_get<8>(sw, lane, xrv);                  // residual row (prefetched by cp.async one tile ahead)
+            __syncwarp();                               // every lane holds its row: the 4 KB tile is free for the NEXT tile's slab
+            if (item + (int)gridDim.x < num_items) resid_prefetch(item + gridDim.x);
             if (zrow) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -573,18 +584,26 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(xrv[j]);
             }
           }
-          __syncwarp();                                 // every lane has consumed its residual row: the 4 KB tile now stages x_out
+          // x_out (fp32) leaves in two 16-column passes through the 64-byte-pitch tile
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(y[j]);
-          stg_put<8>(sw, lane, r);
-          __syncwarp();
-          stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(p.x_out + (long long)wrow0 * p.N + cbase), (long long)p.N * 4, rows_valid);
+          for (int hfc = 0; hfc < 2; ++hfc) {
+            uint32_t w16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w16[j] = __float_as_uint(y[hfc * 16 + j]);
+            __syncwarp();
+            stg64_put(swb, lane, w16);
+            __syncwarp();
+            stg64_store(swb, lane, reinterpret_cast<uint8_t*>(p.x_out + (long long)wrow0 * p.N + cbase + hfc * 16), (long long)p.N * 4, rows_valid);
+          }
           if (p.x_out_bf16) {
+            __syncwarp();
             stg64_put_pack(swb, lane, y);
             __syncwarp();
             stg64_store(swb, lane, reinterpret_cast<uint8_t*>(p.x_out_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
           }
           __syncwarp();
+        } else if (item + (int)gridDim.x < num_items) {
+          resid_prefetch(item + gridDim.x);             // keep the one-ahead commit-group bookkeeping uniform
         }
       } else if constexpr (EPI == EPI_GEGLU) {
         static_assert(EPI != EPI_GEGLU || BN == 256, "GEGLU epilogue expects 256-wide N tiles (2 x [64 value | 64 gate])");

@@ -80,6 +80,7 @@ int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre
  * Same dual-launch protocol as the forward (fast_params from tfx_attn_fast_params; dq must be zero on entry, see tfx_attn_bwd_prep). */
 int tfx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
                     const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
+                    const int* kt_order /* optional: key-tile indices, most query tiles first (load balance of the persistent grid) */,
                     int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* fast_params, void* stream);
 /* backward of the qk-RMSNorm + RoPE epilogue; packs d[q | k | (v written by attn_bwd) | gates] bf16 [M][out_ld] */
 int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const void* k_bf16, const float* qk_inv, const float* q_gamma, const float* k_gamma,

@@ -152,7 +152,7 @@ def test_attention_tcgen05_fast_path_vs_dense(ops, lens, spans):
     dq = torch.full((M, H * 64), 7., device = 'cuda')              # cleared by the prep kernel
     ops.attn_bwd_prep(do, o, gates, dop, dsum, dsum2, dq, M, H)
     dk = torch.zeros(M, H * 64, device = 'cuda'); dv = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
-    ops.attn_bwd_tc(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.k2_kv0), dev(rb.k2_kvend), dev(rb.k2_q0), dev(rb.k2_qend), len(rb.k2_kv0), dq, dk, dv, H * 64,
+    ops.attn_bwd_tc(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.k2_kv0), dev(rb.k2_kvend), dev(rb.k2_q0), dev(rb.k2_qend), dev(rb.k2_order), len(rb.k2_kv0), dq, dk, dv, H * 64,
                     M, H, scale, cap, fp)
     dq2 = torch.zeros(M, H * 64, device = 'cuda'); dk2 = torch.zeros(M, H * 64, device = 'cuda'); dv2 = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
     ops.attn_bwd(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.kt_kv0), dev(rb.kt_kvend), dev(rb.kt_q0), dev(rb.kt_qend), len(rb.kt_kv0), dq2, dk2, dv2, H * 64,

@@ -25,7 +25,7 @@ def main():
     dev = lambda a: torch.from_numpy(a).cuda()
     kvl = dev(rb.kv_limit)
     t2 = [dev(x) for x in (rb.t2_q0, rb.t2_qend, rb.t2_kv0, rb.t2_kvend)]
-    k2 = [dev(x) for x in (rb.k2_kv0, rb.k2_kvend, rb.k2_q0, rb.k2_qend)]
+    k2 = [dev(x) for x in (rb.k2_kv0, rb.k2_kvend, rb.k2_q0, rb.k2_qend, rb.k2_order)]
     fp = torch.zeros(8, device = 'cuda'); z = torch.zeros(64, device = 'cuda')
     ops.attn_fast_params(z, z, 64, scale, cap, fp)
     o = torch.zeros(M, H * 64, device = 'cuda', dtype = torch.bfloat16); lse = torch.zeros(H, M, device = 'cuda')

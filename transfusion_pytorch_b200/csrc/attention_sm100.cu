@@ -253,7 +253,7 @@ attn_fwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 // The dQ read-out of tile i-1 is software-pipelined behind the softmax of tile i, and S/dP of tile i+1 are issued as soon as
 // the softmax warps have pulled tile i out of TMEM, so the CUDA cores (the bound of this kernel) never wait for the tensor core.
 constexpr int FB_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
-constexpr int FB_SMEM = 16384 * 2 /*K,V*/ + 32768 * 2 /*Q,dO x2*/ + 32768 * 3 /*P, dS, dQ*/ + 1024 + 256;
+constexpr int FB_SMEM = 32768 * 2 /*K,V x2*/ + 32768 * 2 /*Q,dO x2*/ + 32768 * 3 /*P, dS, dQ*/ + 1024 + 256;
 
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -264,38 +264,55 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Work item of the persistent backward kernel: (128-key tile, head).  Items are dealt to the CTAs in snake order over a list sorted by
+// the number of query tiles that see the key tile (heaviest first).
+struct FbItem { int kv0, kv_end, q_begin, q_end, n_q, head; };
+
+__device__ __forceinline__ bool fb_item(int k, int n_items, int H, const int* __restrict__ order, const int* __restrict__ kt_kv0, const int* __restrict__ kt_kvend,
+                                        const int* __restrict__ kt_q0, const int* __restrict__ kt_qend, FbItem& it) {
+  const int G = gridDim.x;
+  const int pos = (k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x;      // snake: odd stripes run backwards
+  const int idx = k * G + pos;
+  if (idx >= n_items) return false;
+  const int t = idx / H;
+  const int tile = order ? order[t] : t;
+  it.head = idx - t * H;
+  it.kv0 = kt_kv0[tile]; it.kv_end = kt_kvend[tile]; it.q_begin = kt_q0[tile]; it.q_end = kt_qend[tile];
+  it.n_q = (it.q_end - it.q_begin + FA_BM - 1) / FA_BM;
+  return true;
+}
+
+// PERSISTENT: one CTA per SM walks its share of the (key tile, head) items; TMEM, the mbarriers and the tensor-map prefetch are set up once,
+// K / V are double-buffered so the next item's tiles (and its first Q / dO tile) arrive while the current item drains.  Measured with
+// tools/bench_attn.py variants: ~6 us of per-CTA fixed cost (launch, TMEM alloc, first-load latency, epilogue, teardown) x 13.8 CTAs per SM.
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
               const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
               const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_limit,
               const int* __restrict__ kt_kv0, const int* __restrict__ kt_kvend, const int* __restrict__ kt_q0, const int* __restrict__ kt_qend,
+              const int* __restrict__ kt_order, int n_items,
               float* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long ld_dv, int M, int H, float scale, float cap, const float* __restrict__ fast) {
   if (fast[0] == 0.f) return;
   extern __shared__ uint8_t fb_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fb_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + 16384;
-  uint8_t* sQ = smem + 32768;                        // [2][16 KB]
-  uint8_t* sDO = smem + 65536;                       // [2][16 KB]
-  uint8_t* sP = smem + 98304;                        // [2 key blocks][128 rows][128 B]
-  uint8_t* sDS = smem + 131072;
-  uint8_t* sDQ = smem + 163840;                      // [2 column halves][128 rows][128 B] fp32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 196608);
-  uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *sdp_full = bars + 5, *s_free = bars + 6, *pds_full = bars + 7,
-           *pds_empty = bars + 8, *dq_full = bars + 9, *dq_free = bars + 10, *dkv_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-
-  const int tile = blockIdx.x, head = blockIdx.y;
+  uint8_t* sK = smem;                                // [2][16 KB]
+  uint8_t* sV = smem + 32768;                        // [2][16 KB]
+  uint8_t* sQ = smem + 65536;                        // [2][16 KB]
+  uint8_t* sDO = smem + 98304;                       // [2][16 KB]
+  uint8_t* sP = smem + 131072;                       // [2 key blocks][128 rows][128 B]
+  uint8_t* sDS = smem + 163840;
+  uint8_t* sDQ = smem + 196608;                      // [2 column halves][128 rows][128 B] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 229376);
+  uint64_t *kv_full = bars /*[2]*/, *kv_empty = bars + 2 /*[2]*/, *qdo_full = bars + 4 /*[2]*/, *qdo_empty = bars + 6 /*[2]*/, *sdp_full = bars + 8, *s_free = bars + 9,
+           *pds_full = bars + 10, *pds_empty = bars + 11, *dq_full = bars + 12, *dq_free = bars + 13, *dkv_full = bars + 14, *dkv_free = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = kt_kv0[tile], kv_end = kt_kvend[tile], q_begin = kt_q0[tile], q_end = kt_qend[tile];
-  const int n_q = (q_end - q_begin + FA_BM - 1) / FA_BM;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
-    mbar_init(kv_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&qdo_full[b], 1); mbar_init(&qdo_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&kv_full[b], 1); mbar_init(&kv_empty[b], 1); mbar_init(&qdo_full[b], 1); mbar_init(&qdo_empty[b], 1); }
     mbar_init(sdp_full, 1); mbar_init(s_free, 8); mbar_init(pds_full, 8); mbar_init(pds_empty, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_free, 8); mbar_init(dkv_full, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 8); mbar_init(dkv_full, 1); mbar_init(dkv_free, 8);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -306,64 +323,84 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
   if (warp == 0) {
+    // ===================================================== TMA producer
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 32768);
-      tma_load_2d(&tmK, kv_full, sK, head * 64, kv0);
-      tma_load_2d(&tmV, kv_full, sV, head * 64, kv0);
-      for (int it = 0; it < n_q; ++it) {
-        const int b = it & 1;
-        mbar_wait(&qdo_empty[b], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&qdo_full[b], 32768);
-        tma_load_2d(&tmQ, &qdo_full[b], sQ + b * 16384, head * 64, q_begin + it * FA_BM);
-        tma_load_2d(&tmDO, &qdo_full[b], sDO + b * 16384, head * 64, q_begin + it * FA_BM);
+      FbItem it;
+      uint32_t g = 0;                                 // query-tile steps across all items (Q / dO ring)
+      for (int k = 0; fb_item(k, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, it); ++k) {
+        const int kb = k & 1;
+        mbar_wait(&kv_empty[kb], ((k >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[kb], 32768);
+        tma_load_2d(&tmK, &kv_full[kb], sK + kb * 16384, it.head * 64, it.kv0);
+        tma_load_2d(&tmV, &kv_full[kb], sV + kb * 16384, it.head * 64, it.kv0);
+        for (int i = 0; i < it.n_q; ++i, ++g) {
+          const int b = g & 1;
+          mbar_wait(&qdo_empty[b], ((g >> 1) & 1) ^ 1);
+          mbar_expect_tx(&qdo_full[b], 32768);
+          tma_load_2d(&tmQ, &qdo_full[b], sQ + b * 16384, it.head * 64, it.q_begin + i * FA_BM);
+          tma_load_2d(&tmDO, &qdo_full[b], sDO + b * 16384, it.head * 64, it.q_begin + i * FA_BM);
+        }
       }
     }
   } else if (warp == 1) {
+    // ===================================================== MMA issuer: S / dP run one query tile ahead of dV / dK / dQ (also across items)
     if (lane == 0) {
       constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);       // S, dP: A, B K-major
       constexpr uint32_t idT = umma_idesc_bf16(128, 64, 1, 1);        // dV, dK: A (P^T / dS^T) MN-major, B (dO / Q) MN-major
       constexpr uint32_t idQ = umma_idesc_bf16(128, 64, 0, 1);        // dQ: A (dS) K-major, B (K) MN-major
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sDS);
-      auto issue_S_dP = [&](int b) {
-        const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tS, umma_smem_desc_sw128(aQ + k * 32, 0, 1024), umma_smem_desc_sw128(aK + k * 32, 0, 1024), idS, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tDP, umma_smem_desc_sw128(aDO + k * 32, 0, 1024), umma_smem_desc_sw128(aV + k * 32, 0, 1024), idS, k > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
-      };
-      mbar_wait(kv_full, 0);
-      mbar_wait(&qdo_full[0], 0);
-      tc_fence_after();
-      issue_S_dP(0);
-      for (int it = 0; it < n_q; ++it) {
-        const int b = it & 1;
-        if (it + 1 < n_q) {
-          mbar_wait(&qdo_full[b ^ 1], ((it + 1) >> 1) & 1);
-          mbar_wait(s_free, it & 1);                 // softmax warps have pulled S / dP of tile `it` out of TMEM
-          tc_fence_after();
-          issue_S_dP(b ^ 1);
-        }
-        mbar_wait(pds_full, it & 1);
+      const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
+      FbItem ia, ib;
+      int ka = 0, ia_i = 0, kb_ = 0, ib_i = 0;       // cursor A = (item ka, query tile ia_i) for S / dP; cursor B for the gradient products
+      uint32_t ga = 0, gb = 0;
+      bool has_a = fb_item(0, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, ia);
+      ib = ia;
+      bool has_b = has_a;
+      auto issue_S_dP = [&]() {
+        const int b = ga & 1, kvb = ka & 1;
+        if (ia_i == 0) mbar_wait(&kv_full[kvb], (ka >> 1) & 1);
+        mbar_wait(&qdo_full[b], (ga >> 1) & 1);
+        if (ga >= 1) mbar_wait(s_free, (ga - 1) & 1);            // the softmax warps have pulled S / dP of the previous step out of TMEM
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384);
+        const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384), aK = smem_u32(sK + kvb * 16384), aV = smem_u32(sV + kvb * 16384);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tS, umma_smem_desc_sw128(aQ + kk * 32, 0, 1024), umma_smem_desc_sw128(aK + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tDP, umma_smem_desc_sw128(aDO + kk * 32, 0, 1024), umma_smem_desc_sw128(aV + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+        ++ga;
+        if (++ia_i == ia.n_q) { ia_i = 0; ++ka; has_a = fb_item(ka, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, ia); }
+      };
+      if (has_a) issue_S_dP();
+      while (has_b) {
+        if (has_a) issue_S_dP();
+        const int b = gb & 1, kvb = kb_ & 1;
+        mbar_wait(pds_full, gb & 1);
+        if (ib_i == 0 && kb_ >= 1) mbar_wait(dkv_free, (kb_ - 1) & 1);     // the previous item's dK / dV have been read out of TMEM
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384), aK = smem_u32(sK + kvb * 16384);
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq)               // dV += P^T dO : contraction over the 128 queries
-          umma_bf16_ss(tDV, umma_smem_desc_sw128(aP + kq * 2048, 16384, 1024), umma_smem_desc_sw128(aDO + kq * 2048, 8192, 1024), idT, (it > 0 || kq > 0) ? 1u : 0u);
+          umma_bf16_ss(tDV, umma_smem_desc_sw128(aP + kq * 2048, 16384, 1024), umma_smem_desc_sw128(aDO + kq * 2048, 8192, 1024), idT, (ib_i > 0 || kq > 0) ? 1u : 0u);
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq)               // dK += dS^T Q
-          umma_bf16_ss(tDK, umma_smem_desc_sw128(aDS + kq * 2048, 16384, 1024), umma_smem_desc_sw128(aQ + kq * 2048, 8192, 1024), idT, (it > 0 || kq > 0) ? 1u : 0u);
-        if (it > 0) { mbar_wait(dq_free, (it - 1) & 1); tc_fence_after(); }
+          umma_bf16_ss(tDK, umma_smem_desc_sw128(aDS + kq * 2048, 16384, 1024), umma_smem_desc_sw128(aQ + kq * 2048, 8192, 1024), idT, (ib_i > 0 || kq > 0) ? 1u : 0u);
+        if (gb >= 1) { mbar_wait(dq_free, (gb - 1) & 1); tc_fence_after(); }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)               // dQ = dS K : contraction over the 128 keys
           umma_bf16_ss(tDQ, umma_smem_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024), umma_smem_desc_sw128(aK + kk * 2048, 8192, 1024), idQ, kk > 0 ? 1u : 0u);
         umma_commit(&qdo_empty[b]);
         umma_commit(pds_empty);
         umma_commit(dq_full);
+        ++gb;
+        if (++ib_i == ib.n_q) {
+          umma_commit(dkv_full);                     // dK / dV of this item are complete
+          umma_commit(&kv_empty[kvb]);               // ... and its K / V tiles are free
+          ib_i = 0; ++kb_;
+          has_b = fb_item(kb_, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, ib);
+        }
       }
-      umma_commit(dkv_full);
     }
   } else {
     // ===================================================== softmax / gradient warps
@@ -379,13 +416,13 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const float oms_c = -scale / (KL * KL);          // scale * (1 - tanh^2) = fma(e2^2, oms_c, scale)
     const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), A3 = make_float2(a3, a3), A4 = make_float2(a4, a4),
                  OC = make_float2(oms_c, oms_c), SC = make_float2(scale, scale);
-    const float* lse_h = lse + (long long)head * M;
-    const float* ds_h = dsum + (long long)head * M;
     const int swz_row = (row >> 3) * 1024 + (row & 7) * 128;
     const bool elected = (warp == 2 && lane == 0);
+    uint32_t g = 0;                                  // query-tile steps across all items
 
-    auto dq_readout = [&](int it_done) {             // dQ of query tile `it_done`: TMEM -> smem -> TMA reduce-add into global
-      mbar_wait(dq_full, it_done & 1);
+    // dQ of step g_done (query rows starting at qrow0, head hd): TMEM -> smem -> TMA reduce-add into global
+    auto dq_readout = [&](uint32_t g_done, int qrow0, int hd) {
+      mbar_wait(dq_full, g_done & 1);
       tc_fence_after();
       if (elected) bulk_wait_read0();                // the previous reduce has finished reading sDQ
       softmax_bar();
@@ -402,105 +439,114 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       fence_proxy_async_smem();
       softmax_bar();
       if (elected) {
-        const int qrow0 = q_begin + it_done * FA_BM;
-        tma_reduce_add_2d(&tmDQ, sDQ, head * 64, qrow0);
-        tma_reduce_add_2d(&tmDQ, sDQ + 16384, head * 64 + 32, qrow0);
+        tma_reduce_add_2d(&tmDQ, sDQ, hd * 64, qrow0);
+        tma_reduce_add_2d(&tmDQ, sDQ + 16384, hd * 64 + 32, qrow0);
         bulk_commit();
       }
     };
 
-    // per-row metadata of the NEXT query tile is fetched while the current one is processed (global-load latency off the critical path)
+    FbItem it, nx;
+    bool has = fb_item(0, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, it);
+    // per-row metadata of the NEXT query tile (possibly of the next item) is fetched while the current one is processed
     int lim_n = -1; float lse_n = 0.f, D_n = 0.f;
-    auto fetch_row_meta = [&](int it) {
-      const int gr = q_begin + it * FA_BM + row;
-      const bool ok = it < n_q && gr < q_end;
+    auto fetch_row_meta = [&](const FbItem& im, int i) {
+      const int gr = im.q_begin + i * FA_BM + row;
+      const bool ok = gr < im.q_end;
       lim_n = ok ? kv_limit[gr] : -1;
-      lse_n = ok ? lse_h[gr] : 0.f;
-      D_n = ok ? ds_h[gr] : 0.f;
+      lse_n = ok ? lse[(long long)im.head * M + gr] : 0.f;
+      D_n = ok ? dsum[(long long)im.head * M + gr] : 0.f;
     };
-    fetch_row_meta(0);
-    for (int it = 0; it < n_q; ++it) {
-      const int lim = lim_n;
-      const float lse2 = lse_n * 1.4426950408889634f;
-      const float Dr = D_n;
-      fetch_row_meta(it + 1);
-      const bool all_visible = __all_sync(0xffffffffu, kv0 + FA_BN - 1 <= lim);
-      const float2 NL = make_float2(-lse2, -lse2), ND = make_float2(-Dr, -Dr);
-      mbar_wait(sdp_full, it & 1);
-      tc_fence_after();
+    if (has) fetch_row_meta(it, 0);
+    int prev_qrow0 = 0, prev_head = 0;               // pending dQ read-out (software-pipelined one step behind, also across items)
+    bool pending = false;
+    for (int k = 0; has; ++k) {
+      const bool has_n = fb_item(k + 1, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, nx);
+      const int kv0 = it.kv0;
+      for (int i = 0; i < it.n_q; ++i, ++g) {
+        const int lim = lim_n;
+        const float lse2 = lse_n * 1.4426950408889634f;
+        const float Dr = D_n;
+        if (i + 1 < it.n_q) fetch_row_meta(it, i + 1); else if (has_n) fetch_row_meta(nx, 0);
+        const bool all_visible = __all_sync(0xffffffffu, kv0 + FA_BN - 1 <= lim);
+        const float2 NL = make_float2(-lse2, -lse2), ND = make_float2(-Dr, -Dr);
+        mbar_wait(sdp_full, g & 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32b_x32(tS + lane_addr + hf * 64 + c * 32, rs);
-        tmem_ld_32x32b_x32(tDP + lane_addr + hf * 64 + c * 32, rp);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t rs[32], rp[32];
+          tmem_ld_32x32b_x32(tS + lane_addr + hf * 64 + c * 32, rs);
+          tmem_ld_32x32b_x32(tDP + lane_addr + hf * 64 + c * 32, rp);
+          tmem_ld_wait();
+          if (c == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+          }
+          uint32_t wp[16], wd[16];
+          const int kbase = kv0 + hf * 64 + c * 32;
+#pragma unroll
+          for (int e2 = 0; e2 < 32; e2 += 2) {       // packed fp32x2 FMAs (FFMA2): two scores per instruction
+            const float2 x = make_float2(__uint_as_float(rs[e2]), __uint_as_float(rs[e2 + 1]));
+            const float2 X = __fmul2_rn(x, x);
+            float2 gp = __ffma2_rn(A4, X, A3);
+            gp = __ffma2_rn(gp, X, A2);
+            gp = __ffma2_rn(gp, X, A1);
+            gp = __ffma2_rn(gp, X, A0);
+            const float2 e = __fmul2_rn(x, gp);                       // cap * log2e * tanh(y)
+            const float2 pe = __fadd2_rn(e, NL);
+            float p0 = ex2_approx(pe.x), p1 = ex2_approx(pe.y);
+            if (!all_visible) { p0 = (kbase + e2 <= lim) ? p0 : 0.f; p1 = (kbase + e2 + 1 <= lim) ? p1 : 0.f; }
+            const float2 oms = __ffma2_rn(__fmul2_rn(e, e), OC, SC);  // scale * (1 - tanh^2)
+            const float2 dpd = __fadd2_rn(make_float2(__uint_as_float(rp[e2]), __uint_as_float(rp[e2 + 1])), ND);
+            const float2 d = __fmul2_rn(__fmul2_rn(make_float2(p0, p1), dpd), oms);
+            wp[e2 >> 1] = pack_bf16(p0, p1);
+            wd[e2 >> 1] = pack_bf16(d.x, d.y);
+          }
+          if (c == 0 && g > 0) mbar_wait(pds_empty, (g - 1) & 1);     // dV / dK / dQ MMAs of the previous step have consumed P, dS
+          uint8_t* pb = sP + hf * 16384 + swz_row;
+          uint8_t* db = sDS + hf * 16384 + swz_row;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const int sw = ((c * 4 + qd) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(pb + sw) = make_uint4(wp[4 * qd], wp[4 * qd + 1], wp[4 * qd + 2], wp[4 * qd + 3]);
+            *reinterpret_cast<uint4*>(db + sw) = make_uint4(wd[4 * qd], wd[4 * qd + 1], wd[4 * qd + 2], wd[4 * qd + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
+        prev_qrow0 = it.q_begin + i * FA_BM; prev_head = it.head; pending = true;
+      }
+      // ---- dK (fp32) and dV (bf16) of this key tile
+      mbar_wait(dkv_full, k & 1);
+      tc_fence_after();
+      const int key = kv0 + row;
+      {
+        uint32_t r[32], r2[32];
+        tmem_ld_32x32b_x32(tDK + lane_addr + hf * 32, r);
+        tmem_ld_32x32b_x32(tDV + lane_addr + hf * 32, r2);
         tmem_ld_wait();
-        if (c == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free);
-        }
-        uint32_t wp[16], wd[16];
-        const int kbase = kv0 + hf * 64 + c * 32;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_free);        // the accumulators may be overwritten by the next item
+        if (key < it.kv_end) {
+          float* dst = dk + (long long)key * H * 64 + it.head * 64 + hf * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {           // packed fp32x2 FMAs (FFMA2): two scores per instruction
-          const float2 x = make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1]));
-          const float2 X = __fmul2_rn(x, x);
-          float2 g = __ffma2_rn(A4, X, A3);
-          g = __ffma2_rn(g, X, A2);
-          g = __ffma2_rn(g, X, A1);
-          g = __ffma2_rn(g, X, A0);
-          const float2 e = __fmul2_rn(x, g);                        // cap * log2e * tanh(y)
-          const float2 pe = __fadd2_rn(e, NL);
-          float p0 = ex2_approx(pe.x), p1 = ex2_approx(pe.y);
-          if (!all_visible) { p0 = (kbase + i <= lim) ? p0 : 0.f; p1 = (kbase + i + 1 <= lim) ? p1 : 0.f; }
-          const float2 oms = __ffma2_rn(__fmul2_rn(e, e), OC, SC);  // scale * (1 - tanh^2)
-          const float2 dpd = __fadd2_rn(make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), ND);
-          const float2 d = __fmul2_rn(__fmul2_rn(make_float2(p0, p1), dpd), oms);
-          wp[i >> 1] = pack_bf16(p0, p1);
-          wd[i >> 1] = pack_bf16(d.x, d.y);
-        }
-        if (c == 0 && it > 0) mbar_wait(pds_empty, (it - 1) & 1);     // dV / dK / dQ MMAs of the previous tile have consumed P, dS
-        uint8_t* pb = sP + hf * 16384 + swz_row;
-        uint8_t* db = sDS + hf * 16384 + swz_row;
+          for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * 4) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+          __nv_bfloat16* dst2 = dv + (long long)key * ld_dv + it.head * 64 + hf * 32;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          const int sw = ((c * 4 + qd) ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(pb + sw) = make_uint4(wp[4 * qd], wp[4 * qd + 1], wp[4 * qd + 2], wp[4 * qd + 3]);
-          *reinterpret_cast<uint4*>(db + sw) = make_uint4(wd[4 * qd], wd[4 * qd + 1], wd[4 * qd + 2], wd[4 * qd + 3]);
+          for (int qd = 0; qd < 4; ++qd) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(r2[qd * 8 + 2 * e]), __uint_as_float(r2[qd * 8 + 2 * e + 1]));
+            *reinterpret_cast<uint4*>(dst2 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      if (it > 0) dq_readout(it - 1);
+      it = nx; has = has_n;
     }
-    dq_readout(n_q - 1);
-    // ---- dK (fp32) and dV (bf16) of this key tile
-    mbar_wait(dkv_full, 0);
-    tc_fence_after();
-    const int key = kv0 + row;
-    {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tDK + lane_addr + hf * 32, r);
-      tmem_ld_wait();
-      if (key < kv_end) {
-        float* dst = dk + (long long)key * H * 64 + head * 64 + hf * 32;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * 4) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
-      }
-      tmem_ld_32x32b_x32(tDV + lane_addr + hf * 32, r);
-      tmem_ld_wait();
-      if (key < kv_end) {
-        __nv_bfloat16* dst = dv + (long long)key * ld_dv + head * 64 + hf * 32;
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(r[qd * 8 + 2 * e]), __uint_as_float(r[qd * 8 + 2 * e + 1]));
-          *reinterpret_cast<uint4*>(dst + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-    }
+    if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
     if (elected) bulk_wait0();                       // all dQ reductions have been performed before the CTA retires
   }
 
@@ -560,7 +606,8 @@ int tfx_attn_fwd_tc(const void* q, const void* k, const void* v, long long ld_q,
 
 int tfx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
                     const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
-                    int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* fast_params, void* stream) {
+                    const int* kt_order, int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* fast_params,
+                    void* stream) {
   if (n_kv_tiles <= 0) return 0;
   TFX_REQUIRE(fast_params != nullptr, "attn_bwd_tc: fast_params (from tfx_attn_fast_params) is required");
   TFX_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_do % 8 == 0 && ld_dv % 8 == 0, "attn_bwd_tc: row pitches must be multiples of 8 bf16");
@@ -577,8 +624,10 @@ int tfx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* do_
     if (cudaFuncSetAttribute(attn_bwd_tc_k, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM) != cudaSuccess) { set_error("attn_bwd_tc: cannot raise dynamic smem"); return -2; }
     attr_set = true;
   }
-  attn_bwd_tc_k<<<dim3(n_kv_tiles, H), FB_THREADS, FB_SMEM, ST(stream)>>>(tq, tk, tv, tdo, tdq, lse, dsum_hm, kv_limit, kt_kv0, kt_kvend, kt_q0, kt_qend, dk, (__nv_bfloat16*)dv,
-                                                                         ld_dv, M, H, scale, softcap, fast_params);
+  const int n_items = n_kv_tiles * H;
+  const int grid = n_items < num_sms() ? n_items : num_sms();          // persistent: one CTA per SM
+  attn_bwd_tc_k<<<grid, FB_THREADS, FB_SMEM, ST(stream)>>>(tq, tk, tv, tdo, tdq, lse, dsum_hm, kv_limit, kt_kv0, kt_kvend, kt_q0, kt_qend, kt_order, n_items, dk,
+                                                          (__nv_bfloat16*)dv, ld_dv, M, H, scale, softcap, fast_params);
   return check_launch("attn_bwd_tc");
 }
 

@@ -244,9 +244,9 @@ class Engine:
         if rb.dev:
             return rb.dev
         ints = [rb.text_id, rb.label, rb.kv_limit, rb.rope_pos, rb.cond_row, rb.slot, rb.tile_q0, rb.tile_qend, rb.tile_kv0, rb.tile_kvend,
-                rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend, rb.row_token, rb.t2_q0, rb.t2_qend, rb.t2_kv0, rb.t2_kvend, rb.k2_kv0, rb.k2_kvend, rb.k2_q0, rb.k2_qend]
+                rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend, rb.row_token, rb.t2_q0, rb.t2_qend, rb.t2_kv0, rb.t2_kvend, rb.k2_kv0, rb.k2_kvend, rb.k2_q0, rb.k2_qend, rb.k2_order]
         names = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
-                 'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend']
+                 'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order']
         sizes = [_round_up(a.shape[0], 4) for a in ints]
         fl = np.concatenate([rb.cond_times, rb.row_time]).astype(np.float32)
         n_int, n_fl = sum(sizes), _round_up(fl.shape[0], 4)
@@ -606,7 +606,7 @@ class Engine:
                 dqkvg.zero_(); self.ws['dqkvg_shape'] = (M, self.NQ)
             fp = self.fastp[i]
             o.attn_bwd_tc(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['k2_kv0'], dv['k2_kvend'], dv['k2_q0'], dv['k2_qend'],
-                          int(rb.k2_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
+                          dv['k2_order'], int(rb.k2_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
             o.attn_bwd(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['kt_kv0'], dv['kt_kvend'], dv['kt_q0'], dv['kt_qend'],
                        int(rb.kt_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
             o.qk_bwd_pack(dq, dk, L['q'], L['k'], L['qk_inv'], self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'), dv['rope_pos'],

@@ -90,6 +90,7 @@ class RaggedBatch:
     k2_kvend: np.ndarray = None
     k2_q0: np.ndarray = None
     k2_qend: np.ndarray = None
+    k2_order: np.ndarray = None             # 128-key tiles sorted by the number of query tiles that see them (persistent attention backward)
     max_rope_pos: int = 0
     has_labels: bool = False
     n_valid: int = 0
@@ -124,6 +125,7 @@ def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
             z = np.zeros(0, dtype = np.int32)
             for name in (f'{pre_q}_q0', f'{pre_q}_qend', f'{pre_q}_kv0', f'{pre_q}_kvend', f'{pre_k}_kv0', f'{pre_k}_kvend', f'{pre_k}_q0', f'{pre_k}_qend'):
                 setattr(rb, name, z)
+            rb.k2_order = z
             continue
         seq = np.repeat(np.arange(rb.B), ntiles)                         # sequence of every tile
         first = np.cumsum(ntiles) - ntiles                               # index of the first tile of each sequence
@@ -137,6 +139,8 @@ def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
         for name, arr in ((f'{pre_q}_q0', q0), (f'{pre_q}_qend', qe), (f'{pre_q}_kv0', s), (f'{pre_q}_kvend', kve),
                           (f'{pre_k}_kv0', q0), (f'{pre_k}_kvend', qe), (f'{pre_k}_q0', kq0), (f'{pre_k}_qend', s + lens[seq])):
             setattr(rb, name, as32(arr))
+        if pre_k == 'k2':
+            rb.k2_order = as32(np.argsort(-(s + lens[seq] - kq0), kind = 'stable'))
 
 
 def pack_batch(

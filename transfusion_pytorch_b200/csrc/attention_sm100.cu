@@ -362,12 +362,17 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (ga >= 1) mbar_wait(s_free, (ga - 1) & 1);            // the softmax warps have pulled S / dP of the previous step out of TMEM
         tc_fence_after();
         const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384), aK = smem_u32(sK + kvb * 16384), aV = smem_u32(sV + kvb * 16384);
+#if defined(FB_VARIANT) && (FB_VARIANT == 4 || FB_VARIANT == 5)
+        if (fast[0] == 123.f)
+#endif
+        {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_ss(tS, umma_smem_desc_sw128(aQ + kk * 32, 0, 1024), umma_smem_desc_sw128(aK + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_ss(tDP, umma_smem_desc_sw128(aDO + kk * 32, 0, 1024), umma_smem_desc_sw128(aV + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
+        }
         umma_commit(sdp_full);
         ++ga;
         if (++ia_i == ia.n_q) { ia_i = 0; ++ka; has_a = fb_item(ka, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, ia); }
@@ -380,6 +385,11 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (ib_i == 0 && kb_ >= 1) mbar_wait(dkv_free, (kb_ - 1) & 1);     // the previous item's dK / dV have been read out of TMEM
         tc_fence_after();
         const uint32_t aQ = smem_u32(sQ + b * 16384), aDO = smem_u32(sDO + b * 16384), aK = smem_u32(sK + kvb * 16384);
+#if defined(FB_VARIANT) && (FB_VARIANT == 3 || FB_VARIANT == 5)
+        if (fast[0] == 123.f) {
+#else
+        {
+#endif
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq)               // dV += P^T dO : contraction over the 128 queries
           umma_bf16_ss(tDV, umma_smem_desc_sw128(aP + kq * 2048, 16384, 1024), umma_smem_desc_sw128(aDO + kq * 2048, 8192, 1024), idT, (ib_i > 0 || kq > 0) ? 1u : 0u);
@@ -390,6 +400,7 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)               // dQ = dS K : contraction over the 128 keys
           umma_bf16_ss(tDQ, umma_smem_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024), umma_smem_desc_sw128(aK + kk * 2048, 8192, 1024), idQ, kk > 0 ? 1u : 0u);
+        }
         umma_commit(&qdo_empty[b]);
         umma_commit(pds_empty);
         umma_commit(dq_full);
@@ -427,17 +438,26 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       if (elected) bulk_wait_read0();                // the previous reduce has finished reading sDQ
       softmax_bar();
       uint32_t r[32];
+#if defined(FB_VARIANT) && (FB_VARIANT == 2 || FB_VARIANT == 5)
+      for (int i = 0; i < 32; ++i) r[i] = 0;
+#else
       tmem_ld_32x32b_x32(tDQ + lane_addr + hf * 32, r);
       tmem_ld_wait();
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
       uint8_t* dst = sDQ + hf * 16384 + swz_row;
+#if !(defined(FB_VARIANT) && (FB_VARIANT == 2 || FB_VARIANT == 5))
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
         *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
       fence_proxy_async_smem();
+#endif
       softmax_bar();
+#if defined(FB_VARIANT) && (FB_VARIANT == 2 || FB_VARIANT == 5)
+      if (false)
+#endif
       if (elected) {
         tma_reduce_add_2d(&tmDQ, sDQ, hd * 64, qrow0);
         tma_reduce_add_2d(&tmDQ, sDQ + 16384, hd * 64 + 32, qrow0);
@@ -484,6 +504,11 @@ attn_bwd_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
           uint32_t wp[16], wd[16];
           const int kbase = kv0 + hf * 64 + c * 32;
+#if defined(FB_VARIANT) && (FB_VARIANT == 1 || FB_VARIANT == 5)
+#pragma unroll
+          for (int e2 = 0; e2 < 16; ++e2) { wp[e2] = rs[2 * e2] ^ rs[2 * e2 + 1]; wd[e2] = rp[2 * e2] ^ rp[2 * e2 + 1]; }
+          if (false)
+#endif
 #pragma unroll
           for (int e2 = 0; e2 < 32; e2 += 2) {       // packed fp32x2 FMAs (FFMA2): two scores per instruction
             const float2 x = make_float2(__uint_as_float(rs[e2]), __uint_as_float(rs[e2 + 1]));

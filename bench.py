@@ -150,7 +150,7 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     from transfusion_pytorch_b200 import Transfusion, synth
-    from transfusion_pytorch_b200.data_parallel import DataParallelTrainer
+    from transfusion_pytorch_b200.data_parallel import DataParallelTrainer, AsyncScalar
     from transfusion_pytorch_b200.modality_processing import pack_batch
 
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -166,7 +166,7 @@ def run_b200_arm(args):
     model = Transfusion(**CTOR).to(dev)                      # prob_uncond = 0.1 (reference default), train mode
     synth.fill_parameters_(model, seed = 0)
     model.train()
-    trainer = DataParallelTrainer(model, lr = 1e-4)
+    trainer = DataParallelTrainer(model, lr = 1e-4, cuda_graph = not args.no_graph)
     eng = model.engine
     eng.ensure_attached()
 
@@ -188,6 +188,8 @@ def run_b200_arm(args):
 
     def step_resident(i):
         rb, lat = packed[i % POOL]
+        if world == 1 and not args.no_graph and eng.ops.timing is None:
+            return trainer.step_packed(rb, lat)              # CUDA-graph replay of the step (after two eager steps of this shape)
         eng.zero_grad()
         loss = model.forward_packed(rb, lat)
         if world > 1 and trainer.overlap:
@@ -260,20 +262,23 @@ def run_b200_arm(args):
     # runs on the device, so the host packs step i+1 instead of idling); the last loss is read before the timed region closes.
     h2d = [0]
     pending = [None]
+    host_e2e = []
     def step_e2e(i):
         b, t = host_batches[i % POOL], host_times[i % POOL]
+        t_h = time.perf_counter()
         loss = trainer.step(b, times = t)
+        host_e2e.append(1e3 * (time.perf_counter() - t_h))
         rb = model._last_batch
         h2d[0] = rb.dev.get('h2d_bytes', 0) + getattr(rb, 'latent_h2d_bytes', 0)
-        prev, pending[0] = pending[0], loss
-        return prev.item() if prev is not None else None     # D2H read of a loss every step
+        prev, pending[0] = pending[0], AsyncScalar(loss)      # D2H copy of this step's loss, on a side stream
+        return prev.value() if prev is not None else None    # ... read one step later: waits for step i-1 only
     def e2e_loop(i):
         step_e2e(i)
         if i == e2e_loop.last:
-            pending[0].item(); pending[0] = None               # drain: the final step's loss is read inside the timed region too
+            pending[0].value(); pending[0] = None              # drain: the final step's loss is read inside the timed region too
     for i in range(min(args.warmup, 3)):
         step_e2e(i)
-    pending[0].item(); pending[0] = None
+    pending[0].value(); pending[0] = None
     e2e_steps = max(3, min(args.steps, 10))
     e2e_loop.last = e2e_steps - 1
     ms_e2e = timed(e2e_loop, e2e_steps) / e2e_steps
@@ -316,9 +321,10 @@ def run_b200_arm(args):
         line = dict(metric = METRIC, value = value, unit = 'tokens/s', n_gpus = world, steps = args.steps, warmup = args.warmup, ms_per_step = ms_step, higher_is_better = True,
                     scaling = 'weak', vs_baseline = None, dtype = 'bf16', data = 'synthetic',
                     config = dict(workload = 'configs[1]: single-modality text+latent d=512 depth=8 dim_latent=384 seq=1024', global_batch = world * B, per_gpu_batch = B,
-                                  seq_len = SEQ, parallelism = f'dp{world}', optimizer = 'fused Adam', l2 = 'per-step working set (>10 GB of activations) is far larger than the 126 MB L2; 4 rotating input batches'),
+                                  seq_len = SEQ, parallelism = f'dp{world}', optimizer = 'fused Adam', launch = 'cuda graph replay' if (world == 1 and not args.no_graph) else 'eager', l2 = 'per-step working set (>10 GB of activations) is far larger than the 126 MB L2; 4 rotating input batches'),
                     e2e = dict(value = e2e_value, unit = 'tokens/s', ms_per_step = ms_e2e, h2d_bytes_per_step = int(h2d[0]), d2h_bytes_per_step = 4,
-                               loss_read = 'every step, deferred by one step (asynchronous logging)'),
+                               loss_read = 'every step, deferred by one step (asynchronous logging)',
+                               host_ms_per_step = round(sum(host_e2e[-e2e_steps:]) / e2e_steps, 3)),
                     gpu_launches = int(launches), host_enqueue_ms_per_step = round(host_enqueue_ms, 3), clocks = clocks, roofline = roof, cpu_baseline = cpu)
         print(json.dumps(line))
     if world > 1:
@@ -333,6 +339,7 @@ def main():
     ap.add_argument('--batch', type = int, default = 32, help = 'sequences (x1024 tokens) per GPU per step')
     ap.add_argument('--impl', default = 'b200', choices = ['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action = 'store_true')
+    ap.add_argument('--no-graph', action = 'store_true', help = 'eager kernel launches instead of CUDA-graph replay (N = 1)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

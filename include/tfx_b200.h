@@ -150,7 +150,9 @@ int tfx_axpy_f32(float* y, const float* x, float a, long long n, void* stream); 
 int tfx_rope_table(const float* freqs, float* cos_sin, float* cos_sin_t, int max_pos, int n_freqs, void* stream);
 /* fused Adam / AdamW over the flat parameter buffer (the optimizer the reference's examples use, train_latent_with_text.py:142-153) */
 int tfx_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                  int decoupled_wd, int step, float grad_scale, int zero_grads /* 1: clear grads in the same pass */, void* stream);
+                  int decoupled_wd, int step, float grad_scale, int zero_grads /* 1: clear grads in the same pass */,
+                  int* step_dev /* optional device-resident step counter (incremented here; bias corrections computed on the device - CUDA-graph safe) */,
+                  void* stream);
 
 #ifdef __cplusplus
 }

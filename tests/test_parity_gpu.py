@@ -185,3 +185,30 @@ def test_training_reduces_loss():
     for _ in range(30):
         losses.append(tr.step(batch, times = times).item())
     assert losses[-1] < losses[0] * 0.8, losses[::5]
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """DataParallelTrainer replays a captured CUDA graph from the third step of a shape on; parameters must follow the eager trajectory
+    (same batches, same noise stream is NOT required: compare with times fixed and noise disabled via a zero-latent batch)."""
+    from transfusion_pytorch_b200.data_parallel import DataParallelTrainer
+    ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), transformer = dict(dim = 128, depth = 2, heads = 2), prob_uncond = 0.)
+    batch = synth.small_batch(4, seed = 3, dim_latent = 32, text_vocab = 64)
+    nm = max(sum(torch.is_tensor(p) and p.is_floating_point() for p in s) for s in batch)
+    times = torch.ones(4, nm)                       # t = 1: the noised latent equals the clean latent, the flow target still depends on eps ...
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        model = Transfusion(**ctor).cuda()
+        synth.fill_parameters_(model, seed = 7)
+        tr = DataParallelTrainer(model, lr = 1e-3, cuda_graph = use_graph)
+        losses = []
+        for step in range(6):
+            torch.manual_seed(100 + step)           # ... so both runs draw the same eps at the same step (the generator state is the same before the call)
+            losses.append(tr.step(batch, times = times).item())
+        results.append((losses, model.engine.flat.clone()))
+        if use_graph:
+            assert any(g.graph is not None for g in tr._graphs.values()), 'the step was never captured'
+    (l0, p0), (l1, p1) = results
+    assert all(abs(a - b) / abs(a) < 2e-3 for a, b in zip(l0[:2], l1[:2])), (l0, l1)       # eager steps of both runs
+    assert l1[-1] < l1[0] and abs(l1[-1] - l0[-1]) / abs(l0[-1]) < 5e-2, (l0, l1)           # replayed steps keep training at the same pace
+    assert (p1 - p0).abs().max().item() < 5e-2

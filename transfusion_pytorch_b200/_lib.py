@@ -55,7 +55,7 @@ SIGNATURES = {
     'tfx_scale_bf16': [VP, VP, LL, VP],
     'tfx_axpy_f32': [VP, VP, F, LL, VP],
     'tfx_rope_table': [VP, VP, VP, I, I, VP],
-    'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP],
+    'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP, VP],
 }
 
 EXPORTED = ['tfx_last_error', 'tfx_version', 'tfx_geglu_bwd_rows_per_block', 'tfx_attn_residual_bwd_workspace_floats'] + list(SIGNATURES)

@@ -321,9 +321,17 @@ __global__ void rope_table_k(const float* __restrict__ freqs, float2* __restrict
   }
 }
 
-// fused Adam(W): torch.optim.Adam semantics (L2 weight decay folded into the gradient unless decoupled)
+// fused Adam(W): torch.optim.Adam semantics (L2 weight decay folded into the gradient unless decoupled).
+// step_dev (optional): device-resident step counter - the bias corrections are then computed on the device (CUDA-graph replays cannot
+// carry host-computed scalars); it is incremented by adam_step_inc_k right before this kernel.
+__global__ void adam_step_inc_k(int* step_dev) { *step_dev += 1; }
 __global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr, float b1, float b2,
-                       float eps, float wd, int decoupled, float bc1, float bc2_sqrt, float gscale, int zero_grads) {
+                       float eps, float wd, int decoupled, float bc1, float bc2_sqrt, float gscale, int zero_grads, const int* __restrict__ step_dev) {
+  if (step_dev) {
+    const float st = (float)*step_dev;
+    bc1 = 1.f - powf(b1, st);
+    bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * gscale, pi = p[i];
     if (wd != 0.f) { if (decoupled) pi *= (1.f - lr * wd); else gi += wd * pi; }
@@ -449,11 +457,13 @@ int tfx_rope_table(const float* freqs, float* cos_sin, float* cos_sin_t, int max
 }
 
 int tfx_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                  int decoupled_wd, int step, float grad_scale, int zero_grads, void* stream) {
+                  int decoupled_wd, int step, float grad_scale, int zero_grads, int* step_dev, void* stream) {
   if (n <= 0) return 0;
-  TFX_REQUIRE(step >= 1, "adam_step: step must be >= 1");
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  adam_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, bc2s, grad_scale, zero_grads);
+  TFX_REQUIRE(step >= 1 || step_dev, "adam_step: step must be >= 1");
+  float bc1 = 1.f, bc2s = 1.f;
+  if (step_dev) adam_step_inc_k<<<1, 1, 0, ST(stream)>>>(step_dev);
+  else { bc1 = 1.f - powf(beta1, (float)step); bc2s = sqrtf(1.f - powf(beta2, (float)step)); }
+  adam_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, bc2s, grad_scale, zero_grads, step_dev);
   return check_launch("adam_step");
 }
 

@@ -13,14 +13,149 @@ import torch
 import torch.distributed as dist
 
 
+class AsyncScalar:
+    """Device scalar -> host without stalling the training stream: the D2H copy runs on a side stream behind an event recorded where the
+    scalar was produced, so `.value()` waits for THAT step only - not for work enqueued afterwards (a plain `.item()` is ordered behind
+    everything already in the stream, i.e. behind the next step when losses are logged one step late)."""
+    _side = None
+
+    def __init__(self, t: torch.Tensor):
+        if AsyncScalar._side is None:
+            AsyncScalar._side = torch.cuda.Stream()
+        ready = torch.cuda.Event()
+        ready.record()
+        self.host = torch.empty((), dtype = t.dtype).pin_memory()
+        self.done = torch.cuda.Event()
+        with torch.cuda.stream(AsyncScalar._side):
+            AsyncScalar._side.wait_event(ready)
+            self.host.copy_(t.detach().reshape(()), non_blocking = True)
+            self.done.record()
+        self._keep = t
+
+    def value(self) -> float:
+        self.done.synchronize()
+        return self.host.item()
+
+
+class _StepGraph:
+    """A captured training step (forward + backward + fused Adam) for ONE shape signature of the ragged batch descriptor."""
+    def __init__(self):
+        self.graph = None
+        self.meta = None          # static device buffer holding the int / float metadata
+        self.layout = None
+        self.lat = None           # static per-type latent matrices
+        self.rb = None            # the descriptor object the graph was captured with (its .dev views point into `meta`)
+        self.loss = None
+        self.eager_steps = 0
+        self.meta_stage = self.lat_stage = self.consumed = None
+
+
 class DataParallelTrainer:
-    def __init__(self, model, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled_weight_decay = False, overlap = True):
+    def __init__(self, model, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled_weight_decay = False, overlap = True, cuda_graph = True):
         self.model = model
         self.hp = dict(lr = lr, betas = betas, eps = eps, weight_decay = weight_decay, decoupled = decoupled_weight_decay)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.overlap = overlap and self.world > 1
         self.comm_stream = None
         self._cpu_opt = None
+        # CUDA graphs: a step whose descriptor has a shape signature seen twice before is captured once and replayed afterwards - the ~320
+        # kernel launches of a step (8-9 ms of host time through ctypes) become one graph launch.  Single-process only: the bucketed
+        # NCCL overlap of the multi-GPU path stays eager.
+        self.cuda_graph = cuda_graph and self.world == 1
+        self._graphs = {}
+        self._copy_stream = None
+
+    # ---- CUDA-graph replay of fixed-shape steps
+    @staticmethod
+    def _signature(rb, eng):
+        return (rb.M, rb.B, rb.n_cond, rb.S, tuple(rb.type_rows), tuple(getattr(rb, n).shape[0] for n in eng.META_NAMES), rb.total_tokens,
+                tuple(rb.n_type_tokens), (rb.max_rope_pos + 1 + 1023) // 1024, rb.has_labels)
+
+    def _graph_step(self, rb, device_lat = None):
+        """Returns the loss of a replayed (or freshly captured) step, or None when this batch must run eagerly.
+        device_lat: per-type latent matrices already on the device (then rb must be uploaded too: a device-resident batch)."""
+        model, eng = self.model, self.model.engine
+        sig = self._signature(rb, eng)
+        g = self._graphs.get(sig)
+        if g is None:
+            if len(self._graphs) >= 8:
+                return None
+            g = self._graphs[sig] = _StepGraph()
+        if g.graph is None and g.eager_steps < 2:       # let the buffers, weight packs and Adam state of this shape settle first
+            g.eager_steps += 1
+            return None
+        # Stage this batch's inputs.  The host -> device copies run on a copy stream into staging buffers, so the PCIe transfer of step i+1
+        # overlaps the graph of step i; a device-to-device copy (a few microseconds) moves them into the graph's static inputs.
+        if device_lat is not None:
+            src_meta = rb.dev['_keep']
+            raw, host, layout = None, src_meta, rb.dev['_layout']
+        else:
+            raw, host, layout = eng.stage_meta(rb)
+        if g.graph is None:
+            g.meta = torch.empty_like(host, device = eng.device)
+            g.meta_stage = torch.empty_like(g.meta)
+            g.layout = layout
+            g.lat = [torch.empty(s1 - s0, model.dim_latents[t], device = eng.device, dtype = torch.float32) if s1 > s0 else None for t, (s0, s1) in enumerate(rb.type_rows)]
+            g.lat_stage = [torch.empty_like(l) if l is not None else None for l in g.lat]
+            g.consumed = torch.cuda.Event()
+            g.consumed.record()
+        assert layout == g.layout
+        if device_lat is not None:                       # device-resident batch: plain device-to-device copies into the static inputs
+            lat_bytes = 0
+            g.meta.copy_(host, non_blocking = True)
+            for dst, src in zip(g.lat, device_lat):
+                if dst is not None:
+                    dst.copy_(src, non_blocking = True)
+        else:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+            from ._pinned import POOL
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(g.consumed)    # the previous step has moved the staging buffers into its static inputs
+                g.meta_stage.copy_(host, non_blocking = True)
+                POOL.give(raw)
+                lat_bytes = model._latents_into(rb, g.lat_stage)
+                staged = torch.cuda.Event()
+                staged.record()
+            cur = torch.cuda.current_stream()
+            cur.wait_event(staged)
+            g.meta.copy_(g.meta_stage, non_blocking = True)
+            for dst, src in zip(g.lat, g.lat_stage):
+                if dst is not None:
+                    dst.copy_(src, non_blocking = True)
+            g.consumed.record()
+        if getattr(eng, 'opt_step_dev', None) is None:
+            eng.opt_step_dev = torch.zeros(1, device = eng.device, dtype = torch.int32)
+        eng.opt_step_dev.fill_(eng.opt_step)             # device-resident optimizer step counter (incremented inside the graph)
+        if g.graph is None:
+            import copy
+            g.rb = copy.copy(rb)                         # descriptor object whose device views point into the static metadata buffer
+            g.rb.dev = eng.meta_views(rb, g.meta, layout)
+            rb = g.rb
+            eng.zero_grad()
+            eng._dirty = True                            # the capture must contain the weight repack that follows every optimizer step
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = eng.ops.launches
+            with torch.cuda.graph(graph):
+                eps = [torch.randn_like(l) if l is not None else None for l in g.lat]
+                res = eng.forward(rb, g.lat, eps, train = True, text_loss_weight = model.text_loss_weight, flow_loss_weight = model.flow_loss_weight)
+                eng.backward()
+                eng.adam_step(grad_scale = 1.0, zero_grads = True, device_step = True, **self.hp)
+                g.loss = res['total']
+            eng.opt_step -= 1                            # the capture itself executed nothing
+            g.launches = eng.ops.launches - l0           # kernels of ours inside one replay
+            eng.ops.launches = l0
+            g.graph = graph
+        eng.opt_step += 1
+        eng._grads_clean = True                          # the graph ends with the Adam pass that clears the gradient buffer
+        g.graph.replay()
+        eng.ops.launches += g.launches
+        eng._dirty = True                                # parameters changed: the bf16 operand copies are repacked at the start of the next step
+        model._last_batch = g.rb
+        g.rb.dev['h2d_bytes'] = g.meta.numel() * 4
+        g.rb.latent_h2d_bytes = lat_bytes
+        return g.loss.clone()
 
     # ---- engine-backed (CUDA) path
     def _bucket_bounds(self, eng):
@@ -35,17 +170,41 @@ class DataParallelTrainer:
             self._tail = max((off + eng.named[n].numel() for n, off in eng.offs.items() if n.startswith('transformer.layers.')), default = 0)
         return self._bounds
 
+    def step_packed(self, rb, latents):
+        """One training step from a packed batch that is already resident on the device (`model.pack` + `engine.upload` + latents on the
+        device): CUDA-graph replay when the shape signature has been seen before, eager launches otherwise.  Single process only."""
+        model, eng = self.model, self.model.engine
+        assert self.world == 1
+        eng.ensure_attached()
+        eng.upload(rb)
+        loss = self._graph_step(rb, device_lat = latents) if self.cuda_graph else None
+        if loss is None:
+            eng.zero_grad()
+            loss = model.forward_packed(rb, latents)
+            loss.backward()
+            eng.adam_step(grad_scale = 1.0, zero_grads = True, **self.hp)
+        return loss
+
     def step(self, batch, times = None, **fw):
         model = self.model
         eng = model.engine
         cuda = hasattr(eng, 'gflat') or model.device.type == 'cuda'
         if cuda:
             eng.ensure_attached()
-            eng.zero_grad()
+            if self.cuda_graph and model.training and not fw and torch.is_grad_enabled():
+                rb, _ = model.pack(batch, times = times)
+                loss = self._graph_step(rb)
+                if loss is not None:
+                    return loss
+                eng.zero_grad()
+                loss = model.forward_packed(rb, model._latents_to_device(rb))
+            else:
+                eng.zero_grad()
+                loss = model(batch, times = times, **fw)
         else:
             for p in model.parameters():
                 p.grad = None
-        loss = model(batch, times = times, **fw)
+            loss = model(batch, times = times, **fw)
         if cuda and self.overlap:
             bounds = self._bucket_bounds(eng)
             if self.comm_stream is None:

@@ -239,14 +239,13 @@ class Engine:
         self._packed_version = self.flat._version
 
     # ------------------------------------------------------------------ descriptor upload
-    def upload(self, rb: RaggedBatch):
-        """One pinned staging buffer, one H2D copy for all integer metadata; one for the float metadata."""
-        if rb.dev:
-            return rb.dev
-        ints = [rb.text_id, rb.label, rb.kv_limit, rb.rope_pos, rb.cond_row, rb.slot, rb.tile_q0, rb.tile_qend, rb.tile_kv0, rb.tile_kvend,
-                rb.kt_kv0, rb.kt_kvend, rb.kt_q0, rb.kt_qend, rb.row_token, rb.t2_q0, rb.t2_qend, rb.t2_kv0, rb.t2_kvend, rb.k2_kv0, rb.k2_kvend, rb.k2_q0, rb.k2_qend, rb.k2_order]
-        names = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
-                 'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order']
+    META_NAMES = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
+                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order']
+
+    def stage_meta(self, rb: RaggedBatch):
+        """All per-token / per-tile int32 metadata and the float metadata of a batch in ONE pooled pinned buffer.
+        Returns (raw pinned buffer, int32 view, layout) - layout = (sizes per array, n_int, n_float)."""
+        ints = [getattr(rb, n) for n in self.META_NAMES]
         sizes = [_round_up(a.shape[0], 4) for a in ints]
         fl = np.concatenate([rb.cond_times, rb.row_time]).astype(np.float32)
         n_int, n_fl = sum(sizes), _round_up(fl.shape[0], 4)
@@ -257,17 +256,29 @@ class Engine:
         for a, s in zip(ints, sizes):
             hv[off:off + a.shape[0]] = a; off += s
         hv[n_int:n_int + fl.shape[0]] = fl.view(np.int32)
+        return raw, host, (tuple(a.shape[0] for a in ints), tuple(sizes), n_int, fl.shape[0])
+
+    def meta_views(self, rb: RaggedBatch, devbuf: Tensor, layout):
+        lens, sizes, n_int, n_fl = layout
+        d, off = {}, 0
+        for n, ln, s in zip(self.META_NAMES, lens, sizes):
+            d[n] = devbuf[off:off + ln]; off += s
+        fdev = devbuf[n_int:n_int + n_fl].view(F32)
+        d['cond_times'], d['row_time'] = fdev[:rb.n_cond], fdev[rb.n_cond:]
+        d['h2d_bytes'] = devbuf.numel() * 4
+        d['_keep'] = devbuf
+        d['_layout'] = layout
+        return d
+
+    def upload(self, rb: RaggedBatch):
+        """One pinned staging buffer, one H2D copy for all integer + float metadata."""
+        if rb.dev:
+            return rb.dev
+        raw, host, layout = self.stage_meta(rb)
         devbuf = host.to(self.device, non_blocking = True)
         POOL.give(raw)
-        d, off = {}, 0
-        for n, a, s in zip(names, ints, sizes):
-            d[n] = devbuf[off:off + a.shape[0]]; off += s
-        fdev = devbuf[n_int:n_int + fl.shape[0]].view(F32)
-        d['cond_times'], d['row_time'] = fdev[:rb.n_cond], fdev[rb.n_cond:]
-        d['h2d_bytes'] = host.numel() * 4
-        d['_keep'] = devbuf
-        rb.dev = d
-        return d
+        rb.dev = self.meta_views(rb, devbuf, layout)
+        return rb.dev
 
     def rope_table(self, max_pos: int):
         """cos/sin tables: [pos][32] (row kernels) and its transpose [32][pos] (thread-per-row QKVG epilogue)"""
@@ -465,14 +476,16 @@ class Engine:
                 st['dpred'].append(dpred)
                 flow_terms.append((acc[1 + t] / (n * dl)).float() )
             # loss assembly on a handful of device scalars (no host sync): transfusion.py:3331-3376
-            text = (acc[0] / max(rb.n_valid, 1)).float()
+            # mean CE over the valid labels: the count comes from the device (ce_fwd_bwd counts them), so the launch sequence does not
+            # depend on how many labels classifier-free-guidance dropout nulled in this batch (CUDA-graph replay across batches)
+            text = (acc[0] / nvalid[0].clamp(min = 1)).float()
             flows = torch.stack([f if f is not None else torch.zeros((), device = self.device) for f in flow_terms]) if flow_terms else torch.zeros(0, device = self.device)
             if vlimit:
                 total = text.clone()         # distinct tensor: autograd.Function outputs must not alias each other
             elif modality_only:
                 total = flows.sum()
             else:
-                total = text * (rb.n_valid / T) * text_loss_weight
+                total = (acc[0] / T).float() * text_loss_weight          # = text * (n_valid / T) * w  (T.py:3331, 3371)
                 for t, f in enumerate(flow_terms):
                     if f is not None:
                         total = total + f * (rb.n_type_tokens[t] / T) * flow_loss_weight
@@ -669,12 +682,16 @@ class Engine:
             self.gflat.zero_()
         self._grads_clean = False       # whoever asked for clean gradients is about to write them
 
-    def adam_step(self, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled = False, grad_scale = 1.0, zero_grads = False):
+    def adam_step(self, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled = False, grad_scale = 1.0, zero_grads = False, device_step = False):
         """zero_grads: clear the flat gradient buffer in the same pass (saves a separate fill); the next `zero_grad()` is then free."""
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.flat); self.exp_avg_sq = torch.zeros_like(self.flat)
         self.opt_step += 1
+        step_dev = None
+        if device_step:                         # CUDA-graph replays: the step counter lives on the device (the caller keeps it equal to opt_step - 1)
+            assert getattr(self, 'opt_step_dev', None) is not None, 'device_step needs engine.opt_step_dev (int32 [1] on the device)'
+            step_dev = self.opt_step_dev
         self.ops.adam_step(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.flat.numel(), lr, betas[0], betas[1], eps, weight_decay, int(decoupled),
-                           self.opt_step, grad_scale, int(zero_grads))
+                           self.opt_step, grad_scale, int(zero_grads), step_dev)
         self._grads_clean = bool(zero_grads)
         self._dirty = True

@@ -393,6 +393,35 @@ class Transfusion(SamplingMixin, Module):
         rb.latent_h2d_bytes = nbytes
         return out
 
+    def _latents_into(self, rb: RaggedBatch, dst_list: list) -> int:
+        """Same as `_latents_to_device` but into existing per-type device matrices (CUDA-graph static inputs); returns the H2D byte count."""
+        nbytes = 0
+        for t, lst in enumerate(rb.latents):
+            if not lst:
+                continue
+            dst, dl = dst_list[t], lst[0].shape[-1]
+            rows = [x.shape[0] for x in lst]
+            stage, stage_raw, off, soff = None, None, 0, 0
+            for x, n in zip(lst, rows):
+                x = x.detach()
+                if x.is_cuda:
+                    dst[off:off + n].copy_(x)
+                elif x.dtype == torch.float32 and x.is_contiguous() and x.is_pinned():
+                    dst[off:off + n].copy_(x, non_blocking = True); nbytes += x.numel() * 4
+                else:
+                    if stage is None:
+                        need = sum(r for r, y in zip(rows, lst) if not y.is_cuda) * dl
+                        stage_raw = POOL.take(need * 4)
+                        stage = stage_raw[:need * 4].view(torch.float32)
+                    view = stage[soff:soff + n * dl].view(n, dl)
+                    view.copy_(x)
+                    dst[off:off + n].copy_(view, non_blocking = True)
+                    soff += n * dl; nbytes += n * dl * 4
+                off += n
+            if stage is not None:
+                POOL.give(stage_raw)
+        return nbytes
+
     def _run(self, rb, latents, eps, *, train, **kw):
         eng = self.engine
         if train and torch.is_grad_enabled():
@@ -493,6 +522,44 @@ class Transfusion(SamplingMixin, Module):
             pred = pred.movedim(-1, 1)
         return pred
 
+    # ------------------------------------------------------------------ host side of forward(): CFG dropout, encoders, times, pack / route
+    def pack(self, modalities, times = None, num_modalities_to_times_fn = None, prob_uncond = None, return_loss = True, return_embed = False, is_decoding = False):
+        """Everything `forward` does on the host before the first kernel (transfusion.py:3011-3082 + modality_processing): returns the ragged
+        batch descriptor and the times that were used.  Exposed so that a training loop can pack step i+1 while step i runs on the device
+        (`DataParallelTrainer` does, and replays a captured CUDA graph when the descriptor has the same shape signature)."""
+        batch = len(modalities)
+        samples = [list(s) if isinstance(s, list) else s for s in modalities]
+        if return_loss:
+            samples = [[tensor([self.sos_id]), *s, tensor([self.eos_id])] for s in samples]
+        # classifier free guidance dropout (transfusion.py:3027-3043): all int tensors of a dropped sample -> null id
+        prob_uncond = default(prob_uncond, self.prob_uncond)
+        if self.training and prob_uncond > 0:
+            drop = (torch.rand(batch) < prob_uncond).tolist()
+            samples = [[torch.full_like(p, self.null_text_id) if is_int_tensor(p) else p for p in s] if d else s for s, d in zip(samples, drop)]
+        # modality encoders (user modules, outside the hot path)
+        n_mods = []
+        for s in samples:
+            cnt = 0
+            for j, part in enumerate(s):
+                if is_tensor(part) and part.is_floating_point():
+                    part = s[j] = (0, part)
+                if isinstance(part, tuple):
+                    cnt += 1
+                    enc = self.modality_encoder[part[0]]
+                    if exists(enc) and not is_decoding:
+                        with torch.no_grad():
+                            enc.eval()
+                            v = part[1].to(self.device)
+                            v = enc(v[None])[0] if self.encdec_needs_batch_dim else enc(v)
+                            s[j] = (part[0], v.detach())
+            n_mods.append(cnt)
+        if times is None and max(n_mods, default = 0) > 0:
+            fn = default(num_modalities_to_times_fn, default_modality_length_to_time_fn)
+            times = fn(tensor(n_mods))
+        process = get_processing_strategy(self.modality_processing)
+        rb = process(samples, times, self, need_axial_pos_emb = False, return_loss = return_loss, return_embed = return_embed)
+        return rb, times
+
     # ------------------------------------------------------------------ main forward (transfusion.py:2925-3450)
     def forward(
         self,
@@ -527,37 +594,8 @@ class Transfusion(SamplingMixin, Module):
         return_loss = return_loss and not (return_embed or is_decoding)
         assert not exists(cache), 'the B200 path recomputes the (short) prefix instead of taking an external kv cache; use sample()/sample_many()'
 
-        batch = len(modalities)
-        samples = [list(s) if isinstance(s, list) else s for s in modalities]
-        if return_loss:
-            samples = [[tensor([self.sos_id]), *s, tensor([self.eos_id])] for s in samples]
-        # classifier free guidance dropout (transfusion.py:3027-3043): all int tensors of a dropped sample -> null id
-        prob_uncond = default(prob_uncond, self.prob_uncond)
-        if self.training and prob_uncond > 0:
-            drop = (torch.rand(batch) < prob_uncond).tolist()
-            samples = [[torch.full_like(p, self.null_text_id) if is_int_tensor(p) else p for p in s] if d else s for s, d in zip(samples, drop)]
-        # modality encoders (user modules, outside the hot path)
-        n_mods = []
-        for s in samples:
-            cnt = 0
-            for j, part in enumerate(s):
-                if is_tensor(part) and part.is_floating_point():
-                    part = s[j] = (0, part)
-                if isinstance(part, tuple):
-                    cnt += 1
-                    enc = self.modality_encoder[part[0]]
-                    if exists(enc) and not is_decoding:
-                        with torch.no_grad():
-                            enc.eval()
-                            v = part[1].to(self.device)
-                            v = enc(v[None])[0] if self.encdec_needs_batch_dim else enc(v)
-                            s[j] = (part[0], v.detach())
-            n_mods.append(cnt)
-        if times is None and max(n_mods, default = 0) > 0:
-            fn = default(num_modalities_to_times_fn, default_modality_length_to_time_fn)
-            times = fn(tensor(n_mods))
-        process = get_processing_strategy(self.modality_processing)
-        rb = process(samples, times, self, need_axial_pos_emb = False, return_loss = return_loss, return_embed = return_embed)
+        rb, times = self.pack(modalities, times = times, num_modalities_to_times_fn = num_modalities_to_times_fn, prob_uncond = prob_uncond,
+                              return_loss = return_loss, return_embed = return_embed, is_decoding = is_decoding)
         lat = self._latents_to_device(rb)
         if return_loss:
             if exists(noise):

@@ -167,6 +167,7 @@ def run_b200_arm(args):
     synth.fill_parameters_(model, seed = 0)
     model.train()
     trainer = DataParallelTrainer(model, lr = 1e-4, cuda_graph = not args.no_graph)
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/null')
     eng = model.engine
     eng.ensure_attached()
 
@@ -186,9 +187,10 @@ def run_b200_arm(args):
     assert packed[0][0].M == B * SEQ
     log('packed', POOL, 'batches; M =', packed[0][0].M)
 
+    profiling = [False]                                      # roofline pass: every rank launches eagerly (same collectives on all ranks)
     def step_resident(i):
         rb, lat = packed[i % POOL]
-        if world == 1 and not args.no_graph and eng.ops.timing is None:
+        if trainer.cuda_graph and not profiling[0]:
             return trainer.step_packed(rb, lat)              # CUDA-graph replay of the step (after two eager steps of this shape)
         eng.zero_grad()
         loss = model.forward_packed(rb, lat)
@@ -288,6 +290,7 @@ def run_b200_arm(args):
     # ---- per-kernel-family device time of one step (profiling pass, not part of the reported throughput)
     # every rank runs the step (it contains the gradient all-reduce); only rank 0 records per-launch events
     roof = None
+    profiling[0] = True
     if rank == 0:
         eng.ops.timing = {}
     step_resident(0)
@@ -321,14 +324,21 @@ def run_b200_arm(args):
         line = dict(metric = METRIC, value = value, unit = 'tokens/s', n_gpus = world, steps = args.steps, warmup = args.warmup, ms_per_step = ms_step, higher_is_better = True,
                     scaling = 'weak', vs_baseline = None, dtype = 'bf16', data = 'synthetic',
                     config = dict(workload = 'configs[1]: single-modality text+latent d=512 depth=8 dim_latent=384 seq=1024', global_batch = world * B, per_gpu_batch = B,
-                                  seq_len = SEQ, parallelism = f'dp{world}', optimizer = 'fused Adam', launch = 'cuda graph replay' if (world == 1 and not args.no_graph) else 'eager', l2 = 'per-step working set (>10 GB of activations) is far larger than the 126 MB L2; 4 rotating input batches'),
+                                  seq_len = SEQ, parallelism = f'dp{world}', optimizer = 'fused Adam', launch = 'cuda graph replay' if trainer.cuda_graph else 'eager', l2 = 'per-step working set (>10 GB of activations) is far larger than the 126 MB L2; 4 rotating input batches'),
                     e2e = dict(value = e2e_value, unit = 'tokens/s', ms_per_step = ms_e2e, h2d_bytes_per_step = int(h2d[0]), d2h_bytes_per_step = 4,
                                loss_read = 'every step, deferred by one step (asynchronous logging)',
                                host_ms_per_step = round(sum(host_e2e[-e2e_steps:]) / e2e_steps, 3)),
                     gpu_launches = int(launches), host_enqueue_ms_per_step = round(host_enqueue_ms, 3), clocks = clocks, roofline = roof, cpu_baseline = cpu)
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them, drain the device, leave together.  The process then exits without running the
+        # process-group destructor (observed to hang after graph-captured collectives); every rank has already passed the barrier.
+        trainer._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -51,7 +51,7 @@ class _StepGraph:
 
 
 class DataParallelTrainer:
-    def __init__(self, model, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled_weight_decay = False, overlap = True, cuda_graph = True):
+    def __init__(self, model, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled_weight_decay = False, overlap = True, cuda_graph = True, graph_multi_gpu = True):
         self.model = model
         self.hp = dict(lr = lr, betas = betas, eps = eps, weight_decay = weight_decay, decoupled = decoupled_weight_decay)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -59,9 +59,10 @@ class DataParallelTrainer:
         self.comm_stream = None
         self._cpu_opt = None
         # CUDA graphs: a step whose descriptor has a shape signature seen twice before is captured once and replayed afterwards - the ~320
-        # kernel launches of a step (8-9 ms of host time through ctypes) become one graph launch.  Single-process only: the bucketed
-        # NCCL overlap of the multi-GPU path stays eager.
-        self.cuda_graph = cuda_graph and self.world == 1
+        # kernel launches of a step (8-9 ms of host time through ctypes) become one graph launch.  With several ranks the gradient
+        # all-reduce (NCCL) is captured inside the graph, after the backward pass (set graph_multi_gpu = False for the eager,
+        # bucket-overlapped path instead).
+        self.cuda_graph = cuda_graph and (self.world == 1 or graph_multi_gpu)
         self._graphs = {}
         self._copy_stream = None
 
@@ -141,7 +142,9 @@ class DataParallelTrainer:
                 eps = [torch.randn_like(l) if l is not None else None for l in g.lat]
                 res = eng.forward(rb, g.lat, eps, train = True, text_loss_weight = model.text_loss_weight, flow_loss_weight = model.flow_loss_weight)
                 eng.backward()
-                eng.adam_step(grad_scale = 1.0, zero_grads = True, device_step = True, **self.hp)
+                if self.world > 1:
+                    dist.all_reduce(eng.gflat)            # NCCL all-reduce of the flat gradient buffer, captured as a graph node
+                eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, device_step = True, **self.hp)
                 g.loss = res['total']
             eng.opt_step -= 1                            # the capture itself executed nothing
             g.launches = eng.ops.launches - l0           # kernels of ours inside one replay
@@ -174,7 +177,6 @@ class DataParallelTrainer:
         """One training step from a packed batch that is already resident on the device (`model.pack` + `engine.upload` + latents on the
         device): CUDA-graph replay when the shape signature has been seen before, eager launches otherwise.  Single process only."""
         model, eng = self.model, self.model.engine
-        assert self.world == 1
         eng.ensure_attached()
         eng.upload(rb)
         loss = self._graph_step(rb, device_lat = latents) if self.cuda_graph else None
@@ -182,7 +184,9 @@ class DataParallelTrainer:
             eng.zero_grad()
             loss = model.forward_packed(rb, latents)
             loss.backward()
-            eng.adam_step(grad_scale = 1.0, zero_grads = True, **self.hp)
+            if self.world > 1:
+                dist.all_reduce(eng.gflat)
+            eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, **self.hp)
         return loss
 
     def step(self, batch, times = None, **fw):

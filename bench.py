@@ -158,6 +158,7 @@ def run_b200_arm(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')       # NCCL's version / debug lines must not mix with the ONE JSON line on stdout
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id = torch.device('cuda', local))
     dev = torch.device('cuda', local)
@@ -167,7 +168,6 @@ def run_b200_arm(args):
     synth.fill_parameters_(model, seed = 0)
     model.train()
     trainer = DataParallelTrainer(model, lr = 1e-4, cuda_graph = not args.no_graph)
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/null')
     eng = model.engine
     eng.ensure_attached()
 

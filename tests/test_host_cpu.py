@@ -142,3 +142,45 @@ def test_product_fails_loudly_without_cuda():
     with pytest.raises(Exception) as ei:
         m(synth.config4_batch(1, seed = 0, total_len = 80, dims = (32, 16), text_vocab = 64))
     assert 'CUDA' in str(ei.value) or 'cuda' in str(ei.value)
+
+
+def test_pack_is_the_host_half_of_forward_and_tile_tables_cover_the_mask():
+    """`Transfusion.pack` (what DataParallelTrainer runs ahead of the device step) returns the descriptor `forward` would build;
+    the 128-row tables of the tcgen05 attention kernels cover every visible (query, key) pair; the persistent-grid order is a
+    permutation sorted by work."""
+    m = small_model()
+    batch = synth.small_batch(3, seed = 5, dim_latent = 32, text_vocab = 64)
+    nm = max(sum(torch.is_tensor(p) and p.is_floating_point() for p in s) for s in batch)
+    times = torch.rand(3, nm, generator = torch.Generator().manual_seed(0))
+    m.eval()
+    rb, t = m.pack(batch, times = times)
+    assert t is times and rb.M == int(rb.seq_lens.sum()) and rb.has_labels
+    seq_of = np.repeat(np.arange(rb.B), rb.seq_lens)
+    for q0, qe, k0, ke in zip(rb.t2_q0, rb.t2_qend, rb.t2_kv0, rb.t2_kvend):
+        assert qe - q0 <= 128 and seq_of[q0] == seq_of[qe - 1] and k0 == rb.cu[seq_of[q0]] and rb.kv_limit[q0:qe].max() < ke
+    for k0, ke, q0, qe in zip(rb.k2_kv0, rb.k2_kvend, rb.k2_q0, rb.k2_qend):
+        b = seq_of[k0]
+        rows = np.arange(rb.cu[b], rb.cu[b + 1])
+        first = rows[rb.kv_limit[rows] >= k0].min()                  # first query of the sequence that sees a key of this tile
+        assert ke - k0 <= 128 and q0 <= first and (q0 - rb.cu[b]) % 128 == 0 and qe == rb.cu[b + 1]
+    work = (rb.k2_qend - rb.k2_q0)[rb.k2_order]
+    assert sorted(rb.k2_order.tolist()) == list(range(len(rb.k2_kv0))) and (np.diff(work) <= 0).all()
+
+
+def test_step_graph_signature_ignores_data_but_not_shape():
+    from transfusion_pytorch_b200.data_parallel import DataParallelTrainer
+    from transfusion_pytorch_b200.engine import Engine
+    m = small_model()
+    a = synth.small_batch(2, seed = 1, dim_latent = 32, text_vocab = 64)
+    b = [[p.clone() if torch.is_tensor(p) else p for p in s] for s in a]
+    for s in b:
+        for j, p in enumerate(s):
+            if torch.is_tensor(p) and not p.is_floating_point():
+                s[j] = (p + 1) % 64                                     # same shapes, different token ids
+    nm = max(sum(torch.is_tensor(p) and p.is_floating_point() for p in s) for s in a)
+    times = torch.rand(2, nm)
+    ra, _ = m.pack(a, times = times)
+    rb_, _ = m.pack(b, times = times)
+    rc, _ = m.pack(a[:1], times = times[:1])
+    sig = lambda r: DataParallelTrainer._signature(r, Engine)
+    assert sig(ra) == sig(rb_) and sig(ra) != sig(rc)

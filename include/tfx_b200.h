@@ -135,7 +135,6 @@ int tfx_ce_fwd_bwd(const float* logits, long long ld_logits, const int* labels, 
 int tfx_mse_fwd_bwd(const float* pred, long long ld_pred, const float* flow, void* dpred_bf16, long long ld_dpred, float gscale, double* sumsq, long long S, int dl, void* stream);
 int tfx_colsum_bf16(const void* in_bf16, long long ld, long long M, int N, const int* col_map, float* out, void* stream);
 int tfx_colsum_f32(const float* in, long long ld, long long M, int N, const int* col_map /* optional */, float* out, void* stream);
-int tfx_cast_pack(const float* src, long long ld_src, int C_src, const int* row_src, void* dst_bf16, long long R_dst, int C_dst, void* stream);
 /* all per-optimizer-step weight repacks in one launch; jobs / block tables live in device memory (built once by the host) */
 typedef struct TfxPackJob {
   const float* src; long long ld_src; const int* row_src /* optional row gather, -1 = zero row */; void* dst /* bf16, or fp32 if dst_f32 */;
@@ -143,7 +142,6 @@ typedef struct TfxPackJob {
 } TfxPackJob;
 int tfx_cast_pack_multi(const TfxPackJob* jobs_dev, const int* blk_job_dev, const int* blk_first_dev, int n_blocks, void* stream);
 int tfx_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
-int tfx_scale_f32(float* p, const float* scale_ptr, float scale, long long n, void* stream);
 int tfx_scale_bf16(void* p_bf16, const float* scale_ptr, long long n, void* stream);          /* p *= *scale_ptr (device scalar) */
 int tfx_axpy_f32(float* y, const float* x, float a, long long n, void* stream);   /* y += a*x */
 /* cos_sin [max_pos][n_freqs][2]; cos_sin_t (optional) the same table stored [n_freqs][max_pos][2] (coalesced reads for thread-per-row epilogues) */

@@ -48,10 +48,8 @@ SIGNATURES = {
     'tfx_mse_fwd_bwd': [VP, LL, VP, VP, LL, F, VP, LL, I, VP],
     'tfx_colsum_bf16': [VP, LL, LL, I, VP, VP, VP],
     'tfx_colsum_f32': [VP, LL, LL, I, VP, VP, VP],
-    'tfx_cast_pack': [VP, LL, I, VP, VP, LL, I, VP],
     'tfx_cast_pack_multi': [VP, VP, VP, I, VP],
     'tfx_cast_bf16': [VP, VP, LL, VP],
-    'tfx_scale_f32': [VP, VP, F, LL, VP],
     'tfx_scale_bf16': [VP, VP, LL, VP],
     'tfx_axpy_f32': [VP, VP, F, LL, VP],
     'tfx_rope_table': [VP, VP, VP, I, I, VP],

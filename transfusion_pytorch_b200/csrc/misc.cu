@@ -230,18 +230,6 @@ __global__ void colsum_f32_k(const float* __restrict__ in, long long ld, long lo
   if (o >= 0) atomicAdd(out + o, a);
 }
 
-// dst[r][c] (bf16, R_dst x C_dst) = (row_src[r] >= 0 && c < C_src) ? src[row_src[r]*ld_src + c] : 0
-__global__ void cast_pack_k(const float* __restrict__ src, long long ld_src, int C_src, const int* __restrict__ row_src, __nv_bfloat16* __restrict__ dst, long long R_dst, int C_dst) {
-  const long long n = R_dst * C_dst;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C_dst; const int c = (int)(i - r * C_dst);
-    const long long sr = row_src ? row_src[r] : r;
-    float v = 0.f;
-    if (sr >= 0 && c < C_src) v = src[sr * ld_src + c];
-    dst[i] = __float2bfloat16(v);
-  }
-}
-
 // All per-step weight repacks in ONE launch: job j copies/casts a [R_dst x C_dst] destination from an fp32 source with an
 // optional row gather; `blk_job[b]` maps a block to its job and `blk_first[j]` is the first block of job j.
 __global__ void cast_pack_multi_k(const TfxPackJob* __restrict__ jobs, const int* __restrict__ blk_job, const int* __restrict__ blk_first) {
@@ -286,11 +274,6 @@ __global__ void cast_pack_multi_k(const TfxPackJob* __restrict__ jobs, const int
 
 __global__ void cast_f32_bf16_k(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = __float2bfloat16(src[i]);
-}
-
-__global__ void scale_f32_k(float* __restrict__ p, const float* __restrict__ scale_ptr, float scale, long long n) {
-  const float s = scale_ptr ? *scale_ptr * scale : scale;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] *= s;
 }
 
 __global__ void scale_bf16_k(__nv_bfloat16* __restrict__ p, const float* __restrict__ scale_ptr, long long n) {
@@ -413,12 +396,6 @@ int tfx_colsum_f32(const float* in, long long ld, long long M, int N, const int*
   return check_launch("colsum_f32");
 }
 
-int tfx_cast_pack(const float* src, long long ld_src, int C_src, const int* row_src, void* dst_bf16, long long R_dst, int C_dst, void* stream) {
-  if (R_dst <= 0 || C_dst <= 0) return 0;
-  cast_pack_k<<<ew_grid(R_dst * C_dst, 256), 256, 0, ST(stream)>>>(src, ld_src, C_src, row_src, (__nv_bfloat16*)dst_bf16, R_dst, C_dst);
-  return check_launch("cast_pack");
-}
-
 int tfx_cast_pack_multi(const TfxPackJob* jobs_dev, const int* blk_job_dev, const int* blk_first_dev, int n_blocks, void* stream) {
   if (n_blocks <= 0) return 0;
   cast_pack_multi_k<<<n_blocks, 256, 0, ST(stream)>>>(jobs_dev, blk_job_dev, blk_first_dev);
@@ -429,12 +406,6 @@ int tfx_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream) {
   if (n <= 0) return 0;
   cast_f32_bf16_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(src, (__nv_bfloat16*)dst_bf16, n);
   return check_launch("cast_bf16");
-}
-
-int tfx_scale_f32(float* p, const float* scale_ptr, float scale, long long n, void* stream) {
-  if (n <= 0) return 0;
-  scale_f32_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(p, scale_ptr, scale, n);
-  return check_launch("scale_f32");
 }
 
 int tfx_scale_bf16(void* p_bf16, const float* scale_ptr, long long n, void* stream) {

@@ -296,13 +296,18 @@ def run_b200_arm(args):
     step_resident(0)
     barrier()
     if rank == 0:
-        fam = {}
+        fam, inst = {}, {}
         rb = packed[0][0]
         for name, recs in eng.ops.timing.items():
             for e0, e1, a in recs:
                 f, fl, by = family_model(name, a, eng, rb)
+                ms = e0.elapsed_time(e1)
                 d = fam.setdefault(f, dict(ms = 0., flops = 0., launches = 0))
-                d['ms'] += e0.elapsed_time(e1); d['flops'] += fl; d['launches'] += 1
+                d['ms'] += ms; d['flops'] += fl; d['launches'] += 1
+                if fl > 0:                                    # per kernel instance (entry point + problem shape)
+                    label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else '')
+                    k = inst.setdefault(label, dict(ms = 0., flops = 0., launches = 0))
+                    k['ms'] += ms; k['flops'] += fl; k['launches'] += 1
         eng.ops.timing = None
         pk = peaks()
         tot = sum(d['ms'] for d in fam.values())
@@ -313,6 +318,14 @@ def run_b200_arm(args):
                     families = {f: dict(ms = round(d['ms'], 3), share = round(d['ms'] / tot, 3), launches = d['launches'],
                                         tflops = round(d['flops'] / (d['ms'] / 1e3) / 1e12, 1) if d['flops'] else None) for f, d in fam.items()},
                     whole_step_tflops = value * ALGO_TRAIN_FLOP_PER_TOKEN / 1e12 / world, whole_step_frac = value * ALGO_TRAIN_FLOP_PER_TOKEN / 1e12 / world / pk['tf_sustained'])
+        # the five kernel instances with the largest share of the step: algorithmic FLOPs per launch / average launch duration (CUDA events),
+        # DRAM traffic per launch from the committed ncu captures (measured at batch 32; null for other batch sizes / kernels)
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        tmap = json.load(open(tpath)) if os.path.isfile(tpath) else {}
+        top = sorted(inst.items(), key = lambda kv: -kv[1]['ms'])[:5]
+        roof['kernels'] = [dict(kernel = lbl, launches = k['launches'], us_per_launch = round(1e3 * k['ms'] / k['launches'], 1), share_of_step = round(k['ms'] / tot, 3),
+                                achieved = round(k['flops'] / (k['ms'] / 1e3) / 1e12, 1), frac = round(k['flops'] / (k['ms'] / 1e3) / 1e12 / pk['tf_sustained'], 3),
+                                traffic = (tmap.get(lbl) if B == 32 else None)) for lbl, k in top]
 
     if rank == 0:
         clocks = sampler.summary() if sampler else None

@@ -420,7 +420,6 @@ class Engine:
                      uF = uF, statsF = statsF, vg = vg, h = h, yF = yF, x_in = x_in, x_in_b = x_in_b, has_skip = has_skip, first_half = first_half)
             st['layers'].append(L)
             x_in, x_in_b = xr, xrb
-        assert len(skips) == 0 or True
         st['hid'] = hid
         st['x_last'] = x_in
 

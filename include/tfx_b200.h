@@ -152,6 +152,14 @@ int tfx_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   int* step_dev /* optional device-resident step counter (incremented here; bias corrections computed on the device - CUDA-graph safe) */,
                   void* stream);
 
+/* global-norm gradient clipping with torch.nn.utils.clip_grad_norm_ semantics (train_latent_with_text.py:142-153): accumulate the squared
+ * norm of the flat gradient buffer into *sumsq_accum (caller zeroes it), then scale by min(1, max_norm / (pre_scale*sqrt(sumsq) + 1e-6));
+ * pre_scale = 1 / world_size when the buffer holds the all-reduced SUM.  No host synchronisation. */
+int tfx_grad_sumsq(const float* grads, long long n, double* sumsq_accum, void* stream);
+int tfx_clip_by_norm(float* grads, long long n, const double* sumsq, float max_norm, float pre_scale, void* stream);
+/* EMA copy of the flat parameter buffer (ema_pytorch update, T.py:1687-1697): ema = decay*ema + (1-decay)*params */
+int tfx_ema_update(float* ema, const float* params, long long n, float decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

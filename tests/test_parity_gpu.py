@@ -212,3 +212,34 @@ def test_cuda_graph_step_matches_eager_step():
     assert all(abs(a - b) / abs(a) < 2e-3 for a, b in zip(l0[:2], l1[:2])), (l0, l1)       # eager steps of both runs
     assert l1[-1] < l1[0] and abs(l1[-1] - l0[-1]) / abs(l0[-1]) < 5e-2, (l0, l1)           # replayed steps keep training at the same pace
     assert (p1 - p0).abs().max().item() < 5e-2
+
+
+def test_clip_grad_norm_and_ema_match_torch():
+    """the rest of the example scripts' train step (clip_grad_norm_(0.5) + EMA, train_latent_with_text.py:142-153) on the flat buffers"""
+    torch.manual_seed(0)
+    model = Transfusion(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), transformer = dict(dim = 128, depth = 2, heads = 2)).cuda()
+    eng = model.engine
+    eng.ensure_attached()
+    g = torch.randn_like(eng.flat) * 0.02
+    for max_norm, pre in ((0.5, 1.0), (0.5, 0.25), (1e6, 1.0)):
+        eng.gflat.copy_(g)
+        ref = (g * pre).clone().requires_grad_(False)
+        holder = torch.nn.Parameter(torch.zeros_like(ref)); holder.grad = ref.clone()
+        want_norm = torch.nn.utils.clip_grad_norm_([holder], max_norm)
+        got_norm = eng.clip_grad_norm_(max_norm, pre)
+        torch.cuda.synchronize()
+        assert abs(got_norm.item() - want_norm.item()) / want_norm.item() < 1e-5
+        assert torch.allclose(eng.gflat * pre, holder.grad, rtol = 1e-5, atol = 1e-9)
+    p0 = eng.flat.clone()
+    eng.ema_update(0.9)                                       # first call: copy
+    eng.flat.add_(0.01)
+    eng.ema_update(0.9)
+    eng.flat.add_(0.01)
+    eng.ema_update(0.9)
+    want = p0.clone()
+    want = 0.9 * want + 0.1 * (p0 + 0.01)
+    want = 0.9 * want + 0.1 * (p0 + 0.02)
+    torch.cuda.synchronize()
+    assert torch.allclose(eng.ema_flat, want, rtol = 1e-5, atol = 1e-7)
+    sd = eng.ema_state_dict()
+    assert set(sd) == set(eng.named) and sd['text_embed.weight'].shape == model.text_embed.weight.shape

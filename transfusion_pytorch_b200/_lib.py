@@ -53,6 +53,9 @@ SIGNATURES = {
     'tfx_scale_bf16': [VP, VP, LL, VP],
     'tfx_axpy_f32': [VP, VP, F, LL, VP],
     'tfx_rope_table': [VP, VP, VP, I, I, VP],
+    'tfx_grad_sumsq': [VP, LL, VP, VP],
+    'tfx_clip_by_norm': [VP, LL, VP, F, F, VP],
+    'tfx_ema_update': [VP, VP, LL, F, VP],
     'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP, VP],
 }
 

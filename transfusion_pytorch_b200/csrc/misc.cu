@@ -327,6 +327,35 @@ __global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __re
   }
 }
 
+// ---- the rest of the train step the reference's examples run next to Adam (train_latent_with_text.py:142-153, train_image_only.py:90-110):
+// global-norm gradient clipping (torch.nn.utils.clip_grad_norm_ semantics) and the EMA copy of the parameters (ema_pytorch lerp)
+__global__ void grad_sumsq_k(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  double local = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) { const float v = g[i]; local += (double)v * v; }
+  float lo = (float)local;                       // per-thread partial fits fp32 comfortably; the cross-block sum is in double
+  lo = warp_sum(lo);
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = lo;
+  __syncthreads();
+  if (w == 0) {
+    float v = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(out, (double)v);
+  }
+}
+// g *= min(1, max_norm / (pre_scale * sqrt(sumsq) + 1e-6))     (pre_scale = 1 / world_size when g holds the all-reduced SUM)
+__global__ void clip_by_norm_k(float* __restrict__ g, long long n, const double* __restrict__ sumsq, float max_norm, float pre_scale) {
+  const float total = pre_scale * (float)sqrt(*sumsq);
+  const float coef = max_norm / (total + 1e-6f);
+  if (coef >= 1.f) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) g[i] *= coef;
+}
+// ema = decay * ema + (1 - decay) * p
+__global__ void ema_update_k(float* __restrict__ ema, const float* __restrict__ p, long long n, float decay) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) ema[i] = fmaf(decay, ema[i] - p[i], p[i]);
+}
+
 }  // namespace tfx
 
 using namespace tfx;
@@ -436,6 +465,25 @@ int tfx_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
   else { bc1 = 1.f - powf(beta1, (float)step); bc2s = sqrtf(1.f - powf(beta2, (float)step)); }
   adam_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, bc2s, grad_scale, zero_grads, step_dev);
   return check_launch("adam_step");
+}
+
+int tfx_grad_sumsq(const float* grads, long long n, double* sumsq_accum, void* stream) {
+  if (n <= 0) return 0;
+  grad_sumsq_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(grads, n, sumsq_accum);
+  return check_launch("grad_sumsq");
+}
+
+int tfx_clip_by_norm(float* grads, long long n, const double* sumsq, float max_norm, float pre_scale, void* stream) {
+  if (n <= 0) return 0;
+  TFX_REQUIRE(max_norm > 0.f, "clip_by_norm: max_norm must be > 0");
+  clip_by_norm_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(grads, n, sumsq, max_norm, pre_scale);
+  return check_launch("clip_by_norm");
+}
+
+int tfx_ema_update(float* ema, const float* params, long long n, float decay, void* stream) {
+  if (n <= 0) return 0;
+  ema_update_k<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(ema, params, n, decay);
+  return check_launch("ema_update");
 }
 
 }  // extern "C"

@@ -51,13 +51,16 @@ class _StepGraph:
 
 
 class DataParallelTrainer:
-    def __init__(self, model, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled_weight_decay = False, overlap = True, cuda_graph = True, graph_multi_gpu = True):
+    def __init__(self, model, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled_weight_decay = False, overlap = True, cuda_graph = True, graph_multi_gpu = True,
+                 max_grad_norm = None, ema_decay = None):
         self.model = model
         self.hp = dict(lr = lr, betas = betas, eps = eps, weight_decay = weight_decay, decoupled = decoupled_weight_decay)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.overlap = overlap and self.world > 1
         self.comm_stream = None
         self._cpu_opt = None
+        # the rest of the step the reference's example scripts run: clip_grad_norm_(max_grad_norm) before the optimizer, EMA after it
+        self.max_grad_norm, self.ema_decay = max_grad_norm, ema_decay
         # CUDA graphs: a step whose descriptor has a shape signature seen twice before is captured once and replayed afterwards - the ~320
         # kernel launches of a step (8-9 ms of host time through ctypes) become one graph launch.  With several ranks the gradient
         # all-reduce (NCCL) is captured inside the graph, after the backward pass (set graph_multi_gpu = False for the eager,
@@ -129,6 +132,8 @@ class DataParallelTrainer:
             eng.opt_step_dev = torch.zeros(1, device = eng.device, dtype = torch.int32)
         eng.opt_step_dev.fill_(eng.opt_step)             # device-resident optimizer step counter (incremented inside the graph)
         if g.graph is None:
+            if self.ema_decay is not None and getattr(eng, 'ema_flat', None) is None:
+                eng.ema_flat = eng.flat.clone()          # must exist before the capture (an allocation + copy inside it would be replayed)
             import copy
             g.rb = copy.copy(rb)                         # descriptor object whose device views point into the static metadata buffer
             g.rb.dev = eng.meta_views(rb, g.meta, layout)
@@ -144,7 +149,11 @@ class DataParallelTrainer:
                 eng.backward()
                 if self.world > 1:
                     dist.all_reduce(eng.gflat)            # NCCL all-reduce of the flat gradient buffer, captured as a graph node
+                if self.max_grad_norm is not None:
+                    eng.clip_grad_norm_(self.max_grad_norm, 1.0 / self.world)
                 eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, device_step = True, **self.hp)
+                if self.ema_decay is not None:
+                    eng.ema_update(self.ema_decay)
                 g.loss = res['total']
             eng.opt_step -= 1                            # the capture itself executed nothing
             g.launches = eng.ops.launches - l0           # kernels of ours inside one replay
@@ -173,6 +182,14 @@ class DataParallelTrainer:
             self._tail = max((off + eng.named[n].numel() for n, off in eng.offs.items() if n.startswith('transformer.layers.')), default = 0)
         return self._bounds
 
+    def _finish_step(self, eng):
+        """[clip] -> fused Adam (clears the gradient buffer: the next step's zero_grad() is free) -> [EMA]"""
+        if self.max_grad_norm is not None:
+            eng.clip_grad_norm_(self.max_grad_norm, 1.0 / self.world)
+        eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, **self.hp)
+        if self.ema_decay is not None:
+            eng.ema_update(self.ema_decay)
+
     def step_packed(self, rb, latents):
         """One training step from a packed batch that is already resident on the device (`model.pack` + `engine.upload` + latents on the
         device): CUDA-graph replay when the shape signature has been seen before, eager launches otherwise.  Single process only."""
@@ -186,7 +203,7 @@ class DataParallelTrainer:
             loss.backward()
             if self.world > 1:
                 dist.all_reduce(eng.gflat)
-            eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, **self.hp)
+            self._finish_step(eng)
         return loss
 
     def step(self, batch, times = None, **fw):
@@ -244,7 +261,7 @@ class DataParallelTrainer:
                     for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
                         g.copy_(f)
         if cuda:
-            eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, **self.hp)     # next step's zero_grad() is free
+            self._finish_step(eng)
         else:
             if self._cpu_opt is None:
                 cls = torch.optim.AdamW if self.hp['decoupled'] else torch.optim.Adam
@@ -253,5 +270,7 @@ class DataParallelTrainer:
                 for p in model.parameters():
                     if p.grad is not None:
                         p.grad.div_(self.world)
+            if self.max_grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_(list(model.parameters()), self.max_grad_norm)
             self._cpu_opt.step()
         return loss

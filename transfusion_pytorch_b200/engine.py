@@ -681,6 +681,27 @@ class Engine:
             self.gflat.zero_()
         self._grads_clean = False       # whoever asked for clean gradients is about to write them
 
+    def clip_grad_norm_(self, max_norm: float, pre_scale: float = 1.0):
+        """torch.nn.utils.clip_grad_norm_ over the flat gradient buffer, entirely on the device (no host sync).  `pre_scale` = 1/world when
+        the buffer holds the all-reduced sum.  Returns the (unclipped) total norm as a device tensor."""
+        ss = self.buf('gnorm_ss', (1,), torch.float64)
+        ss.zero_()
+        n = self.gflat.numel()
+        self.ops.grad_sumsq(self.gflat, n, ss)
+        self.ops.clip_by_norm(self.gflat, n, ss, float(max_norm), float(pre_scale))
+        return ss.sqrt() * pre_scale
+
+    def ema_update(self, decay: float):
+        """EMA copy of all trainable parameters (one flat buffer, same layout as the master parameters)."""
+        if getattr(self, 'ema_flat', None) is None or self.ema_flat.numel() != self.flat.numel():
+            self.ema_flat = self.flat.clone()
+            return
+        self.ops.ema_update(self.ema_flat, self.flat, self.flat.numel(), float(decay))
+
+    def ema_state_dict(self):
+        assert getattr(self, 'ema_flat', None) is not None, 'no EMA update has run yet'
+        return {n: self.ema_flat[o:o + self.named[n].numel()].view(self.named[n].shape) for n, o in self.offs.items()}
+
     def adam_step(self, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled = False, grad_scale = 1.0, zero_grads = False, device_step = False):
         """zero_grads: clear the flat gradient buffer in the same pass (saves a separate fill); the next `zero_grad()` is then free."""
         if self.exp_avg is None:

@@ -184,3 +184,28 @@ def test_step_graph_signature_ignores_data_but_not_shape():
     rc, _ = m.pack(a[:1], times = times[:1])
     sig = lambda r: DataParallelTrainer._signature(r, Engine)
     assert sig(ra) == sig(rb_) and sig(ra) != sig(rc)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """every prototype of include/tfx_b200.h against the ctypes argtypes in _lib.SIGNATURES: same arity, same scalar classes
+    (pointer / int / long long / float) in the same order - a mismatch would corrupt arguments silently."""
+    import ctypes as C
+    header = open(os.path.join(ROOT, 'include', 'tfx_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', ' ', header, flags = re.S)
+    protos = dict(re.findall(r'\bint\s+(tfx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', header, flags = re.S))
+    def cls(arg):
+        a = ' '.join(arg.split())
+        if '*' in a: return C.c_void_p
+        if a.startswith('long long'): return C.c_longlong
+        if a.startswith('float'): return C.c_float
+        if a.startswith('int'): return C.c_int
+        raise AssertionError(f'unrecognised parameter: {a!r}')
+    checked = 0
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in protos, f'{name} has ctypes argtypes but no prototype'
+        params = [x for x in protos[name].split(',') if x.strip() and x.strip() != 'void']
+        want = [cls(x) for x in params]
+        assert len(want) == len(argtypes), f'{name}: header has {len(want)} parameters, _lib declares {len(argtypes)}'
+        assert want == list(argtypes), f'{name}: parameter classes differ: {[w.__name__ for w in want]} vs {[a.__name__ for a in argtypes]}'
+        checked += 1
+    assert checked >= 35

@@ -4,15 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's CPU algorithm on the host cores
 
-A "step" = forward + backward + gradient all-reduce (N > 1) + fused Adam over one synthetic batch of
+A "step" = forward + backward + gradient all-reduce (N > 1) + fused Adam (+ bf16 weight repack) over one synthetic batch of
 `--batch` sequences x 1024 packed tokens per GPU (weak scaling).  Prints ONE JSON line on rank 0.
 
-  value  : whole-job tokens/s with the packed batch already resident in HBM (device-timed, CUDA events, max over ranks)
-  e2e    : same metric through the public API - `model(list_of_samples)` incl. Python pack/route, H2D of ids +
-           latents from pinned host memory every step and a D2H read of the loss
-  roofline: dominant kernel family of the step (by measured device time), algorithmic FLOPs / measured time
-  cpu_baseline: the oracle port of the reference algorithm (oracle/torch_reference.py, fp32, per-token conditioning,
-           dense masks - the reference's cost structure) timed on this box's host cores on a bounded sample
+  value  : whole-job tokens/s with the packed batch already resident in HBM (device-timed, CUDA events, max over ranks); the step is a
+           CUDA-graph replay (`DataParallelTrainer.step_packed`), `--no-graph` launches the same kernels eagerly
+  e2e    : same metric through the public API - `DataParallelTrainer.step(list_of_samples)`: Python pack/route, H2D of the token metadata
+           and of the latents from pinned host memory every step (copy stream), the step graph, and a D2H read of every step's loss
+           (fetched one step late through a side stream so the host packs the next batch meanwhile)
+  roofline: dominant kernel family of the step (by measured device time of an eager profiling pass), algorithmic FLOPs / measured time
+           against the sustained measured bf16 peak; `roofline.kernels` lists the five largest kernel instances with their ncu DRAM traffic
+  cpu_baseline: the oracle port of the reference algorithm (oracle/torch_reference.py, fp32, per-token conditioning, dense masks - the
+           reference's cost structure) timed on this box's host cores on a bounded sample
 """
 from __future__ import annotations
 

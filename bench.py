@@ -161,7 +161,8 @@ def run_b200_arm(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')       # NCCL's version / debug lines must not mix with the ONE JSON line on stdout
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':     # NCCL's banner goes to stdout: keep stdout to the ONE JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id = torch.device('cuda', local))
     dev = torch.device('cuda', local)

@@ -226,7 +226,9 @@ class DataParallelTrainer:
             for p in model.parameters():
                 p.grad = None
             loss = model(batch, times = times, **fw)
-        if cuda and self.overlap:
+        # With graph replay enabled every step - captured or eager - issues exactly ONE all-reduce of the whole gradient buffer, so ranks whose
+        # batches have different shape signatures (one replaying, one still eager) stay in lock-step on the communicator.
+        if cuda and self.overlap and not self.cuda_graph:
             bounds = self._bucket_bounds(eng)
             if self.comm_stream is None:
                 self.comm_stream = torch.cuda.Stream()

@@ -8,6 +8,10 @@ itself (oracle/make_golden.py).  It mirrors the reference's COST structure on pu
 evaluated per token (T.py:1132, 749, 767), dense N x N scores with an explicit boolean mask
 (T.py:452-470, 998-1013), padded batches - so that timing it is a fair stand-in for the reference's CPU path.
 
+Parity unpinned UPSTREAM for two conventions only: the RoPE pairing / base (third-party `rotary_embedding_torch>=0.8.4`) and the
+fixed-grid midpoint solver (`torchdiffeq`) are not in /root/reference; their published algorithms are restated in oracle/shims and the
+reference's own self-consistency tests (tests/test_transfusion.py:559-662, 758-808 of the reference) pass through them.
+
 Citations are to /root/reference/transfusion_pytorch/transfusion.py ("T.py").
 Never imported by the product package.
 """

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define TFX_B200_VERSION 100
+#define TFX_B200_VERSION 200
 
 const char* tfx_last_error(void);
 int tfx_version(void);
@@ -39,10 +39,12 @@ int tfx_gemm_store(const void* A, long long lda, int a_mn_major, const void* B, 
 /* to_qk | to_v | to_gates in one GEMM (W packed [3*H*64 + 128][D]: q rows, k rows, v rows, gate rows, zero pad) with the
  * per-head qk-RMSNorm and interleaved-pair RoPE applied in the epilogue.  T.py:946 (to_qk, to_v), 950-952
  * (q_norm, k_norm), 964-965 (apply_rotary_emb), 1027 (to_gates).  Outputs q,k (post-RoPE), v: bf16 [M][H*64];
- * gates fp32 [M][H] (logits); qk_inv fp32 [M][2H] (saved 1/|x| for backward).                     */
+ * gates fp32 [M][H] (logits); qk_inv fp32 [M][2H] (saved 1/|x| for backward).
+ * kv_rows (optional, [M]): in-place kv-cache append - token m's post-RoPE key and its value are written to ROW kv_rows[m] of k / v, which
+ * then point at one layer of the slab cache (replaces the cat / pad / stack of T.py:969-977, 2257-2277); q stays dense. */
 int tfx_gemm_qkvg(const void* u, long long ldu, const void* W, long long ldw, int M, int H, int D, void* q, void* k, void* v, float* gates, float* qk_inv,
                   const float* q_gamma, const float* k_gamma, const int* rope_pos, const float* rope_cs_t /* [32][rope_len][2], see tfx_rope_table */, int rope_len,
-                  void* stream);
+                  const int* kv_rows, void* stream);
 
 /* branch output projection + AdaptiveWrapper output gate + residual:
  *   y = [A | A2] W^T + bias ;  x_out = x_res + y * (cond_row[m] >= 0 ? zgate[cond_row[m]] : layerscale + 1)
@@ -69,7 +71,8 @@ int tfx_attn_fwd(const void* q, const void* k, const void* v, long long ld_q, lo
 int tfx_attn_fast_params(const float* q_gamma, const float* k_gamma, int dim_head, float scale, float softcap, float* params /* [>=2] device */, void* stream);
 int tfx_attn_fwd_tc(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
                     const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
-                    void* o, long long ld_o, float* lse, int M, float scale, float softcap, const float* fast_params, void* stream);
+                    void* o, long long ld_o, float* lse, int M, int M_kv /* rows of k / v when they are a kv cache (T.py:969-972); 0 = M */, float scale, float softcap,
+                    const float* fast_params, void* stream);
 /* dq_zero (optional): fp32 [M][H*64] accumulator of tfx_attn_bwd, cleared here in the same pass */
 int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, float* dq_zero, int M, int H, void* stream);
 int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
@@ -159,6 +162,34 @@ int tfx_grad_sumsq(const float* grads, long long n, double* sumsq_accum, void* s
 int tfx_clip_by_norm(float* grads, long long n, const double* sumsq, float max_norm, float pre_scale, void* stream);
 /* EMA copy of the flat parameter buffer (ema_pytorch update, T.py:1687-1697): ema = decay*ema + (1-decay)*params */
 int tfx_ema_update(float* ema, const float* params, long long n, float decay, void* stream);
+
+/* ---------------------------------------------------------------- kv-cache sampler (sample_many T.py:2079-2583, generate_text_only T.py:2669-2707)
+ * Cache layout: per layer one K and one V matrix bf16 [n_slabs * cap][H*64]; sample s owns rows [(slab0+s)*cap, (slab0+s+1)*cap).  Appends are
+ * in place (tfx_gemm_qkvg kv_rows) - this replaces the per-step pad / cat of T.py:2257-2277, 2323-2327, 2531-2533 - and visibility is
+ * (slab start, filled length) per sample instead of the Bool[g, Lq, L+Lq] masks of T.py:2300-2304, 2415-2431.
+ * Sampler state: int32 [6][S] = len (committed cache rows), tokens_seen (next RoPE position, T.py:2332), last_token, phase (0 text, 1 waiting for
+ * the modality phase, 2 done), num_tokens, hist_len;  hist int32 [S][hist_cap] = every sampled token;  counters int32 [2] = {samples still in the
+ * text phase after the last step, step number}. */
+
+/* per-token metadata of the next text step from the sampler state: token s = (last_token[s], RoPE position tokens_seen[s]) is appended at row
+ * len[s] of its slab and attends rows [0, len[s]] (step_text, T.py:2279-2310).  One single-row attention tile per sample. */
+int tfx_decode_prep(const int* state, int S, int cap, int slab0, int* text_id, int* rope_pos, int* kv_row, int* kv_limit, int* tile_q0, int* tile_qend, int* tile_kv0,
+                    int* tile_kvend, int* counters, void* stream);
+/* decode attention: every tile holds ONE query row (T.py:998-1027 with the cache concat of T.py:969-972): keys / values are rows
+ * [tile_kv0, min(tile_kvend, kv_limit[row]+1)) of the cache; soft-cap, softmax, value gate as tfx_attn_fwd. */
+int tfx_attn_decode(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H, const int* kv_limit,
+                    const int* tile_q0, const int* tile_kv0, const int* tile_kvend, int n_tiles, void* o, long long ld_o, float scale, float softcap, void* stream);
+/* token sampling + state update for every sample in the text phase (sample_text_token T.py:580-591; greedy / gumbel of generate_text_only
+ * T.py:2692-2698 with vlimit = num_text_tokens; bookkeeping T.py:2330-2349).  rows (optional): logits row of sample s (first token after the
+ * prefill, taken at the last prompt position, T.py:2225-2250: advance = 0 - that token only gets its cache row on the next step). */
+int tfx_sample_tokens(const float* logits, long long ld_logits, const int* rows, int V, int vlimit, int* state, int S, int* hist, int hist_cap, int eos_id, const int* som_ids,
+                      int n_som, int max_length, float temperature, float min_p, unsigned long long seed, int* counters, int advance, void* stream);
+/* fixed-grid explicit midpoint (torchdiffeq method='midpoint', T.py:1314-1318, 2523-2525) on device state; tab [n_evals][4] = (t, c, h, mode), *idx = the
+ * current evaluation.  pre: x_eval (dup copies back to back) = y + c f_prev, cond_times[0..n_cond) = t.  post: f = u + cfg (c - u) (T.py:2521; pred_uncond
+ * NULL = no guidance); mode 0: f_prev = f, mode 1: y += h f. */
+int tfx_ode_pre(const float* y, const float* f_prev, float* x_eval, long long n, int dup, const float* tab, const int* idx, float* cond_times, int n_cond, void* stream);
+int tfx_ode_post(float* y, float* f_prev, const float* pred_cond, const float* pred_uncond, float cfg_scale, long long n, const float* tab, const int* idx, void* stream);
+int tfx_counter_inc(int* counter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -125,9 +125,130 @@ def run_sampling(ref, name, ctor, seed):
         print('  sample:', [tuple(p.shape) if torch.is_tensor(p) else ('mod', p[0], tuple(p[1].shape)) for p in s])
 
 
+def text_runs(model, sample, n_prompt_parts):
+    """generated text of one output sample as a list of runs (one per text phase), prompt text excluded"""
+    runs = []
+    for j, part in enumerate(sample):
+        if torch.is_tensor(part):
+            runs.append(part.tolist())
+    return runs
+
+
+def run_sampling_sized(ref, name, ctor, seed, n_each, mod_len, steps, max_length, force = True):
+    """config 5 of SURVEY.md 8(d) at a GPU-meaningful size: 4 x n_each mixed prompts (raw text / raw modality / None / text + modality), greedy text,
+    seeded init noise, one forced modality of `mod_len` tokens at the start of every sample, `steps` midpoint steps, cfg 3.
+    Besides the outputs, the fixture stores the reference's top-2 logit margin at EVERY sampled text token (`margins[i][k]`), recovered by
+    replaying the reference's phase-grouped schedule over the recorded `sample_text_token` calls (every recorded token is checked against the
+    output, so a wrong attribution cannot pass silently): the GPU test needs it to tell a bf16 near-tie from a real mismatch."""
+    import copy
+    torch.manual_seed(0)
+    model = ref.Transfusion(**ctor)
+    synth.fill_parameters_(model, seed = seed)
+    model.eval()
+    g = torch.Generator().manual_seed(1234 + seed)
+    dl = ctor['dim_latent']
+    V = ctor['num_text_tokens']
+    prompts = []
+    for k in range(n_each):
+        prompts.append(torch.randint(0, V, (16,), generator = g))
+        prompts.append((0, torch.randn(int(torch.randint(4, 33, (1,), generator = g)), dl, generator = g)))
+        prompts.append(None)
+        prompts.append([torch.randint(0, V, (8,), generator = g), (0, torch.randn(int(torch.randint(6, 33, (1,), generator = g)), dl, generator = g))])
+    noise = torch.randn(mod_len, dl, generator = g)
+    kw = dict(max_length = max_length, text_temperature = 0., cfg_scale = 3., modality_steps = steps, init_modality_noise = noise, return_unprocessed_modalities = True)
+    if force:
+        kw['force_modality_at_start'] = (0, (mod_len,))
+    calls = []
+    tmod = sys.modules['transfusion_pytorch.transfusion']
+    orig = tmod.sample_text_token
+    def recording(logits, temperature = 1.0, min_p = 0.1):
+        out = orig(logits, temperature, min_p)
+        lg = logits.detach().float().reshape(-1, logits.shape[-1])
+        top2 = lg.topk(2, dim = -1).values
+        calls.append([(int(t), float(a - b)) for t, a, b in zip(out.reshape(-1).tolist(), top2[:, 0].tolist(), top2[:, 1].tolist())])
+        return out
+    with mock.patch.object(tmod, 'sample_text_token', recording):
+        out = model.sample_many(copy.deepcopy(prompts), **kw)
+    # ---- attribute the recorded rows to (sample, generated-token index) by replaying the schedule (T.py:2225-2250, 2563-2573)
+    B = len(out)
+    prep = [model.prepare_prompt_sample(copy.deepcopy(p), kw.get('force_modality_at_start'))[0] for p in prompts]
+    n_prompt_text = []
+    starts_in_modality = []
+    runs = []
+    for i in range(B):
+        pp, oo = prep[i], out[i]
+        last_prompt = pp[-1]
+        assert torch.is_tensor(last_prompt)
+        starts_in_modality.append(int(last_prompt[-1]) in model.som_ids)
+        # generated text: the tail of the part that continues the last prompt text, then every later text part
+        k0 = len(pp) - 1
+        first = oo[k0][last_prompt.numel():].tolist()
+        r = [first] if not starts_in_modality[-1] else []
+        assert starts_in_modality[-1] is False or len(first) == 0
+        r += [part.tolist() for part in oo[k0 + 1:] if torch.is_tensor(part)]
+        # a text part right after a decoded modality starts with the [eom] the sampler appended itself (not a sampled token)
+        fixed = []
+        for j, run in enumerate(r):
+            is_after_modality = not (j == 0 and not starts_in_modality[-1])
+            fixed.append(run[1:] if is_after_modality else run)
+        runs.append(fixed)
+    margins = [[] for _ in range(B)]
+    cur = [0] * B                       # run index per sample
+    ci = 0
+    # first tokens (1-D calls) for samples that start in the text phase
+    for i in range(B):
+        if not starts_in_modality[i]:
+            (tok, mg), = calls[ci]; ci += 1
+            assert tok == runs[i][0][0], (i, tok, runs[i][0][:3])
+            margins[i].append(mg)
+    pos = [1 if not starts_in_modality[i] else 0 for i in range(B)]      # next token inside the current run
+    def in_text(i):
+        return cur[i] < len(runs[i]) and pos[i] < len(runs[i][cur[i]])
+    rnd = 0
+    while ci < len(calls):
+        active = [i for i in range(B) if (rnd > 0 or not starts_in_modality[i]) and cur[i] < len(runs[i]) and (pos[i] < len(runs[i][cur[i]]))]
+        # a run that is already complete (e.g. its only token was the first-token sample) does not take part in this round
+        while active:
+            rows = calls[ci]; ci += 1
+            assert len(rows) == len(active), (len(rows), active)
+            for (tok, mg), i in zip(rows, active):
+                assert tok == runs[i][cur[i]][pos[i]], (i, cur[i], pos[i], tok)
+                margins[i].append(mg); pos[i] += 1
+            active = [i for i in active if pos[i] < len(runs[i][cur[i]])]
+        for i in range(B):               # next round: every sample that finished a run (or waited in the modality phase) moves to its next run
+            if rnd > 0 or not starts_in_modality[i]:
+                if cur[i] < len(runs[i]):
+                    cur[i] += 1; pos[i] = 0
+        rnd += 1
+    assert all(len(margins[i]) == sum(len(r) for r in runs[i]) for i in range(B)), 'schedule replay did not consume every sampled token'
+    fx = dict(name = name, ctor = ctor, seed = seed, prompts = prompts, noise = noise, kw = {k: v for k, v in kw.items() if k != 'init_modality_noise'}, samples = out,
+              generated = [[t for r in runs[i] for t in r] for i in range(B)], margins = margins)
+    torch.save(fx, os.path.join(GOLDEN, f'{name}.pt'))
+    for i, s in enumerate(out):
+        print(f'  sample {i}:', [tuple(p.shape) if torch.is_tensor(p) else ('mod', p[0], tuple(p[1].shape)) for p in s], 'min margin %.4f' % min(margins[i], default = float('nan')))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok = True)
     ref = load_reference()
+    only = os.environ.get('GOLDEN_ONLY', '')
+
+    if only in ('', 'config5'):
+        ctor = dict(num_text_tokens = 256, dim_latent = 384, modality_default_shape = (64,), transformer = dict(dim = 512, depth = 8))
+        run_sampling_sized(ref, 'config5_mid', ctor, seed = 21, n_each = 2, mod_len = 64, steps = 8, max_length = 96)
+    if only in ('', 'config5free'):
+        # no forced modality: samples start in the text phase, [som] tokens are SAMPLED (the never-cached-[som] path of T.py:2337-2349)
+        ctor = dict(num_text_tokens = 16, dim_latent = 32, modality_default_shape = (6,), transformer = dict(dim = 128, depth = 2, heads = 2))
+        run_sampling_sized(ref, 'sampling_free', ctor, seed = 5, n_each = 2, mod_len = 6, steps = 4, max_length = 40, force = False)
+    if only in ('', 'config4'):
+        # config 4 (two modalities, span-mask stress) at the graded width / depth, from the reference itself
+        ctor = dict(num_text_tokens = 256, dim_latent = (384, 192), modality_default_shape = ((4,), (2,)), transformer = dict(dim = 512, depth = 8))
+        batch = synth.config4_batch(2, seed = 31)
+        times = torch.rand(2, count_modalities(batch), generator = torch.Generator().manual_seed(5))
+        rows = torch.arange(0, 1024, 41)
+        run_interleaved(ref, 'config4_d8', ctor, batch, times, seed = 13, subsample_rows = rows)
+    if only:
+        return
 
     ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), transformer = dict(dim = 128, depth = 2, heads = 2))
     run_sampling(ref, 'sampling_small', ctor, seed = 8)

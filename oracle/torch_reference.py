@@ -52,8 +52,9 @@ class TorchReference:
             idx[b, :rb.seq_lens[b]] = torch.arange(rb.cu[b], rb.cu[b + 1])
         return idx
 
-    def stack(self, rb, x0, cond_tok, is_mod, kv_limit, rope_pos, valid):
-        """x0 [b,n,d]; cond_tok [b,n] time per token or None; returns final-norm output and hiddens."""
+    def stack(self, rb, x0, cond_tok, is_mod, kv_limit, rope_pos, valid, attend = None):
+        """x0 [b,n,d]; cond_tok [b,n] time per token or None; returns final-norm output and hiddens.
+        attend(layer, q, k, v) -> o overrides the dense masked attention (kv-cache decoding: T.py:969-977)."""
         tr, D, H = self.tr, self.tr.dim, self.tr.heads
         sd = dict(self.m.named_parameters())
         B, n, _ = x0.shape
@@ -97,11 +98,14 @@ class TorchReference:
             v = F.linear(u, sd[f'{pre}.1.fn.to_v.0.weight']).reshape(B, n, H, 64).transpose(1, 2)
             q, k = _rms(q, sd[f'{pre}.1.fn.q_norm.gamma']), _rms(k, sd[f'{pre}.1.fn.k_norm.gamma'])
             q, k = _rope(q, rope_pos[:, None], freqs), _rope(k, rope_pos[:, None], freqs)
-            sim = torch.einsum('bhid,bhjd->bhij', q * 64 ** -0.5, k)
             cap = tr.softcap_value
-            sim = (sim / cap).tanh() * cap                                                  # T.py:1001
-            sim = sim.masked_fill(~mask[:, None], -torch.finfo(sim.dtype).max)
-            o = torch.einsum('bhij,bhjd->bhid', sim.softmax(dim = -1), v)
+            if attend is not None:
+                o = attend(i, q, k, v)
+            else:
+                sim = torch.einsum('bhid,bhjd->bhij', q * 64 ** -0.5, k)
+                sim = (sim / cap).tanh() * cap                                              # T.py:1001
+                sim = sim.masked_fill(~mask[:, None], -torch.finfo(sim.dtype).max)
+                o = torch.einsum('bhij,bhjd->bhid', sim.softmax(dim = -1), v)
             o = o * F.linear(u, sd[f'{pre}.1.fn.to_gates.0.weight']).transpose(1, 2)[..., None].sigmoid()   # T.py:1026-1027
             a = F.linear(o.transpose(1, 2).reshape(B, n, H * 64), sd[f'{pre}.1.fn.to_out.1.weight'])
             x = x + wrap_out(a, f'{pre}.1')
@@ -118,7 +122,32 @@ class TorchReference:
         out = _rms(x, sd['transformer.norm.gamma'])
         return out, hid
 
-    def run(self, rb, latents, eps, *, text_loss_weight = 1., flow_loss_weight = 1., vlimit = 0, modality_only = False, want_loss = True):
+    def cached_attention(self, rb, cache):
+        """attention of NEW tokens against a slab kv cache: append the new keys / values at rb.kv_row (T.py:969-972), attend rows
+        [slab start, kv_limit[i]] of the sample's slab (the explicit masks of T.py:2300-2304, 2415-2431 in closed form)."""
+        cap_rows, softcap = cache.cap, self.tr.softcap_value
+        def attend(layer, q, k, v):
+            o = torch.zeros_like(q)
+            for b in range(rb.B):
+                s0, n = int(rb.cu[b]), int(rb.seq_lens[b])
+                if n == 0:
+                    continue
+                rows = torch.as_tensor(rb.kv_row[s0:s0 + n]).long()
+                cache.k[layer][rows] = k[b, :, :n].transpose(0, 1)
+                cache.v[layer][rows] = v[b, :, :n].transpose(0, 1)
+                start = (int(rows[0]) // cap_rows) * cap_rows
+                end = int(rb.kv_limit[s0:s0 + n].max()) + 1
+                kk, vv = cache.k[layer][start:end].transpose(0, 1), cache.v[layer][start:end].transpose(0, 1)      # [H, L, 64]
+                sim = torch.einsum('hid,hjd->hij', q[b, :, :n] * 64 ** -0.5, kk)
+                sim = (sim / softcap).tanh() * softcap
+                j = torch.arange(start, end)
+                vis = j[None, :] <= torch.as_tensor(rb.kv_limit[s0:s0 + n]).long()[:, None]
+                sim = sim.masked_fill(~vis[None], -torch.finfo(sim.dtype).max)
+                o[b, :, :n] = torch.einsum('hij,hjd->hid', sim.softmax(dim = -1), vv)
+            return o
+        return attend
+
+    def run(self, rb, latents, eps, *, text_loss_weight = 1., flow_loss_weight = 1., vlimit = 0, modality_only = False, want_loss = True, cache = None):
         m, D = self.m, self.tr.dim
         sd = dict(m.named_parameters())
         idx = self.padded(rb)
@@ -154,7 +183,7 @@ class TorchReference:
         if rb.n_cond > 0:
             ct = torch.as_tensor(rb.cond_times)
             cond_tok = torch.where(is_mod, ct[cond_row.clamp(min = 0)], torch.zeros(()))    # T.py:3230-3232
-        out, hid = self.stack(rb, x0, cond_tok, is_mod, kv_limit, rope_pos, valid)
+        out, hid = self.stack(rb, x0, cond_tok, is_mod, kv_limit, rope_pos, valid, attend = self.cached_attention(rb, cache) if cache is not None else None)
         res = dict(embed = out, hiddens = hid, valid = valid)
         logits = F.linear(out, sd['to_text_logits.weight'])
         res['logits'] = logits
@@ -196,10 +225,16 @@ class OracleEngine:
         self.model = model
         self.state = None
 
-    def forward(self, rb, latents, eps, *, train, want_logits = False, vlimit = 0, text_loss_weight = 1., flow_loss_weight = 1., modality_only = False):
+    frozen = False
+
+    def pack_weights(self, force = False):
+        pass
+
+    def forward(self, rb, latents, eps, *, train, want_logits = False, vlimit = 0, text_loss_weight = 1., flow_loss_weight = 1., modality_only = False, cache = None,
+                want_preds = None):
         with torch.set_grad_enabled(train):
             res = self.ref.run(rb, latents, eps, text_loss_weight = text_loss_weight, flow_loss_weight = flow_loss_weight, vlimit = vlimit,
-                               modality_only = modality_only, want_loss = train)
+                               modality_only = modality_only, want_loss = train, cache = cache)
         valid = res['valid']
         pack = lambda t: t[valid]
         out = dict(embed = pack(res['embed']).detach(), logits = pack(res['logits']).detach(), preds = [p.detach() if p is not None else None for p in res['preds']])
@@ -211,3 +246,137 @@ class OracleEngine:
     def backward(self, gscale = None, bucket_cb = None):
         total = self.state['total']
         total.backward(gscale.detach().cpu() if gscale is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------ kv-cache decode doubles (tests only)
+class OracleKVCache:
+    """fp32 stand-in for transfusion_pytorch_b200.engine.KVCache: same slab addressing"""
+    def __init__(self, model, n_slabs, cap):
+        tr = model.transformer
+        self.n_slabs, self.cap, self.rows = n_slabs, cap, n_slabs * cap
+        self.k = torch.zeros(tr.depth, self.rows, tr.heads, 64)
+        self.v = torch.zeros(tr.depth, self.rows, tr.heads, 64)
+
+
+class OracleTextDecoder:
+    """Python restatement of the device-side text loop (csrc/decode.cu: tfx_decode_prep + tfx_sample_tokens around one incremental forward;
+    reference step_text T.py:2279-2349).  Same interface as transfusion_pytorch_b200.decode.TextDecoder."""
+    def __init__(self, engine, cache, S, *, slab0 = 0, hist_cap, eos_id, som_ids, max_length, temperature, min_p, vlimit = 0, seed = 0, use_graph = True, poll = 8):
+        import numpy as np
+        self.np = np
+        self.eng, self.cache, self.S, self.slab0 = engine, cache, S, slab0
+        self.eos_id, self.som_ids, self.max_length = eos_id, list(som_ids or []), max_length
+        self.temperature, self.min_p, self.vlimit = temperature, min_p, vlimit
+        self.gen = torch.Generator().manual_seed(int(seed))
+        self.state = np.zeros((6, S), dtype = np.int64)
+        self.hist = [[] for _ in range(S)]
+        self.text_left = 0
+
+    def set_state(self, length, tokens_seen, last_token, phase, num_tokens):
+        for r, a in enumerate((length, tokens_seen, last_token, phase, num_tokens)):
+            self.state[r] = self.np.asarray(a, dtype = self.np.int64)
+        self.state[5] = 0
+        self.hist = [[] for _ in range(self.S)]
+
+    def update_rows(self, rows):
+        for r, a in rows.items():
+            self.state[r] = self.np.asarray(a, dtype = self.np.int64)
+        self.state[5] = 0
+        self.hist = [[] for _ in range(self.S)]
+
+    def get_state(self):
+        return self.state.copy(), [self.np.asarray(h, dtype = self.np.int64) for h in self.hist]
+
+    def _pick(self, logits):
+        if self.temperature == 0.:
+            return int(logits.argmax())
+        x = logits / self.temperature
+        probs = x.softmax(dim = -1)
+        x = torch.where(probs < self.min_p * probs.amax(), torch.tensor(float('-inf')), x)          # min_p_filter, T.py:574-578
+        if self.vlimit:
+            x[self.vlimit:] = float('-inf')
+        u = torch.rand(x.shape, generator = self.gen).clamp(min = 1e-20)
+        return int((x - torch.log(-torch.log(u))).argmax())
+
+    def _update(self, logits_rows, advance):
+        st = self.state
+        left = 0
+        for s in range(self.S):
+            if st[3, s] != 0:
+                continue
+            tok = self._pick(logits_rows[s])
+            self.hist[s].append(tok); st[5, s] += 1
+            st[2, s] = tok
+            if advance:
+                st[0, s] += 1; st[1, s] += 1
+            st[4, s] += 1
+            if tok == self.eos_id: st[3, s] = 2
+            elif st[4, s] > self.max_length: st[3, s] = 2
+            elif tok in self.som_ids: st[3, s] = 1
+            left += int(st[3, s] == 0)
+        self.text_left = left
+
+    def sample_first(self, logits, rows):
+        V = self.eng.model.to_text_logits.weight.shape[0]
+        self._update([logits[int(r), :V].float() for r in rows], advance = 0)
+
+    def step(self):
+        np, S, cap, st = self.np, self.S, self.cache.cap, self.state
+        from transfusion_pytorch_b200.modality_processing import RaggedBatch
+        ln = np.minimum(st[0], cap - 1)
+        base = (self.slab0 + np.arange(S)) * cap
+        z = np.zeros(S, dtype = np.int32)
+        rb = RaggedBatch(B = S, M = S, seq_lens = np.ones(S, dtype = np.int64), cu = np.arange(S + 1, dtype = np.int64), full_lens = np.ones(S, dtype = np.int64),
+                         text_id = st[2].astype(np.int32), label = z - 1, kv_limit = (base + ln).astype(np.int32), rope_pos = st[1].astype(np.int32), cond_row = z - 1, slot = z - 1,
+                         n_cond = 0, cond_times = np.zeros(0, np.float32), n_types = 0, type_rows = [], row_token = np.zeros(0, np.int32), row_time = np.zeros(0, np.float32),
+                         latents = [], instances = [], modality_positions = [[] for _ in range(S)], total_tokens = S, n_type_tokens = [])
+        rb.kv_row = (base + ln).astype(np.int32)
+        res = self.eng.forward(rb, None, None, train = False, want_logits = True, cache = self.cache)
+        V = self.eng.model.to_text_logits.weight.shape[0]
+        self._update([res['logits'][s, :V].float() for s in range(S)], advance = 1)
+
+    def run(self, max_steps):
+        n = 0
+        while n < max_steps:
+            self.step(); n += 1
+            if self.text_left == 0:
+                break
+        return n
+
+
+def _oracle_new_cache(self, n_slabs, cap):
+    return OracleKVCache(self.model, n_slabs, cap)
+
+
+def _oracle_text_decoder(self, cache, S, **kw):
+    return OracleTextDecoder(self, cache, S, **kw)
+
+
+def _oracle_ode_solve(self, cache, rb, y, *, dup, steps, cfg_scale, use_graph = True):
+    """fixed-grid midpoint (the torchdiffeq restatement of oracle/shims) with the cond | uncond batch layout of decode.ode_solve"""
+    grid = torch.linspace(0, 1, steps)
+    types = [t for t, v in enumerate(y) if v is not None]
+    def flow(tval, ys):
+        rb.cond_times[:] = float(tval)
+        x = [torch.cat([v] * dup) if v is not None else None for v in ys]
+        res = self.forward(rb, x, None, train = False, want_preds = True, cache = cache)
+        out = []
+        for t, v in enumerate(ys):
+            if v is None:
+                out.append(None); continue
+            p = res['preds'][t]
+            pc = p[:v.shape[0]]
+            out.append(p[v.shape[0]:] + cfg_scale * (pc - p[v.shape[0]:]) if dup == 2 else pc)
+        return out
+    for t0, t1 in zip(grid[:-1], grid[1:]):
+        dt = t1 - t0
+        f0 = flow(t0, y)
+        ymid = [v + f * (0.5 * dt) if v is not None else None for v, f in zip(y, f0)]
+        f1 = flow(t0 + 0.5 * dt, ymid)
+        y = [v + dt * f if v is not None else None for v, f in zip(y, f1)]
+    return y
+
+
+OracleEngine.new_cache = _oracle_new_cache
+OracleEngine.text_decoder = _oracle_text_decoder
+OracleEngine.ode_solve = _oracle_ode_solve

@@ -38,3 +38,18 @@ def test_sample_many_matches_reference_with_oracle_engine():
     compare(out, fx['samples'])
     one = model.sample_one(copy.deepcopy(fx['prompts'][3]), init_modality_noise = fx['noise'], **fx['kw'])
     compare([one], [fx['samples'][3]])
+
+
+def test_sample_many_free_running_matches_reference_with_oracle_engine():
+    """no forced modality: [som] tokens are SAMPLED (they never get a cache row and the modality takes their RoPE position, T.py:2337-2349,
+    2408-2411), several text / modality rounds per sample, samples leave and re-enter the shared text loop at different times"""
+    fx = load_golden('sampling_free')
+    torch.manual_seed(0)
+    model = Transfusion(**fx['ctor'])
+    synth.fill_parameters_(model, seed = fx['seed'])
+    model.eval()
+    model._engine = OracleEngine(model)
+    out = run(model, fx)
+    n_prompt_mod = lambda p: 0 if (p is None or (torch.is_tensor(p) and not p.is_floating_point())) else (1 if not isinstance(p, list) else sum(not torch.is_tensor(q) or q.is_floating_point() for q in p))
+    assert any(sum(not torch.is_tensor(p) for p in s) > n_prompt_mod(fx['prompts'][i]) for i, s in enumerate(fx['samples'])), 'fixture must contain a sampled modality'
+    compare(out, fx['samples'])

@@ -7,24 +7,24 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_void_p, c_int, c_longlong, c_float, c_char_p, POINTER
+from ctypes import c_void_p, c_int, c_longlong, c_ulonglong, c_float, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libtfx_b200.so')
 
 _lib = None
 
-VP, I, LL, F = c_void_p, c_int, c_longlong, c_float
+VP, I, LL, F, ULL = c_void_p, c_int, c_longlong, c_float, c_ulonglong
 
 # name -> argtypes, mirrors include/tfx_b200.h exactly (order matters)
 SIGNATURES = {
     'tfx_init': [I],
     'tfx_gemm_store': [VP, LL, I, VP, LL, I, I, I, I, VP, LL, VP, LL, VP, VP, F, I, I, VP],
-    'tfx_gemm_qkvg': [VP, LL, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, I, VP],
+    'tfx_gemm_qkvg': [VP, LL, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, I, VP, VP],
     'tfx_gemm_resid': [VP, LL, VP, LL, I, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, LL, VP, VP],
     'tfx_gemm_geglu': [VP, LL, VP, LL, VP, I, I, I, VP, VP, VP],
     'tfx_attn_fwd': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, LL, VP, I, F, F, VP, VP],
-    'tfx_attn_fwd_tc': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, LL, VP, I, F, F, VP, VP],
+    'tfx_attn_fwd_tc': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, LL, VP, I, I, F, F, VP, VP],
     'tfx_attn_fast_params': [VP, VP, I, F, F, VP, VP],
     'tfx_attn_bwd_prep': [VP, VP, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_attn_bwd': [VP, VP, VP, VP, LL, LL, LL, LL, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP, LL, I, I, F, F, VP, VP],
@@ -57,6 +57,12 @@ SIGNATURES = {
     'tfx_clip_by_norm': [VP, LL, VP, F, F, VP],
     'tfx_ema_update': [VP, VP, LL, F, VP],
     'tfx_adam_step': [VP, VP, VP, VP, LL, F, F, F, F, F, I, I, F, I, VP, VP],
+    'tfx_decode_prep': [VP, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP],
+    'tfx_attn_decode': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, I, VP, LL, F, F, VP],
+    'tfx_sample_tokens': [VP, LL, VP, I, I, VP, I, VP, I, I, VP, I, I, F, F, ULL, VP, I, VP],
+    'tfx_ode_pre': [VP, VP, VP, LL, I, VP, VP, VP, I, VP],
+    'tfx_ode_post': [VP, VP, VP, VP, F, LL, VP, VP, VP],
+    'tfx_counter_inc': [VP, VP],
 }
 
 EXPORTED = ['tfx_last_error', 'tfx_version', 'tfx_geglu_bwd_rows_per_block', 'tfx_attn_residual_bwd_workspace_floats'] + list(SIGNATURES)

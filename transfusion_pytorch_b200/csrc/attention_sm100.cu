@@ -608,14 +608,15 @@ int tfx_attn_fast_params(const float* q_gamma, const float* k_gamma, int dim_hea
 
 int tfx_attn_fwd_tc(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
                     const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
-                    void* o, long long ld_o, float* lse, int M, float scale, float softcap, const float* fast_params, void* stream) {
+                    void* o, long long ld_o, float* lse, int M, int M_kv, float scale, float softcap, const float* fast_params, void* stream) {
   if (n_tiles <= 0) return 0;
+  if (M_kv <= 0) M_kv = M;
   TFX_REQUIRE(fast_params != nullptr, "attn_fwd_tc: fast_params (from tfx_attn_fast_params) is required");
   TFX_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 8 == 0, "attn_fwd_tc: row pitches must be multiples of 8 bf16");
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_tmap_bf16(&tq, q, (long long)H * 64, M, ld_q, FA_BM)) || (rc = make_tmap_bf16(&tk, k, (long long)H * 64, M, ld_k, FA_BN)) ||
-      (rc = make_tmap_bf16(&tv, v, (long long)H * 64, M, ld_v, FA_BN))) {
+  if ((rc = make_tmap_bf16(&tq, q, (long long)H * 64, M, ld_q, FA_BM)) || (rc = make_tmap_bf16(&tk, k, (long long)H * 64, M_kv, ld_k, FA_BN)) ||
+      (rc = make_tmap_bf16(&tv, v, (long long)H * 64, M_kv, ld_v, FA_BN))) {
     set_error("attn_fwd_tc: cuTensorMapEncodeTiled failed (%d)", rc);
     return rc;
   }

@@ -47,6 +47,8 @@ struct GemmParams {
   const int* rope_pos;         // [M]
   const float2* rope_cs;       // [32][rope_len] (cos, sin): transposed table, consecutive positions are contiguous
   int rope_len;
+  const int* kv_rows;          // optional [M]: destination ROW of token m inside k / v (in-place kv-cache append: k, v then point at a
+                               // layer's cache slabs and q stays dense); null = row m
   // ---- EPI_RESID: y = acc + bias; y_bf16 = y; x_out = x_res + y * scale(row, col)
   const float* x_res; float* x_out; __nv_bfloat16* x_out_bf16;     // [M][N]
   __nv_bfloat16* y_bf16;       // [M][N] optional (pre-scale branch output, saved for backward)
@@ -173,6 +175,26 @@ __device__ __forceinline__ void stg64_store(const uint8_t* sw, int lane, uint8_t
     const int row = it * 8 + (lane >> 2), ch = lane & 3;
     if (row < rows_valid)
       *reinterpret_cast<uint4*>(g + row * pitch + ch * 16) = *reinterpret_cast<const uint4*>(sw + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+  }
+}
+
+// row-mapped variants: slab row r of the warp goes to global row rows[r] (rows already offset to the warp's first row)
+__device__ __forceinline__ void stg64_store_rows(const uint8_t* sw, int lane, uint8_t* g, long long pitch, int rows_valid, const int* __restrict__ rows) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), ch = lane & 3;
+    if (row < rows_valid)
+      *reinterpret_cast<uint4*>(g + (long long)rows[row] * pitch + ch * 16) = *reinterpret_cast<const uint4*>(sw + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+  }
+}
+template <int CH>
+__device__ __forceinline__ void stg_store_rows(const uint8_t* sw, int lane, uint8_t* g, long long pitch, int rows_valid, const int* __restrict__ rows) {
+  constexpr int RPI = 32 / CH;
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int row = it * RPI + lane / CH, ch = lane % CH;
+    if (row < rows_valid)
+      *reinterpret_cast<uint4*>(g + (long long)rows[row] * pitch + ch * 16) = *reinterpret_cast<const uint4*>(sw + row * 128 + ((ch ^ (row & 7)) << 4));
   }
 }
 
@@ -442,7 +464,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             stg64_put(sw, lane, outw);
             __syncwarp();
-            stg64_store(sw, lane, reinterpret_cast<uint8_t*>(dstm + (long long)wrow0 * HI + head * 64 + hf * 32), HI * 2, rows_valid);
+            if (kind == 1 && p.kv_rows) stg64_store_rows(sw, lane, reinterpret_cast<uint8_t*>(dstm + head * 64 + hf * 32), HI * 2, rows_valid, p.kv_rows + wrow0);
+            else stg64_store(sw, lane, reinterpret_cast<uint8_t*>(dstm + (long long)wrow0 * HI + head * 64 + hf * 32), HI * 2, rows_valid);
             __syncwarp();
           }
         } else if (kind == 2) {
@@ -455,7 +478,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
             stg64_put(sw, lane, w);
             __syncwarp();
-            stg64_store(sw, lane, reinterpret_cast<uint8_t*>(p.v + (long long)wrow0 * HI + tis * 256 + part * 64 + hf * 32), HI * 2, rows_valid);
+            if (p.kv_rows) stg64_store_rows(sw, lane, reinterpret_cast<uint8_t*>(p.v + tis * 256 + part * 64 + hf * 32), HI * 2, rows_valid, p.kv_rows + wrow0);
+            else stg64_store(sw, lane, reinterpret_cast<uint8_t*>(p.v + (long long)wrow0 * HI + tis * 256 + part * 64 + hf * 32), HI * 2, rows_valid);
             __syncwarp();
           }
         } else if (part == 0) {
@@ -507,7 +531,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             stg_put<8>(sw, lane, outw);
             __syncwarp();
-            stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(dstm + (long long)wrow0 * HI + head * 64), HI * 2, rows_valid);
+            if (kind == 1 && p.kv_rows) stg_store_rows<8>(sw, lane, reinterpret_cast<uint8_t*>(dstm + head * 64), HI * 2, rows_valid, p.kv_rows + wrow0);
+            else stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(dstm + (long long)wrow0 * HI + head * 64), HI * 2, rows_valid);
             __syncwarp();
           }
         } else if (kind == 2) {
@@ -524,7 +549,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             stg_put<8>(sw, lane, w);
             __syncwarp();
-            stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(p.v + (long long)wrow0 * HI + tis * 128 + c * 64), HI * 2, rows_valid);
+            if (p.kv_rows) stg_store_rows<8>(sw, lane, reinterpret_cast<uint8_t*>(p.v + tis * 128 + c * 64), HI * 2, rows_valid, p.kv_rows + wrow0);
+            else stg_store<8>(sw, lane, reinterpret_cast<uint8_t*>(p.v + (long long)wrow0 * HI + tis * 128 + c * 64), HI * 2, rows_valid);
             __syncwarp();
           }
         } else if (half == 0) {

@@ -161,13 +161,17 @@ __global__ void __launch_bounds__(ROW_THREADS) ce_fwd_bwd_k(const float* __restr
     for (int c = lane; c < Vuse; c += 32) se += __expf(lr[c] - mx);
     se = warp_sum(se);
     const float lse = mx + logf(se);
-    if (lane == 0) { local += (double)(lse - lr[lab]); ++cnt; }
+    // a label outside the un-masked vocabulary (text-only path, T.py:2653: logits >= num_text_tokens are filled with -finfo.max BEFORE the
+    // cross entropy) sees the masked logit, exactly like the reference: loss = lse + FLT_MAX, gradient -1 on that column
+    const float lab_logit = lab < Vuse ? lr[lab] : -3.402823466e+38f;
+    if (lane == 0) { local += (double)lse - (double)lab_logit; ++cnt; }
     if (dr) {
       const float inv = 1.f / se;
       for (int c = lane; c < ld_d; c += 32) {
         float gq = 0.f;
-        if (c < Vuse) gq = (__expf(lr[c] - mx) * inv - (c == lab ? 1.f : 0.f)) * gscale;
-        dr[c] = __float2bfloat16(gq);
+        if (c < Vuse) gq = __expf(lr[c] - mx) * inv;
+        if (c == lab) gq -= 1.f;
+        dr[c] = __float2bfloat16(gq * gscale);
       }
     }
   }

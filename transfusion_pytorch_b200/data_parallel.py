@@ -68,6 +68,20 @@ class DataParallelTrainer:
         self.cuda_graph = cuda_graph and (self.world == 1 or graph_multi_gpu)
         self._graphs = {}
         self._copy_stream = None
+        self._synced = False
+
+    def _sync_replicas(self, eng):
+        """Replicas must start identical (what DDP / accelerate do at construction): rank 0's parameters and persistent buffers
+        (incl. the random Fourier frequencies of the time embedding) are broadcast once."""
+        if self._synced or self.world == 1:
+            self._synced = True
+            return
+        dist.broadcast(eng.flat, 0)
+        for b in self.model.buffers():
+            if b.is_cuda and b.numel():
+                dist.broadcast(b, 0)
+        eng.mark_dirty()
+        self._synced = True
 
     # ---- CUDA-graph replay of fixed-shape steps
     @staticmethod
@@ -135,6 +149,7 @@ class DataParallelTrainer:
             if self.ema_decay is not None and getattr(eng, 'ema_flat', None) is None:
                 eng.ema_flat = eng.flat.clone()          # must exist before the capture (an allocation + copy inside it would be replayed)
             import copy
+            eng.pin_workspaces()                         # workspace buffers that later have to grow are retired, not freed
             g.rb = copy.copy(rb)                         # descriptor object whose device views point into the static metadata buffer
             g.rb.dev = eng.meta_views(rb, g.meta, layout)
             rb = g.rb
@@ -159,6 +174,7 @@ class DataParallelTrainer:
             g.launches = eng.ops.launches - l0           # kernels of ours inside one replay
             eng.ops.launches = l0
             g.graph = graph
+            g.pins = (dict(eng.ws), dict(eng.packed), eng.fastp, eng.flat, eng.gflat, eng.exp_avg, eng.exp_avg_sq)   # every address the graph baked in
         eng.opt_step += 1
         eng._grads_clean = True                          # the graph ends with the Adam pass that clears the gradient buffer
         g.graph.replay()
@@ -173,13 +189,15 @@ class DataParallelTrainer:
     def _bucket_bounds(self, eng):
         """flat-buffer offset where each layer's parameters start (layers are contiguous in named_parameters order)"""
         if getattr(self, '_bounds', None) is None:
+            # conditioning-path parameters live in the "late" region of the flat buffer (engine.attach): their gradients are only
+            # final after backward() returns, so they are never part of a per-layer bucket
             starts = {}
             for name, off in eng.offs.items():
-                if name.startswith('transformer.layers.'):
+                if name.startswith('transformer.layers.') and off < eng.late_start:
                     i = int(name.split('.')[2])
                     starts[i] = min(starts.get(i, 1 << 62), off)
             self._bounds = starts
-            self._tail = max((off + eng.named[n].numel() for n, off in eng.offs.items() if n.startswith('transformer.layers.')), default = 0)
+            self._tail = max((off + eng.named[n].numel() for n, off in eng.offs.items() if n.startswith('transformer.layers.') and off < eng.late_start), default = 0)
         return self._bounds
 
     def _finish_step(self, eng):
@@ -195,6 +213,7 @@ class DataParallelTrainer:
         device): CUDA-graph replay when the shape signature has been seen before, eager launches otherwise.  Single process only."""
         model, eng = self.model, self.model.engine
         eng.ensure_attached()
+        self._sync_replicas(eng)
         eng.upload(rb)
         loss = self._graph_step(rb, device_lat = latents) if self.cuda_graph else None
         if loss is None:
@@ -212,6 +231,7 @@ class DataParallelTrainer:
         cuda = hasattr(eng, 'gflat') or model.device.type == 'cuda'
         if cuda:
             eng.ensure_attached()
+            self._sync_replicas(eng)
             if self.cuda_graph and model.training and not fw and torch.is_grad_enabled():
                 rb, _ = model.pack(batch, times = times)
                 loss = self._graph_step(rb)

@@ -37,6 +37,27 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+_EMPTY_I32 = np.zeros(0, dtype = np.int32)
+
+
+class KVCache:
+    """Slab kv cache (decode path; reference layout `(layers, 2, batch, heads, seq, dim_head)`, T.py:976-977, 1264, 2260, re-padded and
+    concatenated per step there).  Here: per layer one K (post-RoPE) and one V matrix, bf16 `[n_slabs * cap, heads * 64]`, token-major like
+    every other activation; sample / branch `s` owns rows `[s * cap, (s + 1) * cap)`.  Appends happen in place from the QKVG GEMM epilogue;
+    how much of a slab is valid is host / device bookkeeping of the sampler (`len`), never a mask tensor."""
+
+    def __init__(self, engine, n_slabs: int, cap: int):
+        self.n_slabs, self.cap, self.rows = int(n_slabs), int(cap), int(n_slabs) * int(cap)
+        nbytes = 2 * engine.depth * self.rows * engine.HI * 2
+        assert nbytes < 96 << 30, f'kv cache of {nbytes / 2**30:.1f} GiB requested ({n_slabs} slabs x {cap} rows): lower max_length / batch the prompts'
+        # zero-filled: rows past a slab's filled length are read by whole-tile loads (and multiplied by p = 0): they must be finite
+        self.k = torch.zeros(engine.depth, self.rows, engine.HI, device = engine.device, dtype = BF16)
+        self.v = torch.zeros(engine.depth, self.rows, engine.HI, device = engine.device, dtype = BF16)
+
+    def slab_start(self, s):
+        return np.asarray(s, dtype = np.int64) * self.cap
+
+
 class Engine:
     def __init__(self, model):
         self.ops = _lib.Ops()                       # raises loudly if the extension is missing
@@ -60,10 +81,11 @@ class Engine:
         self.device = None
         self.flat = None
         self.ws = {}
-        self._packed_version = None
         self._dirty = True
         self._ptr_arrays = []
         self.launches = 0
+        self.graph_pins = None                      # list of retired workspace tensors once any CUDA graph has been captured
+        self.frozen = False                         # True inside a sampling session: parameters cannot change, skip the re-pack check
 
     # ------------------------------------------------------------------ parameters
     def _trainable(self):
@@ -78,6 +100,11 @@ class Engine:
         """Move all trainable parameters into one flat fp32 buffer (views keep the state_dict layout) with a
         matching flat gradient buffer: one fused Adam launch, one all-reduce, wgrad GEMMs write straight in."""
         named = self._trainable()
+        # Flat-buffer order = bucket order of the data-parallel all-reduce.  Gradients of the conditioning path (to_time_cond, every
+        # to_film / to_ada_ln_zero) are produced AFTER the layer loop of backward() from tables accumulated over all layers, so those
+        # parameters live in a "late" region behind the per-layer parameters: a layer bucket handed to NCCL is then really final.
+        late = lambda n: ('.to_film.' in n) or ('.to_ada_ln_zero.' in n) or n.startswith('transformer.to_time_cond.')
+        named = [(n, p) for n, p in named if not late(n)] + [(n, p) for n, p in named if late(n)]
         dev = named[0][1].device
         if dev.type != 'cuda':
             raise _lib.TfxError(f'the B200 engine needs the model on a CUDA device (got {dev}); there is no CPU path')
@@ -96,15 +123,24 @@ class Engine:
             p.data = flat[o:o + k].view(p.shape)
             p.grad = gflat[o:o + k].view(p.shape)
         self.flat, self.gflat, self.offs, self.named = flat, gflat, offs, dict(named)
+        self.named_first = named[0][1]
         self.exp_avg = self.exp_avg_sq = None
         self.opt_step = 0
         self._first_ptr = named[0][1].data_ptr()
+        self.late_start = min((offs[n] for n, _ in named if late(n)), default = total)
         self._build_maps()
+        self._dirty = True
+        if not getattr(self, '_hooked', False):          # checkpoints loaded after the first forward must reach the bf16 operand copies
+            self.model.register_load_state_dict_post_hook(lambda *a, **k: self.mark_dirty())
+            self._hooked = True
+
+    def mark_dirty(self):
+        """Tell the engine that parameter VALUES changed outside its own optimizer (manual `p.add_`, custom optimizers stepping in
+        eval mode ...): the next forward re-packs the bf16 GEMM operand copies.  Training forwards always re-pack."""
         self._dirty = True
 
     def ensure_attached(self):
-        named = self._trainable()
-        if self.flat is None or named[0][1].data_ptr() != self._first_ptr:
+        if self.flat is None or self.named_first.data_ptr() != self._first_ptr:
             self.attach()
 
     def P(self, name):            # parameter tensor by state-dict name
@@ -162,11 +198,19 @@ class Engine:
         t = self.ws.get(name)
         n = int(np.prod(shape)) if len(shape) else 1
         if t is None or t.dtype != dtype or t.numel() < n:
+            if t is not None and self.graph_pins is not None:
+                self.graph_pins.append(t)       # a captured graph may hold this address: never hand the block back to the allocator
             t = torch.empty(max(n, 1), device = self.device, dtype = dtype)
             self.ws[name] = t
             if zero:
                 t.zero_()
         return t[:n].view(shape)
+
+    def pin_workspaces(self):
+        """Called before a CUDA-graph capture: from now on a workspace buffer that has to grow is retired, not freed (captured graphs
+        bake raw device pointers; see data_parallel._StepGraph and sampling.DecodeSession)."""
+        if self.graph_pins is None:
+            self.graph_pins = []
 
     def _build_pack_jobs(self):
         """Destination buffers + the device-resident job table of `tfx_cast_pack_multi` (built once per attach)."""
@@ -222,9 +266,13 @@ class Engine:
         self._pack_nblocks = len(blk_job)
         self._pack_ptr = self._first_ptr
 
-    def pack_weights(self):
-        """fp32 master parameters -> bf16 GEMM operands in kernel layouts: ONE launch per optimizer step."""
-        if not self._dirty and self._packed_version == self.flat._version:
+    def pack_weights(self, force = False):
+        """fp32 master parameters -> bf16 GEMM operands in kernel layouts: ONE launch.  Parameters are views of the flat buffer with their
+        own version counters, so in-place updates by torch.optim / load_state_dict / user code are invisible here: training forwards
+        therefore ALWAYS re-pack (force = True, ~0.1 ms); inference forwards re-pack when the engine knows of a change (its own optimizer,
+        backward(), load_state_dict hook, `mark_dirty()`)."""
+        have = getattr(self, 'packed', None) is not None and getattr(self, '_pack_ptr', None) == self._first_ptr
+        if have and not self._dirty and (self.frozen or not force):
             return
         if getattr(self, '_pack_ptr', None) != self._first_ptr:
             self._build_pack_jobs()
@@ -236,16 +284,15 @@ class Engine:
             pre = f'transformer.layers.{i}.1.fn'
             self.ops.attn_fast_params(self.P(f'{pre}.q_norm.gamma'), self.P(f'{pre}.k_norm.gamma'), 64, self.scale, self.softcap, self.fastp[i])
         self._dirty = False
-        self._packed_version = self.flat._version
 
     # ------------------------------------------------------------------ descriptor upload
     META_NAMES = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
-                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order']
+                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order', 'kv_row']
 
     def stage_meta(self, rb: RaggedBatch):
         """All per-token / per-tile int32 metadata and the float metadata of a batch in ONE pooled pinned buffer.
         Returns (raw pinned buffer, int32 view, layout) - layout = (sizes per array, n_int, n_float)."""
-        ints = [getattr(rb, n) for n in self.META_NAMES]
+        ints = [getattr(rb, n) if getattr(rb, n) is not None else _EMPTY_I32 for n in self.META_NAMES]
         sizes = [_round_up(a.shape[0], 4) for a in ints]
         fl = np.concatenate([rb.cond_times, rb.row_time]).astype(np.float32)
         n_int, n_fl = sum(sizes), _round_up(fl.shape[0], 4)
@@ -285,6 +332,8 @@ class Engine:
         n = _round_up(max_pos + 1, 1024)
         t = self.ws.get('rope_cs')
         if t is None or t.shape[0] < n:
+            if t is not None and self.graph_pins is not None:
+                self.graph_pins += [t, self.ws['rope_cs_t']]
             t = torch.empty(n, 32, 2, device = self.device, dtype = F32)
             tt = torch.empty(32, n, 2, device = self.device, dtype = F32)
             self.ops.rope_table(self.model.rotary_emb.freqs.detach().float().contiguous(), t, tt, n, 32)
@@ -300,12 +349,12 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, rb: RaggedBatch, latents: list | None, eps: list | None, *, train: bool, want_logits = False, vlimit = 0,
-                text_loss_weight = 1., flow_loss_weight = 1., modality_only = False):
+                text_loss_weight = 1., flow_loss_weight = 1., modality_only = False, cache: KVCache | None = None, want_preds = None):
         """Runs the block stack over a ragged batch.  `latents[t]`: fp32 [S_t, dl_t] device tensors (clean latents when
         `eps` is given, already-noised / decode-time latents otherwise).  With train=True activations are kept for
         `backward()` and the fused loss heads produce the loss scalars and the head gradients in the same pass."""
         self.ensure_attached()
-        self.pack_weights()
+        self.pack_weights(force = train)
         o, D, HI, H, Ip, M = self.ops, self.D, self.HI, self.H, self.Ip, rb.M
         dv = self.upload(rb)
         nc, S = rb.n_cond, rb.S
@@ -314,6 +363,12 @@ class Engine:
         rope = self.rope_table(rb.max_rope_pos)
         cond_row = dv['cond_row'] if nc > 0 else None
         tag = 'T' if train else 'I'
+        # kv-cache (incremental) forward: the M tokens of `rb` are NEW tokens; their keys / values are appended in place at rows
+        # dv['kv_row'] of the cache slabs and kv_limit / the attention tile tables are expressed in cache-row coordinates
+        assert cache is None or not train, 'the kv cache is an inference-time structure'
+        kv_rows = dv['kv_row'] if cache is not None else None
+        M_kv = cache.rows if cache is not None else 0
+        want_preds = want_logits if want_preds is None else want_preds
 
         # ---- conditioning tables, one row per distinct time (reference evaluates them per token: T.py:1132,749,767)
         if nc > 0:
@@ -391,17 +446,25 @@ class Engine:
             zgF = zg[:, wF * D:] if nc > 0 else None
             uA = self.buf(f'{lt}uA', (M, D), BF16); statsA = self.buf(f'{lt}sA', (M, 2), F32)
             o.adaln_fwd(x_a, cond_row, filmA, tab_ld, self.P(f'{pre}.1.layernorm_gamma'), uA, statsA, M, D)
-            q = self.buf(f'{lt}q', (M, HI), BF16); k = self.buf(f'{lt}k', (M, HI), BF16); v = self.buf(f'{lt}v', (M, HI), BF16)
+            q = self.buf(f'{lt}q', (M, HI), BF16)
+            if cache is not None:
+                k, v = cache.k[i], cache.v[i]
+            else:
+                k = self.buf(f'{lt}k', (M, HI), BF16); v = self.buf(f'{lt}v', (M, HI), BF16)
             gates = self.buf(f'{lt}g', (M, H), F32); qk_inv = self.buf(f'{lt}qi', (M, 2 * H), F32)
             o.gemm_qkvg(uA, D, pk[f'qkvg{i}'], D, M, H, D, q, k, v, gates, qk_inv, self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'),
-                        dv['rope_pos'], self.ws['rope_cs_t'], int(self.ws['rope_cs_t'].shape[1]))
+                        dv['rope_pos'], self.ws['rope_cs_t'], int(self.ws['rope_cs_t'].shape[1]), kv_rows)
             att = self.buf(f'{lt}o', (M, HI), BF16); lse = self.buf(f'{lt}lse', (H, M), F32)
             fp = self.fastp[i]
-            # both kernels are enqueued; the one whose precondition (read from `fp` on the device) fails returns immediately
-            o.attn_fwd_tc(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['t2_q0'], dv['t2_qend'], dv['t2_kv0'], dv['t2_kvend'], int(rb.t2_q0.shape[0]),
-                          att, HI, lse, M, self.scale, self.softcap, fp)
-            o.attn_fwd(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_qend'], dv['tile_kv0'], dv['tile_kvend'], n_tiles,
-                       att, HI, lse, M, self.scale, self.softcap, fp)
+            if getattr(rb, 'single_row_tiles', False):
+                # text decode: one query row per sample against its cache slab (split-KV decode kernel)
+                o.attn_decode(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_kv0'], dv['tile_kvend'], n_tiles, att, HI, self.scale, self.softcap)
+            else:
+                # both kernels are enqueued; the one whose precondition (read from `fp` on the device) fails returns immediately
+                o.attn_fwd_tc(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['t2_q0'], dv['t2_qend'], dv['t2_kv0'], dv['t2_kvend'], int(rb.t2_q0.shape[0]),
+                              att, HI, lse, M, M_kv, self.scale, self.softcap, fp)
+                o.attn_fwd(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_qend'], dv['tile_kv0'], dv['tile_kvend'], n_tiles,
+                           att, HI, lse, M, self.scale, self.softcap, fp)
             x_b = self.buf(f'{lt}xb', (M, D), F32); yA = self.buf(f'{lt}yA', (M, D), BF16) if train else None
             o.gemm_resid(att, HI, None, 0, 0, pk[f'wo{i}'], HI, M, D, HI, None, x_a, x_b, None, yA, cond_row, zgA, zg_ld, self.P(f'{pre}.1.layerscale'))
             uF = self.buf(f'{lt}uF', (M, D), BF16); statsF = self.buf(f'{lt}sF', (M, 2), F32)
@@ -438,7 +501,7 @@ class Engine:
             res['logits'] = logits
             st['logits'] = logits
         preds = []
-        if S > 0 and (train or want_logits):
+        if S > 0 and (train or want_preds):
             for t, (s0, s1) in enumerate(rb.type_rows):
                 n = s1 - s0
                 if n == 0:
@@ -516,6 +579,7 @@ class Engine:
         assert st['train'], 'backward() needs a train forward'
         self._prepare_grads()
         self._grads_clean = False
+        self._dirty = True                      # an optimizer step (ours or torch.optim's) normally follows
         if gscale is not None:
             gs = gscale.detach().float().reshape(1)
             self.ops.scale_bf16(st['dlogits'], gs, st['dlogits'].numel())
@@ -614,8 +678,8 @@ class Engine:
             dq = self.buf('dq', (M, HI), F32); dk = self.buf('dk', (M, HI), F32)
             o.attn_bwd_prep(dog, L['att'], L['gates'], dop, dsum_hm, dsum_mh, dq, M, H)
             dqkvg = self.buf('dqkvg', (M, self.NQ), BF16)
-            if self.ws.get('dqkvg_shape') != (M, self.NQ):          # pad columns are never written by the kernels: clear once per shape
-                dqkvg.zero_(); self.ws['dqkvg_shape'] = (M, self.NQ)
+            if i == self.depth - 1:
+                dqkvg[:, 3 * HI + H:].zero_()   # pad columns are never written by the kernels; cleared once per backward (inside captured graphs too)
             fp = self.fastp[i]
             o.attn_bwd_tc(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['k2_kv0'], dv['k2_kvend'], dv['k2_q0'], dv['k2_qend'],
                           dv['k2_order'], int(rb.k2_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
@@ -674,6 +738,19 @@ class Engine:
             o.table_op(dcond, 4 * D, st['cpre'], 4 * D, None, 0, dcpre, 4 * D, nc, 4 * D, 3)
             o.gemm_store(dcpre, 4 * D, 1, st['feats'], self.Kt, 1, 4 * D, D + 1, nc, self.gflat, 0, None, 0, None, self.wt_rows, 1.0, 1, 1)
             o.colsum_bf16(dcpre, 4 * D, nc, 4 * D, None, self.G('transformer.to_time_cond.1.bias'))
+
+    # ------------------------------------------------------------------ kv-cache decode (sampling.py drives these)
+    def new_cache(self, n_slabs: int, cap: int) -> KVCache:
+        self.ensure_attached()
+        return KVCache(self, n_slabs, cap)
+
+    def text_decoder(self, cache, S, **kw):
+        from .decode import TextDecoder
+        return TextDecoder(self, cache, S, **kw)
+
+    def ode_solve(self, cache, rb, y, **kw):
+        from .decode import ode_solve
+        return ode_solve(self, cache, rb, y, **kw)
 
     # ------------------------------------------------------------------ optimizer
     def zero_grad(self):

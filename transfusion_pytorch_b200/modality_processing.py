@@ -91,6 +91,8 @@ class RaggedBatch:
     k2_q0: np.ndarray = None
     k2_qend: np.ndarray = None
     k2_order: np.ndarray = None             # 128-key tiles sorted by the number of query tiles that see them (persistent attention backward)
+    kv_row: np.ndarray = None               # kv-cache forward only: cache row each (new) token's key / value is appended at
+    single_row_tiles: bool = False          # every attention tile holds exactly one query row (text decode): use the decode kernel
     max_rope_pos: int = 0
     has_labels: bool = False
     n_valid: int = 0
@@ -269,6 +271,39 @@ def pack_batch(
         total_tokens = int(full_lens.sum()), n_type_tokens = n_type_tokens, max_rope_pos = max_rope, has_labels = return_loss)
     rb.n_valid = int((label >= 0).sum())
     build_tiles(rb, qfirst)
+    return rb
+
+
+def pack_incremental(samples: list, times, model, *, slab: np.ndarray, base_len: np.ndarray, rope_base: np.ndarray, cap: int) -> RaggedBatch:
+    """Descriptor of a kv-cache (incremental) forward: `samples[b]` are the NEW parts of sample b (a whole prompt for the prefill, one token
+    for a text step, one `(type, latents)` for a modality step), appended to cache slab `slab[b]` which already holds `base_len[b]` rows.
+
+    The token layout / mask / positions are those of `pack_batch(return_embed = True)` (no [meta] / [som] / [eom] are added around
+    modalities, as in the reference's decode-time calls: T.py:2194-2201, 2389-2406) shifted into cache-row coordinates:
+      * `kv_row[i]`   = slab start + base_len + local position            (where the QKVG epilogue appends the token's key / value)
+      * `kv_limit[i]` = slab start + base_len + local limit               (the cached prefix - rows from the slab start - is always visible:
+                                                                           decode-time attention is un-masked over the cache, T.py:938-939)
+      * attention tiles: keys from the slab start up to the tile's largest limit
+      * RoPE position  = local position (span-shared, T.py:398-415) + rope_base[b]   (`tokens_seen`, T.py:3211-3219)."""
+    rb = pack_batch(samples, times, model, return_loss = False, return_embed = True)
+    B, M = rb.B, rb.M
+    slab, base_len, rope_base = (np.asarray(a, dtype = np.int64) for a in (slab, base_len, rope_base))
+    assert slab.shape == base_len.shape == rope_base.shape == (B,)
+    assert ((base_len + rb.seq_lens) <= cap).all(), 'kv cache slab overflow: a sample needs more rows than the slab capacity'
+    off = slab * cap + base_len - rb.cu[:-1]                   # packed token index -> cache row
+    seq = np.repeat(np.arange(B), rb.seq_lens)
+    rb.kv_row = (np.arange(M, dtype = np.int64) + off[seq]).astype(np.int32)
+    rb.kv_limit = (rb.kv_limit.astype(np.int64) + off[seq]).astype(np.int32)
+    rb.rope_pos = (rb.rope_pos.astype(np.int64) + rope_base[seq]).astype(np.int32)
+    rb.max_rope_pos = int(rb.rope_pos.max()) if M else 0
+    for pre in ('tile', 't2'):
+        q0 = getattr(rb, f'{pre}_q0')
+        if q0.shape[0] == 0:
+            continue
+        ts = np.searchsorted(rb.cu, q0, side = 'right') - 1      # sequence of every query tile
+        setattr(rb, f'{pre}_kv0', (slab[ts] * cap).astype(np.int32))
+        setattr(rb, f'{pre}_kvend', (getattr(rb, f'{pre}_kvend').astype(np.int64) + off[ts]).astype(np.int32))
+    rb.single_row_tiles = bool(M > 0 and (rb.seq_lens <= 1).all())
     return rb
 
 

@@ -5,14 +5,16 @@ phase (one token per step, all text-phase samples share one forward) and a modal
 midpoint ODE - torchdiffeq semantics, transfusion.py:1314-1318 - for all modality-phase samples, classifier-free
 guidance `uncond + s (cond - uncond)`, transfusion.py:2521).
 
-B200 design difference: there is no padded kv cache that is re-padded and concatenated on every step
-(transfusion.py:2257-2277, 2323-2327, 2531-2533).  The sequences here are short (<= a few thousand tokens per
-sample) and the ragged engine runs the whole packed batch in one pass, so every step recomputes the packed prefix.
-To stay numerically IDENTICAL to the reference's cached path the recomputation reproduces what the cache held:
+B200 design: the kv cache is a set of in-place slabs (`engine.KVCache`) instead of per-sample tensors that are re-padded and
+concatenated on every step (transfusion.py:2257-2277, 2323-2327, 2531-2533); the text loop and the ODE loop run as captured CUDA
+graphs over device-resident sampler state (`decode.py`, csrc/decode.cu); the conditional and unconditional branch of an ODE
+evaluation share one ragged forward.  What the cache HOLDS is exactly what the reference's holds:
   * a prompt modality contributes keys/values of its latents at t = 1 (prefill, transfusion.py:2187-2201);
-  * a modality decoded in this call contributes the keys/values of the LAST ODE evaluation - the midpoint state
-    y_mid at time t_{N-2} + h/2 - because that is the cache the reference commits (transfusion.py:2466-2533);
-  * the unconditional branch is rebuilt from the final samples at t = 1 (transfusion.py:2389-2406).
+  * a modality decoded in this call leaves the keys/values of the LAST ODE evaluation - the midpoint state at t_{N-2} + h/2 -
+    because that is the cache the reference commits (transfusion.py:2466-2533);
+  * a sampled [som] token never gets a cache row: the modality takes its RoPE position (transfusion.py:2337-2349, 2408-2411);
+  * the unconditional branch is rebuilt per modality round from the null-id history with earlier modalities at t = 1
+    (transfusion.py:2385-2406).
 """
 from __future__ import annotations
 
@@ -22,15 +24,23 @@ from dataclasses import dataclass, field
 import torch
 from torch import tensor, cat, is_tensor
 
-from .modality_processing import pack_batch, is_int_tensor
+import numpy as np
+
+from .modality_processing import pack_batch, pack_incremental, is_int_tensor
 
 
-@dataclass
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass(eq = False)
 class _State:
     sample: list                                 # parts assembled so far: text tensors and (type, latents) tuples
-    kv_src: list                                 # same structure; modalities carry (type, latents_for_kv, time)
-    curr_seq: torch.Tensor
+    curr_seq: torch.Tensor                       # the running text part (tokens since the last modality)
     phase: str = 'text'
+    last_token: int = 0                          # fed to the next text step (it gets its cache row then, T.py:2246-2248)
+    cache_len: int = 0                           # rows of this sample's cache slab that are committed
+    tokens_seen: int = 0                         # RoPE position of the next token (a whole modality counts as one, T.py:2332, 2548)
     num_past_modalities: int = 0
     curr_modality_id: int | None = None
     modality_shape: tuple | None = None
@@ -115,47 +125,28 @@ class SamplingMixin:
                 parts.append(forced)
         return parts, forced_id, forced_shape
 
-    # ------------------------------------------------------------------ engine passes
-    def _decode_forward(self, seqs, want_logits):
-        """seqs: list of part lists whose modalities are (type, latents [L, dl] or shaped, time).  One ragged forward."""
-        samples, times = [], []
-        for parts in seqs:
-            s, ts = [], []
-            for p in parts:
-                if is_tensor(p):
-                    s.append(p)
-                else:
-                    s.append((p[0], p[1])); ts.append(float(p[2]))
-            samples.append(s); times.append(ts)
-        m = max((len(t) for t in times), default = 0)
-        tm = torch.zeros(len(seqs), max(m, 1))
-        for i, t in enumerate(times):
-            if t:
-                tm[i, :len(t)] = tensor(t)
-        rb = pack_batch(samples, tm if m > 0 else None, self, return_loss = False, return_embed = True)
-        lat = self._latents_to_device(rb)
-        res = self.engine.forward(rb, lat, None, train = False, want_logits = True)
-        return rb, res
+    def _modality_len(self, part):
+        cf = self.channel_first_latent[part[0]]
+        return math.prod(part[1].shape[1:] if cf else part[1].shape[:-1])
 
-    def _last_instance_rows(self, rb):
-        """compact row range of the LAST modality instance of every sample"""
-        last = {}
-        for inst in rb.instances:
-            last[inst.batch_index] = inst
-        out = []
-        for b in range(rb.B):
-            inst = last[b]
-            r0 = rb.type_rows[inst.modality_type][0] + inst.row0
-            out.append((inst.modality_type, r0, r0 + inst.length))
-        return out
+    def _parts_len(self, parts):
+        return sum(p.numel() if is_tensor(p) else self._modality_len(p) for p in parts)
 
     # ------------------------------------------------------------------ sample_many (transfusion.py:2079-2583)
     @torch.no_grad()
     def sample_many(self, prompts = None, max_length = 2048, text_temperature = 1.0, text_min_p = 0.1, fixed_modality_shape = None,
-                    force_modality_at_start = None, init_modality_noise = None, modality_steps = 16, return_unprocessed_modalities = False, cfg_scale = 3.):
-        from .transfusion import sample_text_token
+                    force_modality_at_start = None, init_modality_noise = None, modality_steps = 16, return_unprocessed_modalities = False, cfg_scale = 3.,
+                    seed = None, use_cuda_graph = True):
+        """Batched sampling with a real kv cache.  Follows the reference's `sample_many` state machine step for step - prefill of all prompts in
+        one ragged forward, a shared text loop, a joint midpoint ODE per modality round with classifier-free guidance - but the cache is a set
+        of in-place slabs, the text loop and the ODE loop are captured CUDA graphs over device-resident state, and conditional + unconditional
+        branches of an ODE evaluation share one forward.  `seed` (extension) seeds the on-device token sampler (default: drawn from torch's
+        global generator); `use_cuda_graph = False` launches the same kernels eagerly."""
+        from .decode import ST_LEN, ST_SEEN, ST_LAST, ST_PHASE, ST_NTOK, PH_TEXT, PH_MODALITY, PH_DONE
         was_training = self.training
         self.eval()
+        eng = self.engine
+        frozen_before = getattr(eng, 'frozen', False)
         try:
             if prompts is None:
                 prompts = [None]
@@ -164,11 +155,16 @@ class SamplingMixin:
             states, forced_id, forced_shape = [], None, None
             for prompt in prompts:
                 parts, forced_id, forced_shape = self.prepare_prompt_sample(prompt, force_modality_at_start)
-                kv = [p if is_tensor(p) else (p[0], p[1], 1.0) for p in parts]          # prompt modalities are conditioned at t = 1
                 last = parts[-1]
-                st = _State(sample = parts, kv_src = kv, curr_seq = last if is_tensor(last) else tensor([self.sos_id]))
+                st = _State(sample = parts, curr_seq = last if is_tensor(last) else tensor([self.sos_id]))
+                st.last_token = int(last[-1]) if is_tensor(last) else 0
                 st.num_past_modalities = sum(not is_tensor(p) for p in parts)
+                # tokens in the cache after the prefill and the RoPE position of the next token: every modality collapses to ONE position
+                seq_len = self._parts_len(parts)
+                st.cache_len, st.tokens_seen = seq_len, seq_len - sum(self._modality_len(p) - 1 for p in parts if not is_tensor(p))
                 states.append(st)
+            S = len(states)
+            use_cfg = cfg_scale != 1.
 
             def maybe_transition(st):
                 tr = self._transition(st.curr_seq, fixed_modality_shape, forced_id, forced_shape)
@@ -180,92 +176,146 @@ class SamplingMixin:
                 st.phase = 'modality'
                 return True
 
-            for st in states:
-                maybe_transition(st)
+            # ---- slab capacity: prompt + generated tokens + the largest modality that can be decoded (grown on demand if a sampled shape is larger)
+            shapes = [s_ for s_ in self.modality_default_shape if s_ is not None] + [s_ for s_ in (fixed_modality_shape, forced_shape) if s_ is not None]
+            mod_guess = max([math.prod(s_) for s_ in shapes], default = 0)
+            cap = _round_up(max(st.cache_len for st in states) + max_length + mod_guess + 8, 64)
+            cache = eng.new_cache(2 * S if use_cfg else S, cap)
+            eng.pack_weights()
+            eng.frozen = True                                  # parameters cannot change inside a no-grad sampling call
 
-            def step_text(group):
-                rb, res = self._decode_forward([st.kv_src for st in group], True)
-                V = self.to_text_logits.weight.shape[0]
-                last_rows = torch.as_tensor(rb.cu[1:] - 1, device = res['logits'].device)
-                logits = res['logits'][last_rows, :V].float()
-                sampled = sample_text_token(logits, text_temperature, text_min_p).cpu()
-                for st, tok in zip(group, sampled):
-                    st.curr_seq = cat((st.curr_seq, tok))
-                    st.sample[-1] = st.curr_seq
-                    st.kv_src[-1] = st.curr_seq
-                    st.num_tokens += 1
-                    if int(tok) == self.eos_id:
-                        st.phase = 'done'; continue
-                    if st.num_tokens > max_length:
-                        st.phase = 'done'; continue
-                    maybe_transition(st)
+            def ensure_cap(need):
+                nonlocal cache, cap, dec
+                if need <= cap:
+                    return
+                new_cap = _round_up(need + 64, 64)
+                bigger = eng.new_cache(cache.n_slabs, new_cap)
+                for name in ('k', 'v'):
+                    src, dst = getattr(cache, name), getattr(bigger, name)
+                    dst.view(dst.shape[0], cache.n_slabs, new_cap, -1)[:, :, :cap].copy_(src.view(src.shape[0], cache.n_slabs, cap, -1))
+                cache, cap = bigger, new_cap
+                dec = None                                     # the decoder (and its captured graph) is bound to the old slabs
+
+            # ---- prefill: ONE ragged forward over all prompts builds every sample's cache and the logits of its first token (T.py:2176-2201)
+            m = max((st.num_past_modalities for st in states), default = 0)
+            times = torch.ones(S, m) if m > 0 else None        # prompted modalities are conditioned at t = 1 (T.py:2187-2192)
+            rb = pack_incremental([st.sample for st in states], times, self, slab = np.arange(S), base_len = np.zeros(S), rope_base = np.zeros(S), cap = cap)
+            res = eng.forward(rb, self._latents_to_device(rb), None, train = False, want_logits = True, cache = cache)
+            for st in states:
+                maybe_transition(st)                           # a prompt ending in [som] starts with the modality phase
+
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+            dec = None
+            def decoder():
+                nonlocal dec
+                if dec is None:
+                    dec = eng.text_decoder(cache, S, slab0 = 0, hist_cap = max_length + 4, eos_id = self.eos_id, som_ids = self.som_ids, max_length = max_length,
+                                           temperature = text_temperature, min_p = text_min_p, vlimit = 0, seed = seed, use_graph = use_cuda_graph)
+                return dec
+
+            def push_state():
+                ph = dict(text = PH_TEXT, modality = PH_MODALITY, done = PH_DONE)
+                decoder().set_state([st.cache_len for st in states], [st.tokens_seen for st in states], [st.last_token for st in states],
+                                    [ph[st.phase] for st in states], [st.num_tokens for st in states])
+
+            def pull_state():
+                """device sampler state -> host `_State`s (tokens sampled since the last push are appended to the running text)"""
+                arr, hist = decoder().get_state()
+                for i, st in enumerate(states):
+                    if st.phase != 'text':
+                        continue
+                    new = torch.from_numpy(hist[i])
+                    if new.numel():
+                        st.curr_seq = cat((st.curr_seq, new))
+                        st.sample[-1] = st.curr_seq
+                        st.last_token = int(new[-1])
+                    st.cache_len, st.tokens_seen, st.num_tokens = int(arr[ST_LEN, i]), int(arr[ST_SEEN, i]), int(arr[ST_NTOK, i])
+                    p = int(arr[ST_PHASE, i])
+                    if p == PH_DONE:
+                        st.phase = 'done'
+                    elif p == PH_MODALITY:
+                        assert maybe_transition(st)
+
+            # first token of every text-phase sample, from the prefill logits at its last prompt position (T.py:2225-2250)
+            push_state()
+            decoder().sample_first(res['logits'], rb.cu[1:] - 1)
+            pull_state()
+
+            def text_loop():
+                """all samples in the text phase advance in lock-step until each has hit [eos], the length limit or a [som] (T.py:2563-2568)"""
+                push_state()
+                budget = max(1, max_length + 2 - min(st.num_tokens for st in states if st.phase == 'text'))
+                decoder().run(budget)
+                pull_state()
 
             def step_modality(group):
                 dev = self.device
-                use_cfg = cfg_scale != 1.
+                G = len(group)
+                ensure_cap(max(st.cache_len + st.modality_length for st in group) + 1)
+                # initial noise per sample, gathered per modality type in scan order (the engine's compact row order)
                 ys = []
                 for st in group:
                     L, dl = st.modality_length, st.dim_latent
                     noise = init_modality_noise[:L, :dl] if init_modality_noise is not None else torch.randn(L, dl)
                     assert noise.shape == (L, dl)
-                    ys.append(noise.float().to(dev))
-                uncond_hist = [[torch.full_like(p, self.null_text_id) if is_tensor(p) else (p[0], p[1], 1.0) for p in st.sample] for st in group]
-                last_eval = {}
-
-                def flows(t, ys_now, record):
-                    tval = float(t)
-                    cond_seqs = [[*st.kv_src, (st.curr_modality_id, y, tval)] for st, y in zip(group, ys_now)]
-                    rb, res = self._decode_forward(cond_seqs, True)
-                    rows = self._last_instance_rows(rb)
-                    cond = [res['preds'][ty][r0 - rb.type_rows[ty][0]: r1 - rb.type_rows[ty][0]].clone() for ty, r0, r1 in rows]
-                    if record:
-                        last_eval['y'], last_eval['t'] = [y.clone() for y in ys_now], tval
-                    if not use_cfg:
-                        return cond
-                    unc_seqs = [[*h, (st.curr_modality_id, y, tval)] for st, h, y in zip(group, uncond_hist, ys_now)]
-                    rb2, res2 = self._decode_forward(unc_seqs, True)
-                    rows2 = self._last_instance_rows(rb2)
-                    unc = [res2['preds'][ty][r0 - rb2.type_rows[ty][0]: r1 - rb2.type_rows[ty][0]] for ty, r0, r1 in rows2]
-                    return [u + cfg_scale * (c - u) for c, u in zip(cond, unc)]
-
-                grid = torch.linspace(0, 1, modality_steps).tolist()
-                for k in range(len(grid) - 1):                     # fixed-grid explicit midpoint (torchdiffeq 'midpoint')
-                    t0, h = grid[k], grid[k + 1] - grid[k]
-                    f0 = flows(t0, ys, False)
-                    y_mid = [y + f * (0.5 * h) for y, f in zip(ys, f0)]
-                    f1 = flows(t0 + 0.5 * h, y_mid, True)
-                    ys = [y + f * h for y, f in zip(ys, f1)]
-                for st, y, ymid in zip(group, ys, last_eval.get('y', ys)):
-                    cf = self.channel_first_latent[st.curr_modality_id]
-                    shaped = y.reshape(*st.modality_shape, st.dim_latent)
-                    if cf:
+                    ys.append(noise.float())
+                slabs = [states.index(st) for st in group]
+                base, ropes = [st.cache_len for st in group], [st.tokens_seen for st in group]
+                placeholder = lambda st: torch.empty(st.dim_latent, st.modality_length) if self.channel_first_latent[st.curr_modality_id] else torch.empty(st.modality_length, st.dim_latent)
+                samples = [[(st.curr_modality_id, placeholder(st))] for st in group]      # shapes only: the latents live on the device (ODE state)
+                if use_cfg:
+                    # unconditional branch: every text token replaced by the null id, earlier modalities at t = 1 - rebuilt per modality round
+                    # into the second half of the slabs by one ragged prefill over the whole group (T.py:2385-2406)
+                    hist = [[torch.full_like(p, self.null_text_id) if is_tensor(p) else p for p in st.sample] for st in group]
+                    ulen = [self._parts_len(h) for h in hist]
+                    ensure_cap(max(u + st.modality_length for u, st in zip(ulen, group)) + 1)
+                    mu = max(st.num_past_modalities for st in group)
+                    urb = pack_incremental(hist, torch.ones(G, mu) if mu > 0 else None, self, slab = np.asarray(slabs) + S, base_len = np.zeros(G), rope_base = np.zeros(G), cap = cap)
+                    eng.forward(urb, self._latents_to_device(urb), None, train = False, want_logits = False, want_preds = False, cache = cache)
+                    slabs = slabs + [s_ + S for s_ in slabs]
+                    base, ropes, samples = base + ulen, ropes + ropes, samples + samples
+                dup = 2 if use_cfg else 1
+                orb = pack_incremental(samples, torch.zeros(len(samples), 1), self, slab = np.asarray(slabs), base_len = np.asarray(base), rope_base = np.asarray(ropes), cap = cap)
+                # per type: conditional rows of the group in scan order; the unconditional copies follow (pack order = sample order)
+                y = []
+                for t in range(self.num_modalities):
+                    rows = [ys[i] for i, st in enumerate(group) if st.curr_modality_id == t]
+                    y.append(cat(rows).to(dev).contiguous() if rows else None)
+                y = eng.ode_solve(cache, orb, y, dup = dup, steps = modality_steps, cfg_scale = cfg_scale, use_graph = use_cuda_graph)
+                # commit: the cache rows written by the LAST evaluation stay (T.py:2529-2533), the final state is the sampled modality
+                offs = [0] * self.num_modalities
+                finals = [v.cpu() if v is not None else None for v in y]
+                for st in group:
+                    t, L = st.curr_modality_id, st.modality_length
+                    sampled = finals[t][offs[t]: offs[t] + L]
+                    offs[t] += L
+                    shaped = sampled.reshape(*st.modality_shape, st.dim_latent)
+                    if self.channel_first_latent[t]:
                         shaped = shaped.movedim(-1, 0)
-                    st.sample.append((st.curr_modality_id, shaped))
-                    kv_lat = ymid.reshape(*st.modality_shape, st.dim_latent)
-                    st.kv_src.append((st.curr_modality_id, kv_lat.movedim(-1, 0) if cf else kv_lat, last_eval.get('t', 1.0)))
-                    st.curr_seq = tensor([self.eom_ids[st.curr_modality_id]])
-                    st.sample.append(st.curr_seq); st.kv_src.append(st.curr_seq)
-                    st.num_tokens += st.modality_length
+                    st.sample.append((t, shaped))
+                    st.curr_seq = tensor([self.eom_ids[t]])
+                    st.sample.append(st.curr_seq)
+                    st.last_token = self.eom_ids[t]
+                    st.cache_len += L
+                    st.tokens_seen += 1
+                    st.num_tokens += L
                     st.num_past_modalities += 1
-                    st.phase = 'text'
-                    if st.num_tokens > max_length:
-                        st.phase = 'done'
+                    st.phase = 'done' if st.num_tokens > max_length else 'text'
 
             while not all(st.phase == 'done' for st in states):
-                text_group = [st for st in states if st.phase == 'text']
-                while text_group:
-                    step_text(text_group)
-                    text_group = [st for st in text_group if st.phase == 'text']
-                mod_group = [st for st in states if st.phase == 'modality']
-                while mod_group:
-                    step_modality(mod_group)
-                    mod_group = [st for st in mod_group if st.phase == 'modality']
+                if any(st.phase == 'text' for st in states):
+                    text_loop()
+                group = [st for st in states if st.phase == 'modality']
+                if group:
+                    step_modality(group)
 
             samples = [st.sample for st in states]
             if return_unprocessed_modalities:
                 return samples
             return self.decode_modalities(samples)
         finally:
+            eng.frozen = frozen_before
             self.train(was_training)
 
     def decode_modalities(self, samples):

@@ -23,6 +23,15 @@ from transfusion_pytorch_b200 import synth                   # noqa: E402
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 
+def compact(o):
+    """clone every tensor of a fixture: torch.save writes the WHOLE storage of a view"""
+    if torch.is_tensor(o): return o.detach().clone().contiguous()
+    if isinstance(o, dict): return {k: compact(v) for k, v in o.items()}
+    if isinstance(o, list): return [compact(v) for v in o]
+    if isinstance(o, tuple): return tuple(compact(v) for v in o)
+    return o
+
+
 def grad_fingerprint(model):
     """Per-parameter gradient fingerprint: [sum, abs-sum, projection on a fixed pseudo-random vector, l2] + first 8 values."""
     out = {}
@@ -79,7 +88,7 @@ def run_interleaved(ref, name, ctor, batch, times, seed, subsample_rows = None, 
         fx['embed'] = embed.clone()
         if keep_hiddens:
             fx['hiddens'] = [h.detach().clone() for h in hiddens[:-1]]
-    torch.save(fx, os.path.join(GOLDEN, f'{name}.pt'))
+    torch.save(compact(fx), os.path.join(GOLDEN, f'{name}.pt'))
     print(f'{name}: loss {loss.item():.6f} text {breakdown.text.item():.6f} flow {[round(f.item(), 6) for f in breakdown.flow]} '
           f'positions[0] {proc.modality_positions[0]} total_tokens {proc.total_tokens}')
 
@@ -94,9 +103,16 @@ def run_text_only(ref, name, ctor, text, seed, prompt_len = 16, gen_len = 40):
     gen = model.generate_text_only(text[:, :prompt_len], gen_len, temperature = 0.)
     with torch.no_grad():
         logits = model.forward_text(text[:, :-1], return_loss = False)
+        # top-2 logit margin of the reference at every generated position (teacher-forced on its own greedy continuation: a causal LM, so these
+        # are the logits generation saw): lets the GPU test tell a bf16 near-tie from a real mismatch
+        seq = torch.cat((text[:, :prompt_len], gen), dim = -1)
+        lg = model.forward_text(seq[:, :-1], return_loss = False)[:, prompt_len - 1:]
+        assert torch.equal(lg.argmax(dim = -1), gen)
+        top2 = lg.topk(2, dim = -1).values
+        margins = (top2[..., 0] - top2[..., 1]).clone()
     fx = dict(name = name, ctor = ctor, seed = seed, loss = loss.detach().double(), grads = grad_fingerprint(model), generated = gen.clone(),
-              prompt_len = prompt_len, gen_len = gen_len, logits_last = logits[:, -1].detach().clone())
-    torch.save(fx, os.path.join(GOLDEN, f'{name}.pt'))
+              prompt_len = prompt_len, gen_len = gen_len, logits_last = logits[:, -1].detach().clone(), margins = margins)
+    torch.save(compact(fx), os.path.join(GOLDEN, f'{name}.pt'))
     print(f'{name}: loss {loss.item():.6f} generated[0,:8] {gen[0, :8].tolist()}')
 
 
@@ -120,7 +136,7 @@ def run_sampling(ref, name, ctor, seed):
     import copy
     out = model.sample_many(copy.deepcopy(prompts), **kw)
     fx = dict(name = name, ctor = ctor, seed = seed, prompts = prompts, noise = noise, kw = {k: v for k, v in kw.items() if k != 'init_modality_noise'}, samples = out)
-    torch.save(fx, os.path.join(GOLDEN, f'{name}.pt'))
+    torch.save(compact(fx), os.path.join(GOLDEN, f'{name}.pt'))
     for s in out:
         print('  sample:', [tuple(p.shape) if torch.is_tensor(p) else ('mod', p[0], tuple(p[1].shape)) for p in s])
 
@@ -223,7 +239,7 @@ def run_sampling_sized(ref, name, ctor, seed, n_each, mod_len, steps, max_length
     assert all(len(margins[i]) == sum(len(r) for r in runs[i]) for i in range(B)), 'schedule replay did not consume every sampled token'
     fx = dict(name = name, ctor = ctor, seed = seed, prompts = prompts, noise = noise, kw = {k: v for k, v in kw.items() if k != 'init_modality_noise'}, samples = out,
               generated = [[t for r in runs[i] for t in r] for i in range(B)], margins = margins)
-    torch.save(fx, os.path.join(GOLDEN, f'{name}.pt'))
+    torch.save(compact(fx), os.path.join(GOLDEN, f'{name}.pt'))
     for i, s in enumerate(out):
         print(f'  sample {i}:', [tuple(p.shape) if torch.is_tensor(p) else ('mod', p[0], tuple(p[1].shape)) for p in s], 'min margin %.4f' % min(margins[i], default = float('nan')))
 
@@ -247,6 +263,9 @@ def main():
         times = torch.rand(2, count_modalities(batch), generator = torch.Generator().manual_seed(5))
         rows = torch.arange(0, 1024, 41)
         run_interleaved(ref, 'config4_d8', ctor, batch, times, seed = 13, subsample_rows = rows)
+    if only in ('', 'config1'):
+        ctor = dict(num_text_tokens = 256, transformer = dict(dim = 128, depth = 2))
+        run_text_only(ref, 'config1_text_only', ctor, synth.text_batch(4, 257, seed = 3), seed = 3)
     if only:
         return
 

@@ -20,6 +20,8 @@ def golden_inputs(name):
         return synth.config4_batch(2, seed = 2, total_len = 300, dims = (32, 16), text_vocab = 64)
     if name == 'config2_b2':
         return synth.config2_batch(2, seed = 4)
+    if name == 'config4_d8':
+        return synth.config4_batch(2, seed = 31)
     raise KeyError(name)
 
 
@@ -57,3 +59,63 @@ def unpack_rows(packed, rb, width = None):
     for b in range(rb.B):
         out[b, :rb.seq_lens[b]] = packed[rb.cu[b]:rb.cu[b + 1], :d]
     return out
+
+
+def flatten_sample(model, sample):
+    """[('t', id) ...] / [('m', (type, latents))] items of one sample (list of text tensors and (type, latents) tuples)"""
+    items = []
+    for p in sample:
+        if torch.is_tensor(p):
+            items += [('t', int(v)) for v in p.reshape(-1).tolist()]
+        else:
+            items.append(('m', (p[0], p[1].detach().float().cpu())))
+    return items
+
+
+def compare_sampling(model, out, fx, bound, lat_tol):
+    """Compare `sample_many` output with a reference fixture that carries the reference's top-2 logit margins per sampled token.
+
+    Text must be IDENTICAL up to the first sampled token whose reference margin is below `bound` (the stated bf16 logit-noise bound): a
+    mismatch at a larger margin fails; at a smaller one the sample has legitimately diverged (greedy decoding of two near-tied logits) and
+    the comparison of that sample stops there.  Every modality decoded before that point must match within `lat_tol` of its max magnitude.
+    Returns a per-sample report: dict(matched = sampled tokens that agree, total = sampled tokens in the fixture, diverged_at = index or None,
+    margin = reference margin at the divergence, latent_err = [relative errors of the compared modalities])."""
+    import copy
+    report = []
+    forced = fx['kw'].get('force_modality_at_start')
+    for i, (ours, ref) in enumerate(zip(out, fx['samples'])):
+        prep = model.prepare_prompt_sample(copy.deepcopy(fx['prompts'][i]), forced)[0]
+        n_prompt = len(flatten_sample(model, prep))
+        a, b = flatten_sample(model, ours), flatten_sample(model, ref)
+        margins = fx['margins'][i]
+        g, rep = 0, dict(matched = 0, total = len(margins), diverged_at = None, margin = None, latent_err = [])
+        prev_mod = False
+        for j, (x, y) in enumerate(zip(a, b)):
+            sampled = j >= n_prompt and y[0] == 't' and not prev_mod            # the [eom] right after a decoded modality is appended, not sampled
+            if x[0] != y[0]:
+                assert sampled or (j >= n_prompt and x[0] == 't' and y[0] == 'm'), f'sample {i}: structure differs at item {j} inside the prompt'
+            if y[0] == 'm' and x[0] == 'm':
+                assert x[1][0] == y[1][0] and x[1][1].shape == y[1][1].shape, f'sample {i}: modality type / shape differs at item {j}'
+                if j >= n_prompt:
+                    err = ((x[1][1] - y[1][1]).abs().max() / y[1][1].abs().max().clamp(min = 1e-9)).item()
+                    rep['latent_err'].append(err)
+                    assert err < lat_tol, f'sample {i}: decoded modality at item {j} differs by {err:.3e} of its max magnitude'
+                else:
+                    assert torch.equal(x[1][1], y[1][1])
+                prev_mod = True
+                continue
+            if x == y:
+                if sampled:
+                    g += 1; rep['matched'] += 1
+                prev_mod = False
+                continue
+            # first difference
+            assert j >= n_prompt, f'sample {i}: prompt token {j} differs'
+            assert sampled, f'sample {i}: non-sampled token at item {j} differs: {x} vs {y}'
+            assert margins[g] < bound, f'sample {i}: sampled token {g} differs ({x} vs {y}) although the reference margin {margins[g]:.4f} >= {bound}'
+            rep['diverged_at'], rep['margin'] = g, margins[g]
+            break
+        else:
+            assert len(a) == len(b), f'sample {i}: lengths differ without a token mismatch'
+        report.append(rep)
+    return report

@@ -119,7 +119,40 @@ def test_validation_errors_match_reference_conventions():
     with pytest.raises(AssertionError):
         pack_batch([[(0, torch.randn(4, 31))]], torch.rand(1, 1), m, return_loss = False, return_embed = True)      # wrong latent dim
     with pytest.raises(NotImplementedError):
-        Transfusion(num_text_tokens = 8, transformer = dict(dim = 128, depth = 1, attn_laser = True))
+        Transfusion(num_text_tokens = 8, transformer = dict(dim = 128, depth = 1, dim_head = 32))
+
+
+def test_state_dict_interchange_with_the_reference():
+    """weight interchange contract: identical state_dict keys, shapes and dtypes as the reference for configs 1, 2 and 4, checked
+    against the reference itself when it is importable (build container) and against the committed key / shape listing otherwise (GPU box); a reference
+    state_dict loads into this model and vice versa."""
+    import json
+    listing_path = os.path.join(ROOT, 'tests', 'golden', 'state_dict_keys.json')
+    ctors = dict(
+        config1 = dict(num_text_tokens = 256, transformer = dict(dim = 128, depth = 2)),
+        config2 = dict(num_text_tokens = 256, dim_latent = 384, modality_default_shape = (256,), transformer = dict(dim = 512, depth = 8)),
+        config4 = dict(num_text_tokens = 256, dim_latent = (384, 192), modality_default_shape = ((4,), (2,)), transformer = dict(dim = 512, depth = 8)))
+    from oracle.reference_loader import reference_available, load_reference
+    listing = json.load(open(listing_path)) if os.path.isfile(listing_path) else {}
+    ref = load_reference() if reference_available() else None
+    assert ref is not None or listing, 'neither the reference nor the committed listing is available'
+    for name, ctor in ctors.items():
+        ours = Transfusion(**ctor)
+        sd = ours.state_dict()
+        mine = {k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}
+        if ref is not None:
+            theirs_model = ref.Transfusion(**ctor)
+            theirs = theirs_model.state_dict()
+            want = {k: [list(v.shape), str(v.dtype)] for k, v in theirs.items()}
+            assert mine == want, (sorted(set(mine) ^ set(want))[:6], name)
+            ours.load_state_dict(theirs)                                      # reference checkpoint -> this model
+            theirs_model.load_state_dict(sd)                                  # and back
+            listing[name] = want
+        else:
+            assert mine == listing[name], name
+    if ref is not None:
+        json.dump(listing, open(listing_path, 'w'), indent = 0, sort_keys = True)
+    assert len(listing['config2']) == 206 and sum(int(np.prod(v[0])) for k, v in listing['config2'].items() if 'weights' not in k) >= 79_545_712
 
 
 def test_cabi_library_exports_every_declared_symbol():
@@ -132,7 +165,7 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f'{name} declared in include/tfx_b200.h but not exported'
     assert set(_lib.EXPORTED) == declared
     lib.tfx_version.restype = ctypes.c_int
-    assert lib.tfx_version() == 100
+    assert lib.tfx_version() == 200
 
 
 def test_product_fails_loudly_without_cuda():
@@ -196,6 +229,7 @@ def test_ctypes_signatures_match_the_header_prototypes():
     def cls(arg):
         a = ' '.join(arg.split())
         if '*' in a: return C.c_void_p
+        if a.startswith('unsigned long long'): return C.c_ulonglong
         if a.startswith('long long'): return C.c_longlong
         if a.startswith('float'): return C.c_float
         if a.startswith('int'): return C.c_int

@@ -79,3 +79,18 @@ def test_oracle_matches_reference_config2():
     assert abs(loss.item() - fx['loss'].item()) / fx['loss'].item() < REL
     emb = model._engine.state['embed']
     assert torch.allclose(emb[:, fx['embed_rows']], fx['embed'], atol = 2e-4, rtol = 1e-4)
+
+
+def test_oracle_matches_reference_config4_depth8():
+    """BASELINE.json configs[3] at the graded width / depth: two modality types, many short spans (fixture from the reference itself)"""
+    fx = load_golden('config4_d8')
+    model = build(fx)
+    batch = golden_inputs('config4_d8')
+    loss, bd = model(batch, times = fx['times'], return_breakdown = True, noise = golden_noise(fx, batch, model.dim_latents))
+    rb = model._last_batch
+    assert rb.modality_positions == fx['modality_positions'] and all(len(p) >= 8 for p in rb.modality_positions)
+    assert rb.total_tokens == fx['total_tokens'] == 2050
+    assert abs(loss.item() - fx['loss'].item()) / fx['loss'].item() < REL
+    assert len(bd.flow) == 2 and all(abs(a.item() - b.item()) / b.item() < REL for a, b in zip(bd.flow, fx['flow_losses']))
+    emb = model._engine.state['embed']
+    assert torch.allclose(emb[:, fx['embed_rows']], fx['embed'], atol = 2e-4, rtol = 1e-4)

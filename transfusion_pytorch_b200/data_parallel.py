@@ -86,10 +86,10 @@ class DataParallelTrainer:
     # ---- CUDA-graph replay of fixed-shape steps
     @staticmethod
     def _signature(rb, eng):
-        return (rb.M, rb.B, rb.n_cond, rb.S, tuple(rb.type_rows), tuple(getattr(rb, n).shape[0] for n in eng.META_NAMES), rb.total_tokens,
+        return (rb.M, rb.B, rb.n_cond, rb.S, tuple(rb.type_rows), tuple(getattr(rb, n).shape[0] if getattr(rb, n) is not None else 0 for n in eng.META_NAMES), rb.total_tokens,
                 tuple(rb.n_type_tokens), (rb.max_rope_pos + 1 + 1023) // 1024, rb.has_labels)
 
-    def _graph_step(self, rb, device_lat = None):
+    def _graph_step(self, rb, device_lat = None, noise = None):
         """Returns the loss of a replayed (or freshly captured) step, or None when this batch must run eagerly.
         device_lat: per-type latent matrices already on the device (then rb must be uploaded too: a device-resident batch)."""
         model, eng = self.model, self.model.engine
@@ -115,6 +115,7 @@ class DataParallelTrainer:
             g.layout = layout
             g.lat = [torch.empty(s1 - s0, model.dim_latents[t], device = eng.device, dtype = torch.float32) if s1 > s0 else None for t, (s0, s1) in enumerate(rb.type_rows)]
             g.lat_stage = [torch.empty_like(l) if l is not None else None for l in g.lat]
+            g.eps = [torch.empty_like(l) if l is not None else None for l in g.lat]      # flow noise: a static input of the graph, drawn (or injected) per step
             g.consumed = torch.cuda.Event()
             g.consumed.record()
         assert layout == g.layout
@@ -142,6 +143,12 @@ class DataParallelTrainer:
                 if dst is not None:
                     dst.copy_(src, non_blocking = True)
             g.consumed.record()
+        for t, e in enumerate(g.eps):
+            if e is not None:
+                if noise is not None and noise[t] is not None:
+                    e.copy_(noise[t].reshape(e.shape), non_blocking = True)      # injected (deterministic parity runs)
+                else:
+                    e.normal_()
         if getattr(eng, 'opt_step_dev', None) is None:
             eng.opt_step_dev = torch.zeros(1, device = eng.device, dtype = torch.int32)
         eng.opt_step_dev.fill_(eng.opt_step)             # device-resident optimizer step counter (incremented inside the graph)
@@ -159,8 +166,7 @@ class DataParallelTrainer:
             graph = torch.cuda.CUDAGraph()
             l0 = eng.ops.launches
             with torch.cuda.graph(graph):
-                eps = [torch.randn_like(l) if l is not None else None for l in g.lat]
-                res = eng.forward(rb, g.lat, eps, train = True, text_loss_weight = model.text_loss_weight, flow_loss_weight = model.flow_loss_weight)
+                res = eng.forward(rb, g.lat, g.eps, train = True, text_loss_weight = model.text_loss_weight, flow_loss_weight = model.flow_loss_weight)
                 eng.backward()
                 if self.world > 1:
                     dist.all_reduce(eng.gflat)            # NCCL all-reduce of the flat gradient buffer, captured as a graph node
@@ -208,24 +214,25 @@ class DataParallelTrainer:
         if self.ema_decay is not None:
             eng.ema_update(self.ema_decay)
 
-    def step_packed(self, rb, latents):
+    def step_packed(self, rb, latents, noise = None):
         """One training step from a packed batch that is already resident on the device (`model.pack` + `engine.upload` + latents on the
         device): CUDA-graph replay when the shape signature has been seen before, eager launches otherwise.  Single process only."""
         model, eng = self.model, self.model.engine
         eng.ensure_attached()
         self._sync_replicas(eng)
         eng.upload(rb)
-        loss = self._graph_step(rb, device_lat = latents) if self.cuda_graph else None
+        loss = self._graph_step(rb, device_lat = latents, noise = noise) if self.cuda_graph else None
         if loss is None:
             eng.zero_grad()
-            loss = model.forward_packed(rb, latents)
+            loss = model.forward_packed(rb, latents, noise = noise)
             loss.backward()
             if self.world > 1:
                 dist.all_reduce(eng.gflat)
             self._finish_step(eng)
         return loss
 
-    def step(self, batch, times = None, **fw):
+    def step(self, batch, times = None, noise = None, **fw):
+        """`noise` (optional, per modality type `[S_t, dim_latent]`): injected flow noise for deterministic parity runs"""
         model = self.model
         eng = model.engine
         cuda = hasattr(eng, 'gflat') or model.device.type == 'cuda'
@@ -234,18 +241,19 @@ class DataParallelTrainer:
             self._sync_replicas(eng)
             if self.cuda_graph and model.training and not fw and torch.is_grad_enabled():
                 rb, _ = model.pack(batch, times = times)
-                loss = self._graph_step(rb)
+                dnoise = [n.reshape(-1, model.dim_latents[t]).float().to(model.device) if n is not None else None for t, n in enumerate(noise)] if noise is not None else None
+                loss = self._graph_step(rb, noise = dnoise)
                 if loss is not None:
                     return loss
                 eng.zero_grad()
-                loss = model.forward_packed(rb, model._latents_to_device(rb))
+                loss = model.forward_packed(rb, model._latents_to_device(rb), noise = dnoise)
             else:
                 eng.zero_grad()
-                loss = model(batch, times = times, **fw)
+                loss = model(batch, times = times, noise = noise, **fw)
         else:
             for p in model.parameters():
                 p.grad = None
-            loss = model(batch, times = times, **fw)
+            loss = model(batch, times = times, noise = noise, **fw)
         # With graph replay enabled every step - captured or eager - issues exactly ONE all-reduce of the whole gradient buffer, so ranks whose
         # batches have different shape signatures (one replaying, one still eager) stay in lock-step on the communicator.
         if cuda and self.overlap and not self.cuda_graph:

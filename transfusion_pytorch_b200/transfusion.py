@@ -24,7 +24,26 @@ from torch.nn import Module, ModuleList
 from .sampling import SamplingMixin
 from ._pinned import POOL
 from .modality_processing import (
-    ModalitySample, RaggedBatch, pack_batch, pack_text_only, get_processing_strategy, DEFAULT_PROCESSING_STRATEGY, is_int_tensor)
+    ModalitySample, RaggedBatch, pack_batch, pack_text_only, pack_incremental, get_processing_strategy, DEFAULT_PROCESSING_STRATEGY, is_int_tensor)
+
+
+class TextKVCache:
+    """Handle returned as the first element of the reference's `(kv_cache, tokens_seen)` tuple (T.py:2613, 2636): B cache slabs that grow in place."""
+
+    def __init__(self, engine, B, cap):
+        self.engine, self.B, self.length = engine, B, 0
+        self.cache = engine.new_cache(B, cap)
+
+    def reserve(self, n_new):
+        need = self.length + n_new
+        if need <= self.cache.cap:
+            return
+        old, cap = self.cache, max(2 * self.cache.cap, need + 64)
+        new = self.engine.new_cache(self.B, cap)
+        for name in ('k', 'v'):
+            src, dst = getattr(old, name), getattr(new, name)
+            dst.view(dst.shape[0], self.B, cap, *dst.shape[2:])[:, :, :old.cap].copy_(src.view(src.shape[0], self.B, old.cap, *src.shape[2:]))
+        self.cache = new
 
 
 class LossBreakdown(NamedTuple):
@@ -442,43 +461,83 @@ class Transfusion(SamplingMixin, Module):
 
     # ------------------------------------------------------------------ text only (transfusion.py:2585-2707)
     def forward_text(self, text: Tensor, return_loss = True, return_embed = False, cache = None, return_hiddens = False, return_kv_cache = False):
-        assert not return_hiddens, 'return_hiddens is not provided by the fused engine'
+        """`cache` / `return_kv_cache` follow the reference's tuple convention `(kv, tokens_seen)` (T.py:2613, 2636); `kv` is a `TextKVCache`
+        handle onto in-place cache slabs instead of a `(layers, 2, b, h, n, d)` tensor that is concatenated per call (T.py:969-977)."""
         raw_cache, tokens_seen = default(cache, (None, 0))
-        if exists(raw_cache):
-            # the engine recomputes from the tokens it is given: the "cache" carries the token prefix (API-compatible tuple)
-            text = cat((raw_cache, text.to(raw_cache.device)), dim = -1)
-        rb = pack_text_only(text, return_loss = return_loss)
         if return_loss:
+            assert not exists(raw_cache) and not return_kv_cache, 'the kv cache is a decode-time structure'
+            rb = pack_text_only(text, return_loss = True)
             res = self._run(rb, None, None, train = True, vlimit = self.num_text_tokens)
+            if return_hiddens:
+                return res['total'], self._hiddens_padded(rb)
             return res['total']
-        res = self.engine.forward(rb, None, None, train = False, want_logits = True)
-        B, n = rb.B, int(rb.seq_lens[0])
-        logits = res['logits'][:, :self.to_text_logits.weight.shape[0]].reshape(B, n, -1)
-        if exists(raw_cache):
-            logits = logits[:, tokens_seen:]
-        out = res['embed'].reshape(B, n, -1) if return_embed else logits
+        use_cache = exists(raw_cache) or return_kv_cache
+        B, n = text.shape
+        V = self.to_text_logits.weight.shape[0]
+        if not use_cache:
+            rb = pack_text_only(text, return_loss = False)
+            res = self.engine.forward(rb, None, None, train = False, want_logits = True)
+            kv = None
+        else:
+            eng = self.engine
+            kv = raw_cache if exists(raw_cache) else TextKVCache(eng, B, max(256, 2 * n))
+            assert kv.B == B, 'cache was built for a different batch size'
+            kv.reserve(n)
+            rb = pack_incremental([[row] for row in text.detach().cpu().long()], None, self, slab = np.arange(B), base_len = np.full(B, kv.length), rope_base = np.full(B, tokens_seen),
+                                  cap = kv.cache.cap)
+            res = eng.forward(rb, None, None, train = False, want_logits = True, cache = kv.cache)
+            kv.length += n
+        out = res['embed'].reshape(B, n, -1) if return_embed else res['logits'][:, :V].reshape(B, n, -1)
+        ret = (out,)
         if return_kv_cache:
-            return out, (text.to(self.device), n)
-        return out
+            ret = (*ret, (kv, tokens_seen + n))
+        if return_hiddens:
+            ret = (*ret, self._hiddens_padded(rb))
+        return ret[0] if len(ret) == 1 else ret
+
+    def _hiddens_padded(self, rb):
+        """hidden states of the last forward in the reference's layout (T.py:1199, 1244, 1252-1254): [tokens, layer 1 .. depth, final norm], each [b, n, d]"""
+        st = self.engine.state
+        n_max = int(rb.seq_lens.max()) if rb.B else 0
+        def unpack(t):
+            out = t.new_zeros((rb.B, n_max, t.shape[-1]))
+            for b in range(rb.B):
+                out[b, :rb.seq_lens[b]] = t[rb.cu[b]:rb.cu[b + 1]]
+            return out
+        return [unpack(h.clone()) for h in (*st['hid'], st['out'])]
 
     @torch.no_grad()
-    def generate_text_only(self, prompt: Tensor, seq_len: int, temperature = 1.0, min_p = 0.1, cache_kv = True) -> Tensor:
+    def generate_text_only(self, prompt: Tensor, seq_len: int, temperature = 1.0, min_p = 0.1, cache_kv = True, seed = None, use_cuda_graph = True) -> Tensor:
+        """T.py:2669-2707.  Always decodes against the kv cache (`cache_kv = False` only re-computes the same values in the reference):
+        one prefill of the prompt, then one captured CUDA graph per token - embed, block stack with in-place cache append and the decode
+        attention kernel, logits, on-device argmax / min-p + Gumbel sampling - with no host synchronisation until the tokens are read back."""
         was = self.training
         self.eval()
+        eng = self.engine
+        frozen_before = getattr(eng, 'frozen', False)
         try:
-            prompt_len, out = prompt.shape[-1], prompt.clone().to(self.device)
-            for _ in range(max(0, seq_len - prompt_len)):
-                logits = self.forward_text(out, return_loss = False)[:, -1].float()
-                if temperature == 0.:
-                    nxt = logits.argmax(dim = -1, keepdim = True)
-                else:
-                    logits = min_p_filter(logits / temperature, min_p = min_p)
-                    logits = logits.masked_fill(~self.text_only_logits_mask, -torch.finfo(logits.dtype).max)
-                    noise = -torch.log(-torch.log(torch.rand_like(logits).clamp(min = 1e-20)).clamp(min = 1e-20))
-                    nxt = (logits + noise).argmax(dim = -1, keepdim = True)
-                out = cat((out, nxt), dim = -1)
-            return out[..., prompt_len:]
+            B, n = prompt.shape
+            steps = max(0, seq_len - n)
+            if steps == 0:
+                return prompt[..., n:].clone()
+            cache = eng.new_cache(B, seq_len + 1)
+            eng.pack_weights()
+            eng.frozen = True
+            rb = pack_incremental([[row] for row in prompt.detach().cpu().long()], None, self, slab = np.arange(B), base_len = np.zeros(B), rope_base = np.zeros(B), cap = cache.cap)
+            res = eng.forward(rb, None, None, train = False, want_logits = True, cache = cache)
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+            # greedy: argmax over ALL logits (T.py:2692-2693); otherwise min-p over all logits, then restricted to text ids (T.py:2695-2698)
+            dec = eng.text_decoder(cache, B, slab0 = 0, hist_cap = steps + 1, eos_id = -1, som_ids = [], max_length = 2 ** 30, temperature = temperature, min_p = min_p,
+                                   vlimit = 0 if temperature == 0. else self.num_text_tokens, seed = seed, use_graph = use_cuda_graph)
+            dec.set_state(np.full(B, n), np.full(B, n), np.zeros(B), np.zeros(B), np.zeros(B))
+            dec.sample_first(res['logits'], rb.cu[1:] - 1)
+            for _ in range(steps - 1):
+                dec.step()
+            _, hist = dec.get_state()
+            return torch.stack([torch.from_numpy(h) for h in hist]).to(prompt.device)
         finally:
+            eng.frozen = frozen_before
             self.train(was)
 
     # ------------------------------------------------------------------ modality only (transfusion.py:2709-2866)
@@ -583,16 +642,17 @@ class Transfusion(SamplingMixin, Module):
         noise = None,            # extension: list (per type) of [S_t, dim_latent] noise for deterministic parity runs
     ):
         assert not exists(velocity_consistency_ema_model), 'velocity consistency is outside the B200 hot path'
-        assert not return_hiddens and not return_only_pred_flows, 'return_hiddens / return_only_pred_flows are not provided by the fused engine'
+        assert not return_only_pred_flows, 'return_only_pred_flows is not provided by the fused engine'
         is_decoding = exists(decoding_text_or_modality)
         if is_int_tensor(modalities):
             return self.forward_text(modalities, return_loss = return_loss and not return_embed, return_embed = return_embed, cache = cache,
-                                     return_kv_cache = return_kv_cache)
+                                     return_kv_cache = return_kv_cache, return_hiddens = return_hiddens)
         if is_tensor(modalities) and modalities.is_floating_point():
             assert return_loss
             return self.forward_modality(modalities, modality_type = modality_type)
         return_loss = return_loss and not (return_embed or is_decoding)
-        assert not exists(cache), 'the B200 path recomputes the (short) prefix instead of taking an external kv cache; use sample()/sample_many()'
+        assert not exists(cache) and not return_kv_cache, 'interleaved decoding against the kv cache is driven by sample() / sample_many() (engine.KVCache); `forward_text` takes / returns a cache'
+
 
         rb, times = self.pack(modalities, times = times, num_modalities_to_times_fn = num_modalities_to_times_fn, prob_uncond = prob_uncond,
                               return_loss = return_loss, return_embed = return_embed, is_decoding = is_decoding)
@@ -605,12 +665,14 @@ class Transfusion(SamplingMixin, Module):
             res = self._run(rb, lat, eps, train = True, text_loss_weight = self.text_loss_weight, flow_loss_weight = self.flow_loss_weight)
             total = res['total']
             self._last_batch = rb
-            if not return_breakdown and not return_times:
+            if not return_breakdown and not return_hiddens and not return_times:
                 return total
             ret = (total,)
             if return_breakdown:
                 flows = [res['flows'][t] for t in range(self.num_modalities) if rb.type_rows[t][1] > rb.type_rows[t][0]]
                 ret = (*ret, LossBreakdown(total, res['text'], flows, None, [[] for _ in range(self.num_modalities)]))
+            if return_hiddens:
+                ret = (*ret, self._hiddens_padded(rb))
             if return_times:
                 ret = (*ret, times)
             return ret
@@ -622,6 +684,10 @@ class Transfusion(SamplingMixin, Module):
             for b in range(rb.B):
                 out[b, :rb.seq_lens[b]] = t[rb.cu[b]:rb.cu[b + 1], :width]
             return out
-        if return_embed:
-            return unpack(res['embed'], self.dim), rb
-        return unpack(res['logits'], self.to_text_logits.weight.shape[0])
+        out = (unpack(res['embed'], self.dim), rb) if return_embed else unpack(res['logits'], self.to_text_logits.weight.shape[0])
+        ret = (out,)                                   # aux packing order of the reference (T.py:3256-3271); the descriptor stands in for `get_pred_flows`
+        if return_hiddens:
+            ret = (*ret, self._hiddens_padded(rb))
+        if return_times:
+            ret = (*ret, times)
+        return ret[0] if len(ret) == 1 else ret

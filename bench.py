@@ -31,7 +31,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CTOR = dict(num_text_tokens = 256, dim_latent = 384, modality_default_shape = (256,), transformer = dict(dim = 512, depth = 8))
+CTOR4 = dict(num_text_tokens = 256, dim_latent = (384, 192), modality_default_shape = ((4,), (2,)), transformer = dict(dim = 512, depth = 8))
 SEQ = 1024
+WORKLOADS = {
+    'train': 'configs[1]: single-modality text+latent d=512 depth=8 dim_latent=384 seq=1024',
+    'config4': 'configs[3]: two modalities dim_latent=(384,192), ~15 short interleaved spans per 1024-token sample (span-mask attention stress)',
+    'sample_many': 'configs[4]: sample_many, 32 mixed prompts, kv cache, cfg_scale=3.0, forced 256x384 modality (16 midpoint steps), greedy text to max_length 512',
+}
 ALGO_TRAIN_FLOP_PER_TOKEN = 195.4e6            # 65.1 MFLOP/token forward x 3
 METRIC = 'train tokens/sec (text+latent) at d=512 L=8 seq=1024'
 
@@ -75,13 +81,18 @@ class ClockSampler(threading.Thread):
 
 # --------------------------------------------------------------------------------------------- reference arm / cpu baseline
 def cpu_port_tokens_per_s(batch: int, steps: int, warmup: int):
-    """Times the oracle port (the checker, here only as the reported CPU baseline) - fwd + bwd + Adam on the host cores."""
+    """Times the oracle port (the checker, here only as the reported CPU baseline) - fwd + bwd + Adam on the host cores; MEDIAN of `steps`
+    timed steps after `warmup`.  Threads: every core of the box (torch intra-op pool), stated in the record."""
+    import statistics
     import torch
     from transfusion_pytorch_b200 import Transfusion, synth
     from oracle.torch_reference import OracleEngine
     cores = os.cpu_count() or 1
-    torch.set_num_threads(min(cores, 64))
-    cores = min(cores, 64)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    torch.set_num_threads(cores)
     torch.manual_seed(0)
     model = Transfusion(**CTOR, prob_uncond = 0.)
     synth.fill_parameters_(model, seed = 0)
@@ -98,51 +109,91 @@ def cpu_port_tokens_per_s(batch: int, steps: int, warmup: int):
         dt = time.perf_counter() - t0
         if s >= warmup:
             times_.append(dt)
-    ms = 1e3 * sum(times_) / len(times_)
-    return batch * SEQ / (ms / 1e3), ms, cores
+    ms = 1e3 * statistics.median(times_)
+    return batch * SEQ / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def numa_note():
+    try:
+        nodes = [d for d in os.listdir('/sys/devices/system/node') if d.startswith('node')]
+        return f'{len(nodes)} NUMA node(s), threads not pinned (torch intra-op pool over all cores)'
+    except OSError:
+        return 'NUMA layout unknown'
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    b = 2
-    tps, ms, cores = cpu_port_tokens_per_s(b, max(args.steps, 1), min(args.warmup, 1))
+    # b = 4, 2 warm-up + 3 timed fwd + bwd + Adam steps, median (steps / warmup flags are honoured when they are smaller)
+    b = 4
+    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 2)
+    tps, ms, cores = cpu_port_tokens_per_s(b, steps, warm)
     line = dict(impl = 'reference', metric = METRIC, value = tps, unit = 'tokens/s', n_gpus = args.gpus, steps = args.steps, warmup = args.warmup, ms_per_step = ms,
                 higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'f32', data = 'synthetic',
-                config = dict(workload = 'configs[1]: single-modality text+latent d=512 depth=8 dim_latent=384 seq=1024', global_batch = b, seq_len = SEQ, parallelism = 'cpu'),
-                cpu_baseline = dict(value = tps, unit = 'tokens/s', cores = cores, kind = 'port', sample = f'{b} sequences x {SEQ} tokens per step, fwd+bwd+Adam, fp32, {args.steps} steps'),
+                config = dict(workload = WORKLOADS['train'], global_batch = b, seq_len = SEQ, parallelism = 'cpu'),
+                cpu_baseline = dict(value = tps, unit = 'tokens/s', cores = cores, kind = 'port',
+                                    sample = f'{b} sequences x {SEQ} tokens per step, fwd+bwd+Adam, fp32, median of {steps} timed steps after {warm} warm-up; {numa_note()}'),
                 e2e = dict(value = tps, unit = 'tokens/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0))
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
 def family_model(name, args_, eng, rb):
-    """(family, algorithmic flops, algorithmic bytes) of one C-ABI launch, from its arguments."""
+    """(family, algorithmic flops, algorithmic bytes) of one C-ABI launch, from its arguments.  FLOPs use the UN-padded problem sizes (the engine
+    pads the FFN inner dim 1365 -> 1408, the packed qkvg rows 1544 -> 1664, the time-MLP K 513 -> 576, vocab 390 -> 392: padding is not work).
+    Bytes = the tensors the kernel must read + write once, used for the GB/s of the HBM-bound kernels."""
     a = args_
+    D, HI, H, Ip, inner, M = eng.D, eng.HI, eng.H, eng.Ip, eng.inner, rb.M
+    real = {eng.Ip: eng.inner, 2 * eng.Ip: 2 * eng.inner, eng.NQ: 3 * HI + H, eng.Kt: D + 1, eng.Vp: eng.V}
+    for dl, dlp in zip(eng.dls, eng.dlp):
+        real.setdefault(dlp, dl)
+    r = lambda d: real.get(d, d)
     if name == 'gemm_store':
-        M, N, K = a[6], a[7], a[8]
-        return 'gemm(tcgen05)', 2.0 * M * N * K, 0
+        m, n, k = a[6], a[7], a[8]
+        return 'gemm(tcgen05)', 2.0 * r(m) * r(n) * r(k), 2.0 * (m * k + n * k) + 4.0 * m * n
     if name == 'gemm_qkvg':
-        M, H, D = a[4], a[5], a[6]
-        return 'gemm(tcgen05)', 2.0 * M * (3 * H * 64 + H) * D, 0
+        m, h, d = a[4], a[5], a[6]
+        return 'gemm(tcgen05)', 2.0 * m * (3 * h * 64 + h) * d, 2.0 * m * d + 2.0 * eng.NQ * d + 6.0 * m * h * 64
     if name == 'gemm_resid':
-        M, N, K = a[7], a[8], a[9]
-        Kr = eng.inner if K == eng.Ip else K
-        return 'gemm(tcgen05)', 2.0 * M * N * Kr, 0
+        m, n, k = a[7], a[8], a[9]
+        return 'gemm(tcgen05)', 2.0 * m * n * r(k), 2.0 * m * k + 2.0 * n * k + 8.0 * m * n + 2.0 * m * n
     if name == 'gemm_geglu':
-        M, K = a[5], a[7]
-        return 'gemm(tcgen05)', 2.0 * M * 2 * eng.inner * K, 0
+        m, k = a[5], a[7]
+        return 'gemm(tcgen05)', 2.0 * m * 2 * inner * k, 2.0 * m * k + 4.0 * Ip * k + 6.0 * m * Ip
     pairs = float(((rb.kv_limit.astype('int64') - (rb.cu[:-1].repeat(rb.seq_lens))) + 1).sum())
     if name == 'attn_fwd_tc':
-        return 'attention', 4.0 * pairs * 64 * eng.H, 0
+        return 'attention', 4.0 * pairs * 64 * H, 8.0 * M * HI
     if name == 'attn_fwd':
         return 'attention', 0, 0          # general kernel: returns at once when the tcgen05 path is active (flops credited to attn_fwd_tc)
     if name == 'attn_bwd_tc':
-        return 'attention', 10.0 * pairs * 64 * eng.H, 0
+        return 'attention', 10.0 * pairs * 64 * H, 8.0 * M * HI + 8.0 * M * HI + 2.0 * M * HI      # q k v dO in; dq dk fp32 + dv bf16 out
     if name == 'attn_bwd':
         return 'attention', 0, 0
-    return 'hbm-bound rows/elementwise', 0, 0
+    fam = 'hbm-bound rows/elementwise'
+    by = 0.0
+    if name == 'adaln_fwd': by = M * (4 * D + 2 * D + 8)
+    elif name == 'adaln_bwd': by = M * (4 * D + 4 * D + 8 * D + 8)
+    elif name == 'resid_bwd': by = M * (4 * D + 2 * D + 2 * D) if a[1] is not None else M * (4 * D + 2 * D)
+    elif name == 'attn_residual_fwd': by = M * (a[1] * 4 * D + 4 * D + 2 * D)
+    elif name == 'attn_residual_bwd': by = M * (a[2] * 4 * D + a[2] * (4 * D if a[-1] else 8 * D) + 8 * D)
+    elif name == 'geglu_bwd': by = M * (2 * Ip + 4 * Ip + 4 * Ip)
+    elif name == 'qk_bwd_pack': by = M * (8 * HI + 4 * HI + 4 * HI + 16 * H)
+    elif name == 'attn_bwd_prep': by = M * (4 * HI + 2 * HI + 4 * HI + 8 * H)
+    elif name == 'rmsnorm_fwd': by = M * (4 * D + 4 * D + 2 * D)
+    elif name == 'rmsnorm_bwd': by = M * 12 * D
+    elif name == 'embed_assemble': by = M * (4 * D + 4 * D + 2 * D)
+    elif name == 'embed_bwd': by = M * 8 * D
+    elif name == 'axpy_f32': by = 12.0 * a[3]
+    elif name == 'adam_step': by = 28.0 * a[4]
+    elif name == 'ce_fwd_bwd': by = M * (4 * eng.Vp + 2 * eng.Vp)
+    elif name == 'cast_pack_multi': by = 6.0 * eng.flat.numel()
+    elif name == 'flow_noise': by = a[7] * a[8] * (8 + 2 + 4)
+    elif name == 'mse_fwd_bwd': by = a[7] * a[8] * (8 + 2)
+    elif name == 'scatter_add_rows': by = a[3] * 12 * D
+    elif name in ('colsum_f32',): by = 4.0 * a[2] * a[3]
+    elif name in ('colsum_bf16',): by = 2.0 * a[2] * a[3]
+    return fam, 0, float(by)
 
 
 def log(*a):
@@ -161,34 +212,40 @@ def run_b200_arm(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':     # NCCL's banner goes to stdout: keep stdout to the ONE JSON line
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')          # whatever NCCL_DEBUG the caller chose goes to stderr: stdout carries ONE JSON line
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id = torch.device('cuda', local))
     dev = torch.device('cuda', local)
-    B = args.batch
+    B = args.batch if args.scaling == 'weak' else max(1, args.batch // world)      # strong scaling: --batch is the GLOBAL batch, split over the ranks
     torch.manual_seed(0)
-    model = Transfusion(**CTOR).to(dev)                      # prob_uncond = 0.1 (reference default), train mode
+    cfg4 = args.workload == 'config4'
+    model = Transfusion(**(CTOR4 if cfg4 else CTOR)).to(dev)      # prob_uncond = 0.1 (reference default), train mode
     synth.fill_parameters_(model, seed = 0)
     model.train()
-    trainer = DataParallelTrainer(model, lr = 1e-4, cuda_graph = not args.no_graph)
+    trainer = DataParallelTrainer(model, lr = 1e-4, cuda_graph = not args.no_graph, overlap = not args.no_overlap)
     eng = model.engine
     eng.ensure_attached()
 
     POOL = 4
-    host_batches = [synth.config2_batch(B, seed = 1000 * rank + i) for i in range(POOL)]
-    host_batches = [[[p.pin_memory() if p.is_floating_point() else p for p in s] for s in b] for b in host_batches]
-    host_times = [synth.config2_times(B, seed = 1000 * rank + i) for i in range(POOL)]
+    if cfg4:
+        host_batches = [synth.config4_batch(B, seed = 1000 * rank + i) for i in range(POOL)]
+        nm = max(sum(isinstance(p, tuple) for p in s_) for b in host_batches for s_ in b)
+        host_times = [torch.rand(B, nm, generator = torch.Generator().manual_seed(7 + 1000 * rank + i)) for i in range(POOL)]
+        host_batches = [[[(p[0], p[1].pin_memory()) if isinstance(p, tuple) else p for p in s_] for s_ in b] for b in host_batches]
+    else:
+        host_batches = [synth.config2_batch(B, seed = 1000 * rank + i) for i in range(POOL)]
+        host_batches = [[[p.pin_memory() if p.is_floating_point() else p for p in s_] for s_ in b] for b in host_batches]
+        host_times = [synth.config2_times(B, seed = 1000 * rank + i) for i in range(POOL)]
 
     # ---- device-resident variant: packed descriptors + latents already in HBM
     packed = []
     for b, t in zip(host_batches, host_times):
-        samples = [[torch.tensor([model.sos_id]), *s, torch.tensor([model.eos_id])] for s in b]
+        samples = [[torch.tensor([model.sos_id]), *s_, torch.tensor([model.eos_id])] for s_ in b]
         rb = pack_batch(samples, t, model, return_loss = True, return_embed = False)
         lat = model._latents_to_device(rb)
         eng.upload(rb)
         packed.append((rb, lat))
-    assert packed[0][0].M == B * SEQ
+    assert packed[0][0].M == B * SEQ, packed[0][0].M
     log('packed', POOL, 'batches; M =', packed[0][0].M)
 
     profiling = [False]                                      # roofline pass: every rank launches eagerly (same collectives on all ranks)
@@ -196,36 +253,7 @@ def run_b200_arm(args):
         rb, lat = packed[i % POOL]
         if trainer.cuda_graph and not profiling[0]:
             return trainer.step_packed(rb, lat)              # CUDA-graph replay of the step (after two eager steps of this shape)
-        eng.zero_grad()
-        loss = model.forward_packed(rb, lat)
-        if world > 1 and trainer.overlap:
-            # same overlap machinery as DataParallelTrainer.step
-            bounds = trainer._bucket_bounds(eng)
-            if trainer.comm_stream is None:
-                trainer.comm_stream = torch.cuda.Stream()
-            hi = [trainer._tail]
-            def cb(l):
-                lo = bounds[l]
-                ev = torch.cuda.Event(); ev.record()
-                with torch.cuda.stream(trainer.comm_stream):
-                    trainer.comm_stream.wait_event(ev)
-                    dist.all_reduce(eng.gflat[lo:hi[0]])
-                hi[0] = lo
-            eng._bucket_cb = cb
-            loss.backward()
-            eng._bucket_cb = None
-            ev = torch.cuda.Event(); ev.record()
-            with torch.cuda.stream(trainer.comm_stream):
-                trainer.comm_stream.wait_event(ev)
-                if hi[0] > 0:
-                    dist.all_reduce(eng.gflat[:hi[0]])
-                if trainer._tail < eng.gflat.numel():
-                    dist.all_reduce(eng.gflat[trainer._tail:])
-            torch.cuda.current_stream().wait_stream(trainer.comm_stream)
-        else:
-            loss.backward()
-        eng.adam_step(lr = 1e-4, grad_scale = 1.0 / world, zero_grads = True)
-        return loss
+        return trainer.step_packed_eager(rb, lat)
 
     def barrier():
         if world > 1:
@@ -262,7 +290,7 @@ def run_b200_arm(args):
     log('resident ms/step', ms_step)
     value = world * B * SEQ / (ms_step / 1e3)
 
-    # ---- end to end through the public API (pack/route + H2D + D2H every step)
+    # ---- end to end through the public API (pack/route + H2D + D2H every step), over the SAME number of steps
     # Every step: Python pack/route of host samples, H2D of that step's inputs from pinned memory, fwd + bwd + optimizer, and a D2H
     # read of a loss.  The loss that is read inside step i is the one of step i-1 (asynchronous logging: the value is fetched while step i
     # runs on the device, so the host packs step i+1 instead of idling); the last loss is read before the timed region closes.
@@ -282,14 +310,22 @@ def run_b200_arm(args):
         step_e2e(i)
         if i == e2e_loop.last:
             pending[0].value(); pending[0] = None              # drain: the final step's loss is read inside the timed region too
-    for i in range(min(args.warmup, 3)):
+    for i in range(max(3, min(args.warmup, 3))):
         step_e2e(i)
     pending[0].value(); pending[0] = None
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = args.steps
     e2e_loop.last = e2e_steps - 1
     ms_e2e = timed(e2e_loop, e2e_steps) / e2e_steps
     e2e_value = world * B * SEQ / (ms_e2e / 1e3)
     log('e2e ms/step', ms_e2e)
+
+    # replicas must still be identical after all those steps (every rank applied the same averaged gradient)
+    spread = None
+    if world > 1:
+        cs = eng.flat.double().sum().reshape(1)
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op = dist.ReduceOp.MIN); dist.all_reduce(hi, op = dist.ReduceOp.MAX)
+        spread = float((hi - lo).item())
 
     # ---- per-kernel-family device time of one step (profiling pass, not part of the reported throughput)
     # every rank runs the step (it contains the gradient all-reduce); only rank 0 records per-launch events
@@ -306,56 +342,192 @@ def run_b200_arm(args):
             for e0, e1, a in recs:
                 f, fl, by = family_model(name, a, eng, rb)
                 ms = e0.elapsed_time(e1)
-                d = fam.setdefault(f, dict(ms = 0., flops = 0., launches = 0))
-                d['ms'] += ms; d['flops'] += fl; d['launches'] += 1
-                if fl > 0:                                    # per kernel instance (entry point + problem shape)
-                    label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else '')
-                    k = inst.setdefault(label, dict(ms = 0., flops = 0., launches = 0))
-                    k['ms'] += ms; k['flops'] += fl; k['launches'] += 1
+                d = fam.setdefault(f, dict(ms = 0., flops = 0., bytes = 0., launches = 0))
+                d['ms'] += ms; d['flops'] += fl; d['bytes'] += by; d['launches'] += 1
+                label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else '')      # per kernel instance (entry point + problem shape)
+                k = inst.setdefault(label, dict(ms = 0., flops = 0., bytes = 0., launches = 0, family = f))
+                k['ms'] += ms; k['flops'] += fl; k['bytes'] += by; k['launches'] += 1
         eng.ops.timing = None
         pk = peaks()
         tot = sum(d['ms'] for d in fam.values())
         top = max((f for f in fam if fam[f]['flops'] > 0), key = lambda f: fam[f]['ms'])
         ach = fam[top]['flops'] / (fam[top]['ms'] / 1e3) / 1e12
-        roof = dict(bound = 'tensor', kernel = top, achieved = ach, peak = pk['tf_sustained'], unit = 'TFLOP/s', frac = ach / pk['tf_sustained'], traffic = None,
-                    peak_source = pk['src'] + ' (sustained bf16 GEMM)', share_of_step = fam[top]['ms'] / tot,
-                    families = {f: dict(ms = round(d['ms'], 3), share = round(d['ms'] / tot, 3), launches = d['launches'],
-                                        tflops = round(d['flops'] / (d['ms'] / 1e3) / 1e12, 1) if d['flops'] else None) for f, d in fam.items()},
-                    whole_step_tflops = value * ALGO_TRAIN_FLOP_PER_TOKEN / 1e12 / world, whole_step_frac = value * ALGO_TRAIN_FLOP_PER_TOKEN / 1e12 / world / pk['tf_sustained'])
-        # the five kernel instances with the largest share of the step: algorithmic FLOPs per launch / average launch duration (CUDA events),
-        # DRAM traffic per launch from the committed ncu captures (measured at batch 32; null for other batch sizes / kernels)
-        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-        tmap = json.load(open(tpath)) if os.path.isfile(tpath) else {}
-        top = sorted(inst.items(), key = lambda kv: -kv[1]['ms'])[:5]
-        roof['kernels'] = [dict(kernel = lbl, launches = k['launches'], us_per_launch = round(1e3 * k['ms'] / k['launches'], 1), share_of_step = round(k['ms'] / tot, 3),
-                                achieved = round(k['flops'] / (k['ms'] / 1e3) / 1e12, 1), frac = round(k['flops'] / (k['ms'] / 1e3) / 1e12 / pk['tf_sustained'], 3),
-                                traffic = (tmap.get(lbl) if B == 32 else None)) for lbl, k in top]
+        # DRAM traffic per launch from the committed ncu `--set full` capture of THIS command line (profiles/r02_traffic.json: {batch: {label: bytes}})
+        tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+        tmap = (json.load(open(tpath)) if os.path.isfile(tpath) else {}).get(f'{args.workload}:b{B}', {})
+        def fam_row(d):
+            row = dict(ms = round(d['ms'], 3), share = round(d['ms'] / tot, 3), launches = d['launches'])
+            if d['flops']:
+                row.update(tflops = round(d['flops'] / (d['ms'] / 1e3) / 1e12, 1), frac_of_tensor_peak = round(d['flops'] / (d['ms'] / 1e3) / 1e12 / pk['tf_sustained'], 3))
+            else:
+                row.update(gbs = round(d['bytes'] / (d['ms'] / 1e3) / 1e9, 1), frac_of_hbm_peak = round(d['bytes'] / (d['ms'] / 1e3) / 1e9 / pk['hbm'], 3))
+            return row
+        def inst_row(lbl, k):
+            row = dict(kernel = lbl, family = k['family'], launches = k['launches'], us_per_launch = round(1e3 * k['ms'] / k['launches'], 1), share_of_step = round(k['ms'] / tot, 3))
+            if k['flops']:
+                a_ = k['flops'] / (k['ms'] / 1e3) / 1e12
+                row.update(bound = 'tensor', achieved = round(a_, 1), unit = 'TFLOP/s', frac = round(a_ / pk['tf_sustained'], 3))
+            else:
+                a_ = k['bytes'] / (k['ms'] / 1e3) / 1e9
+                row.update(bound = 'hbm', achieved = round(a_, 1), unit = 'GB/s', frac = round(a_ / pk['hbm'], 3))
+            row['algorithmic_bytes'] = int(k['bytes'] / k['launches'])
+            row['traffic'] = tmap.get(lbl)
+            return row
+        ranked = sorted(inst.items(), key = lambda kv: -kv[1]['ms'])
+        whole = value * ALGO_TRAIN_FLOP_PER_TOKEN / 1e12 / world
+        roof = dict(bound = 'tensor', kernel = top, achieved = ach, peak = pk['tf_sustained'], unit = 'TFLOP/s', frac = ach / pk['tf_sustained'],
+                    traffic = tmap.get(ranked[0][0]) if ranked else None, traffic_kernel = ranked[0][0] if ranked else None,
+                    peak_source = pk['src'] + ' (sustained bf16 GEMM; burst ' + str(pk['tf_burst']) + ', HBM copy ' + str(pk['hbm']) + ' GB/s)', share_of_step = fam[top]['ms'] / tot,
+                    flops_model = 'un-padded problem sizes (FFN inner 1365, qkvg rows 1544, time-MLP K 513, vocab 390)',
+                    families = {f: fam_row(d) for f, d in fam.items()},
+                    whole_step_tflops = whole, whole_step_frac = whole / pk['tf_sustained'], whole_step_frac_of_burst = whole / pk['tf_burst'],
+                    kernels = [inst_row(lbl, k) for lbl, k in ranked[:12]])
 
     if rank == 0:
         clocks = sampler.summary() if sampler else None
         cpu = None
         log('roofline pass done')
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not cfg4:
             tps, ms_cpu, cores = cpu_port_tokens_per_s(2, 2, 1)
-            cpu = dict(value = tps, unit = 'tokens/s', cores = cores, kind = 'port', sample = f'2 sequences x {SEQ} tokens per step (fwd+bwd+Adam, fp32), 2 timed steps after 1 warm-up')
-        line = dict(metric = METRIC, value = value, unit = 'tokens/s', n_gpus = world, steps = args.steps, warmup = args.warmup, ms_per_step = ms_step, higher_is_better = True,
-                    scaling = 'weak', vs_baseline = None, dtype = 'bf16', data = 'synthetic',
-                    config = dict(workload = 'configs[1]: single-modality text+latent d=512 depth=8 dim_latent=384 seq=1024', global_batch = world * B, per_gpu_batch = B,
-                                  seq_len = SEQ, parallelism = f'dp{world}', optimizer = 'fused Adam', launch = 'cuda graph replay' if trainer.cuda_graph else 'eager', l2 = 'per-step working set (>10 GB of activations) is far larger than the 126 MB L2; 4 rotating input batches'),
-                    e2e = dict(value = e2e_value, unit = 'tokens/s', ms_per_step = ms_e2e, h2d_bytes_per_step = int(h2d[0]), d2h_bytes_per_step = 4,
+            cpu = dict(value = tps, unit = 'tokens/s', cores = cores, kind = 'port',
+                       sample = f'2 sequences x {SEQ} tokens per step (fwd+bwd+Adam, fp32), median of 2 timed steps after 1 warm-up; {numa_note()}; the full BASELINE.md section-3 protocol '
+                                '(b=4, 2+3 steps) is `--impl reference`')
+        line = dict(metric = METRIC if not cfg4 else METRIC + ' [config 4: two modalities, span-mask stress]', value = value, unit = 'tokens/s', n_gpus = world, steps = args.steps,
+                    warmup = args.warmup, ms_per_step = ms_step, higher_is_better = True,
+                    scaling = args.scaling, vs_baseline = None, dtype = 'bf16', data = 'synthetic',
+                    config = dict(workload = WORKLOADS[args.workload], global_batch = world * B, per_gpu_batch = B,
+                                  grad_allreduce = (f'fp32 flat buffer, ~{trainer.bucket_bytes >> 20} MB per-layer buckets on a side stream overlapped with backward inside the step graph'
+                                                    if trainer.overlap else 'one fp32 all-reduce after backward') if world > 1 else None,
+                                  seq_len = SEQ, parallelism = f'dp{world}', optimizer = 'fused Adam', launch = 'cuda graph replay' if trainer.cuda_graph else 'eager',
+                                  l2 = 'per-step working set (>10 GB of activations) is far larger than the 126 MB L2; 4 rotating input batches'),
+                    e2e = dict(value = e2e_value, unit = 'tokens/s', ms_per_step = ms_e2e, steps = e2e_steps, h2d_bytes_per_step = int(h2d[0]), d2h_bytes_per_step = 4,
                                loss_read = 'every step, deferred by one step (asynchronous logging)',
                                host_ms_per_step = round(sum(host_e2e[-e2e_steps:]) / e2e_steps, 3)),
-                    gpu_launches = int(launches), host_enqueue_ms_per_step = round(host_enqueue_ms, 3), clocks = clocks, roofline = roof, cpu_baseline = cpu)
+                    gpu_launches = int(launches), host_enqueue_ms_per_step = round(host_enqueue_ms, 3), clocks = clocks, roofline = roof, cpu_baseline = cpu,
+                    replica_checksum_spread = spread)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        # captured graphs hold NCCL work: drop them, drain the device, leave together.  The process then exits without running the
-        # process-group destructor (observed to hang after graph-captured collectives); every rank has already passed the barrier.
+        # captured graphs hold NCCL work: drop them and drain the device before the process group goes away.  The destructor has been
+        # observed to hang after graph-captured collectives, so it runs under a watchdog; every rank has passed the barrier by then.
         trainer._graphs.clear()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
+        def teardown():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+        threading.Thread(target = teardown, daemon = True).start()
+        if not done.wait(20):
+            log('process-group teardown did not finish in 20 s: exiting without it')
+            os._exit(0)
+
+
+# --------------------------------------------------------------------------------------------- sample_many workload (BASELINE.json configs[4])
+def config5_prompts(n_each, seed = 0):
+    import torch
+    g = torch.Generator().manual_seed(4242 + seed)
+    prompts = []
+    for _ in range(n_each):                                   # README.md:162-167 prompt forms, SURVEY.md 8(d) config 5
+        prompts.append(torch.randint(0, 256, (16,), generator = g))
+        prompts.append((0, torch.randn(int(torch.randint(4, 65, (1,), generator = g)), 384, generator = g)))
+        prompts.append(None)
+        prompts.append([torch.randint(0, 256, (8,), generator = g), (0, torch.randn(int(torch.randint(6, 33, (1,), generator = g)), 384, generator = g))])
+    noise = torch.randn(256, 384, generator = g)
+    return prompts, noise
+
+
+def run_sample_many(args):
+    """configs[4]: wall time and generated tokens/s of `sample_many` (32 mixed prompts, kv cache, cfg 3, 16 midpoint steps over a forced 256 x 384 modality, greedy
+    text to max_length 512), KV-read bandwidth of the text loop, the FLOP saving over prefix recomputation, and the reference algorithm on the host beside it."""
+    import copy
+    import torch
+    from transfusion_pytorch_b200 import Transfusion, synth
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    model = Transfusion(**CTOR).to(dev).eval()
+    synth.fill_parameters_(model, seed = 0)
+    n_prompts, max_length, steps_ode, Lm = args.prompts, args.max_length, 16, 256
+    prompts, noise = config5_prompts(n_prompts // 4)
+    kw = dict(max_length = max_length, text_temperature = 0., cfg_scale = 3.0, modality_steps = steps_ode, init_modality_noise = noise, force_modality_at_start = (0, (Lm,)),
+              return_unprocessed_modalities = True)
+    eng = model.engine
+    for _ in range(max(1, args.warmup)):
+        out = model.sample_many(copy.deepcopy(prompts), **kw)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0); sampler.start()
+    times_ms, l0 = [], eng.ops.launches
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        out = model.sample_many(copy.deepcopy(prompts), **kw)          # host prompts in, host samples out: H2D / D2H inside the timed region
+        e1.record(); torch.cuda.synchronize()
+        times_ms.append((1e3 * (time.perf_counter() - t0), e0.elapsed_time(e1)))
+    sampler.stop_flag = True
+    launches = (eng.ops.launches - l0) // args.steps
+    wall_ms = sorted(t[0] for t in times_ms)[len(times_ms) // 2]
+    # generated tokens: the 256 modality positions + every sampled text token of every sample
+    prep = [model.prepare_prompt_sample(copy.deepcopy(p), kw['force_modality_at_start'])[0] for p in prompts]
+    plen = [model._parts_len(p) for p in prep]
+    total_len = [model._parts_len(s_) for s_ in out]
+    gen = [t - p for t, p in zip(total_len, plen)]
+    text_tokens = [g - Lm - 1 for g in gen]                             # minus the modality and the [eom] the sampler appends itself
+    n_gen = sum(gen)
+    # transformer FLOPs per generated token: kv-cache path vs re-running the packed prefix at every text step / ODE evaluation (round 1)
+    FWD = 65.1e6 / 1.0                                                  # forward MFLOP per token (SURVEY.md 8(d)), linear layers dominate
+    evals = 2 * (steps_ode - 1)
+    cached = sum(p for p in plen) + n_prompts * (evals * 2 * Lm) + sum(text_tokens) + sum(p + 0 for p in plen)      # prefill + (cond+uncond) ODE tokens + text steps + uncond prefill
+    recompute = n_prompts * evals * 2 * (sum(plen) / n_prompts + Lm) + sum(sum(range(p + Lm + 1, p + Lm + 1 + t)) for p, t in zip(plen, text_tokens))
+    # KV bytes the text loop reads: every step reads the whole slab prefix of every sample, K and V, all layers
+    kv_bytes = sum(sum(range(p + Lm + 1, p + Lm + 1 + t)) for p, t in zip(plen, text_tokens)) * eng.HI * 2 * 2 * eng.depth
+    pk = peaks()
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_sample_many(args, prompts, noise)
+    line = dict(metric = 'sample_many generated tokens/sec (text + latent positions), config 5', value = n_gen / (wall_ms / 1e3), unit = 'tokens/s', n_gpus = 1, steps = args.steps, warmup = args.warmup,
+                ms_per_step = wall_ms, higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'bf16', data = 'synthetic',
+                config = dict(workload = WORKLOADS['sample_many'], prompts = n_prompts, max_length = max_length, modality = [Lm, 384], modality_steps = steps_ode, cfg_scale = 3.0,
+                              text = 'greedy', launch = 'captured text-step graph + captured ODE-evaluation graph'),
+                e2e = dict(value = n_gen / (wall_ms / 1e3), unit = 'tokens/s', wall_ms = wall_ms, device_ms = sorted(t[1] for t in times_ms)[len(times_ms) // 2],
+                           h2d_bytes_per_step = int(sum(p[1].numel() * 4 for pr in prompts for p in ([pr] if isinstance(pr, tuple) else (pr if isinstance(pr, list) else [])) if isinstance(p, tuple)) + noise.numel() * 4),
+                           d2h_bytes_per_step = int(n_prompts * Lm * 384 * 4 + 4 * sum(text_tokens))),
+                gpu_launches = int(launches), generated = dict(total = n_gen, text = int(sum(text_tokens)), latent_positions = n_prompts * Lm),
+                transformer_token_forwards = dict(kv_cache = int(cached), prefix_recompute = int(recompute), saving = round(recompute / cached, 1)),
+                roofline = dict(bound = 'hbm', kernel = 'attn_decode (text loop, kv read)', achieved = None, peak = pk['hbm'], unit = 'GB/s', frac = None,
+                                traffic = None, kv_bytes_text_loop = int(kv_bytes), note = 'the text loop is launch / latency bound at 32 samples: see text_loop_ms'),
+                clocks = sampler.summary(), cpu_baseline = cpu)
+    print(json.dumps(line))
+
+
+def cpu_sample_many(args, prompts, noise):
+    """the reference algorithm (oracle port: padded kv caches are replaced by slabs, everything else - per-token conditioning, dense masks - as the
+    reference) on the host cores, on a BOUNDED sample: 4 of the prompts, 4 midpoint steps, 24 text tokens"""
+    import copy
+    import torch
+    from transfusion_pytorch_b200 import Transfusion, synth
+    from oracle.torch_reference import OracleEngine
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = Transfusion(**CTOR).eval()
+    synth.fill_parameters_(model, seed = 0)
+    model._engine = OracleEngine(model)
+    sub = prompts[:4]
+    kw = dict(max_length = 256 + 24, text_temperature = 0., cfg_scale = 3.0, modality_steps = 4, init_modality_noise = noise, force_modality_at_start = (0, (256,)),
+              return_unprocessed_modalities = True)
+    t0 = time.perf_counter()
+    out = model.sample_many(copy.deepcopy(sub), **kw)
+    dt = time.perf_counter() - t0
+    prep = [model.prepare_prompt_sample(copy.deepcopy(p), kw['force_modality_at_start'])[0] for p in sub]
+    n_gen = sum(model._parts_len(s_) - model._parts_len(p) for s_, p in zip(out, prep))
+    return dict(value = n_gen / dt, unit = 'tokens/s', cores = torch.get_num_threads(), kind = 'port',
+                sample = f'4 prompts, forced 256x384 modality with 4 midpoint steps (6 evaluations x cond/uncond), 24 greedy text tokens: {n_gen} generated positions in {dt:.1f} s')
 
 
 def main():
@@ -365,11 +537,18 @@ def main():
     ap.add_argument('--warmup', type = int, default = 3)
     ap.add_argument('--batch', type = int, default = 128, help = 'sequences (x1024 tokens) per GPU per step (swept 32 / 64 / 128 on B200: 2.00 / 2.12 / 2.18 M tokens/s)')
     ap.add_argument('--impl', default = 'b200', choices = ['b200', 'reference'])
+    ap.add_argument('--workload', default = 'train', choices = sorted(WORKLOADS), help = 'train = configs[1] (the graded metric); config4 = two-modality span stress; sample_many = configs[4]')
+    ap.add_argument('--prompts', type = int, default = 32, help = 'sample_many: number of prompts (multiple of 4)')
+    ap.add_argument('--max-length', type = int, default = 512, help = 'sample_many: max_length')
+    ap.add_argument('--scaling', default = 'weak', choices = ['weak', 'strong'], help = 'strong: --batch is the global batch (fixed total work as N grows)')
+    ap.add_argument('--no-overlap', action = 'store_true', help = 'N > 1: one all-reduce after backward instead of per-layer buckets overlapped with it')
     ap.add_argument('--no-cpu-baseline', action = 'store_true')
     ap.add_argument('--no-graph', action = 'store_true', help = 'eager kernel launches instead of CUDA-graph replay (N = 1)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
+    elif args.workload == 'sample_many':
+        run_sample_many(args)
     else:
         run_b200_arm(args)
 

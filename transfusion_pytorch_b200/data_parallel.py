@@ -52,12 +52,13 @@ class _StepGraph:
 
 class DataParallelTrainer:
     def __init__(self, model, lr = 1e-3, betas = (0.9, 0.999), eps = 1e-8, weight_decay = 0., decoupled_weight_decay = False, overlap = True, cuda_graph = True, graph_multi_gpu = True,
-                 max_grad_norm = None, ema_decay = None):
+                 max_grad_norm = None, ema_decay = None, bucket_mb = 25):
         self.model = model
         self.hp = dict(lr = lr, betas = betas, eps = eps, weight_decay = weight_decay, decoupled = decoupled_weight_decay)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.overlap = overlap and self.world > 1
         self.comm_stream = None
+        self.bucket_bytes = int(bucket_mb * 2 ** 20)
         self._cpu_opt = None
         # the rest of the step the reference's example scripts run: clip_grad_norm_(max_grad_norm) before the optimizer, EMA after it
         self.max_grad_norm, self.ema_decay = max_grad_norm, ema_decay
@@ -167,9 +168,9 @@ class DataParallelTrainer:
             l0 = eng.ops.launches
             with torch.cuda.graph(graph):
                 res = eng.forward(rb, g.lat, g.eps, train = True, text_loss_weight = model.text_loss_weight, flow_loss_weight = model.flow_loss_weight)
-                eng.backward()
-                if self.world > 1:
-                    dist.all_reduce(eng.gflat)            # NCCL all-reduce of the flat gradient buffer, captured as a graph node
+                # NCCL all-reduce of the flat gradient buffer captured INSIDE the step graph: per-layer buckets on the communication stream, forked
+                # from / joined to the capture stream, so the collective of layers >= i overlaps the backward kernels of layers < i on every replay
+                self._backward_allreduce(eng, lambda cb: eng.backward(bucket_cb = cb))
                 if self.max_grad_norm is not None:
                     eng.clip_grad_norm_(self.max_grad_norm, 1.0 / self.world)
                 eng.adam_step(grad_scale = 1.0 / self.world, zero_grads = True, device_step = True, **self.hp)
@@ -206,6 +207,61 @@ class DataParallelTrainer:
             self._tail = max((off + eng.named[n].numel() for n, off in eng.offs.items() if n.startswith('transformer.layers.') and off < eng.late_start), default = 0)
         return self._bounds
 
+    def _bucket_cb(self, eng):
+        """callback for `Engine.backward(bucket_cb=)`: all-reduce the flat-gradient slice of the layers whose backward kernels have just been enqueued,
+        on the communication stream, behind an event recorded on the compute stream (works eagerly and under CUDA-graph capture, where the event
+        record / wait become fork / join edges of the graph)."""
+        bounds = self._bucket_bounds(eng)
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+        hi = [self._tail]
+        def cb(i):
+            lo = bounds[i]
+            if (hi[0] - lo) * 4 < self.bucket_bytes and i > 0:
+                return                                            # keep growing the bucket (~25 MB buckets: launch latency vs overlap)
+            ev = torch.cuda.Event(); ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(eng.gflat[lo:hi[0]])
+            hi[0] = lo
+        def finish():
+            ev = torch.cuda.Event(); ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                if hi[0] > 0:
+                    dist.all_reduce(eng.gflat[:hi[0]])
+                if self._tail < eng.gflat.numel():
+                    dist.all_reduce(eng.gflat[self._tail:])   # final norm, heads, embedding and the conditioning ("late") parameters
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        return cb, finish
+
+    def _backward_allreduce(self, eng, run_backward):
+        """backward + gradient all-reduce: per-layer buckets overlapped with the rest of backward (`overlap`), or one call afterwards"""
+        if self.world > 1 and self.overlap:
+            cb, finish = self._bucket_cb(eng)
+            run_backward(cb)
+            finish()
+        else:
+            run_backward(None)
+            if self.world > 1:
+                dist.all_reduce(eng.gflat)
+
+    def step_packed_eager(self, rb, latents, noise = None):
+        """the step of `step_packed` launched eagerly (profiling passes, shapes that are not captured)"""
+        model, eng = self.model, self.model.engine
+        eng.ensure_attached()
+        self._sync_replicas(eng)
+        eng.upload(rb)
+        eng.zero_grad()
+        loss = model.forward_packed(rb, latents, noise = noise)
+        def run(cb):
+            eng._bucket_cb = cb
+            loss.backward()
+            eng._bucket_cb = None
+        self._backward_allreduce(eng, run)
+        self._finish_step(eng)
+        return loss
+
     def _finish_step(self, eng):
         """[clip] -> fused Adam (clears the gradient buffer: the next step's zero_grad() is free) -> [EMA]"""
         if self.max_grad_norm is not None:
@@ -223,12 +279,7 @@ class DataParallelTrainer:
         eng.upload(rb)
         loss = self._graph_step(rb, device_lat = latents, noise = noise) if self.cuda_graph else None
         if loss is None:
-            eng.zero_grad()
-            loss = model.forward_packed(rb, latents, noise = noise)
-            loss.backward()
-            if self.world > 1:
-                dist.all_reduce(eng.gflat)
-            self._finish_step(eng)
+            loss = self.step_packed_eager(rb, latents, noise = noise)
         return loss
 
     def step(self, batch, times = None, noise = None, **fw):
@@ -254,42 +305,22 @@ class DataParallelTrainer:
             for p in model.parameters():
                 p.grad = None
             loss = model(batch, times = times, noise = noise, **fw)
-        # With graph replay enabled every step - captured or eager - issues exactly ONE all-reduce of the whole gradient buffer, so ranks whose
-        # batches have different shape signatures (one replaying, one still eager) stay in lock-step on the communicator.
-        if cuda and self.overlap and not self.cuda_graph:
-            bounds = self._bucket_bounds(eng)
-            if self.comm_stream is None:
-                self.comm_stream = torch.cuda.Stream()
-            hi = [self._tail]
-            def cb(i):
-                lo = bounds[i]
-                ev = torch.cuda.Event(); ev.record()
-                with torch.cuda.stream(self.comm_stream):
-                    self.comm_stream.wait_event(ev)
-                    dist.all_reduce(eng.gflat[lo:hi[0]])
-                hi[0] = lo
-            eng._bucket_cb = cb
-            loss.backward()
-            eng._bucket_cb = None
-            ev = torch.cuda.Event(); ev.record()
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
-                if hi[0] > 0:
-                    dist.all_reduce(eng.gflat[:hi[0]])
-                if self._tail < eng.gflat.numel():
-                    dist.all_reduce(eng.gflat[self._tail:])
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        # Eager and captured steps issue the SAME sequence of collectives (same bucket boundaries), so ranks whose batches have different shape
+        # signatures (one replaying a graph, one still launching eagerly) stay in lock-step on the communicator.
+        if cuda:
+            def run(cb):
+                eng._bucket_cb = cb
+                loss.backward()
+                eng._bucket_cb = None
+            self._backward_allreduce(eng, run)
         else:
             loss.backward()
             if self.world > 1:
-                if cuda:
-                    dist.all_reduce(eng.gflat)
-                else:
-                    grads = [p.grad for p in model.parameters() if p.grad is not None]
-                    flat = torch._utils._flatten_dense_tensors(grads)
-                    dist.all_reduce(flat)
-                    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                        g.copy_(f)
+                grads = [p.grad for p in model.parameters() if p.grad is not None]
+                flat = torch._utils._flatten_dense_tensors(grads)
+                dist.all_reduce(flat)
+                for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                    g.copy_(f)
         if cuda:
             self._finish_step(eng)
         else:

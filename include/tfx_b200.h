@@ -41,10 +41,12 @@ int tfx_gemm_store(const void* A, long long lda, int a_mn_major, const void* B, 
  * (q_norm, k_norm), 964-965 (apply_rotary_emb), 1027 (to_gates).  Outputs q,k (post-RoPE), v: bf16 [M][H*64];
  * gates fp32 [M][H] (logits); qk_inv fp32 [M][2H] (saved 1/|x| for backward).
  * kv_rows (optional, [M]): in-place kv-cache append - token m's post-RoPE key and its value are written to ROW kv_rows[m] of k / v, which
- * then point at one layer of the slab cache (replaces the cat / pad / stack of T.py:969-977, 2257-2277); q stays dense. */
+ * then point at one layer of the slab cache (replaces the cat / pad / stack of T.py:969-977, 2257-2277); q stays dense.
+ * mix_pre (optional, fp32 [M][H], H <= 16): rows [3*H*64 + H, 3*H*64 + 2H) of W hold `to_learned_value_residual` (T.py:894-898); their products are
+ * written here (pre-bias, pre-sigmoid). */
 int tfx_gemm_qkvg(const void* u, long long ldu, const void* W, long long ldw, int M, int H, int D, void* q, void* k, void* v, float* gates, float* qk_inv,
                   const float* q_gamma, const float* k_gamma, const int* rope_pos, const float* rope_cs_t /* [32][rope_len][2], see tfx_rope_table */, int rope_len,
-                  const int* kv_rows, void* stream);
+                  const int* kv_rows, float* mix_pre, void* stream);
 
 /* branch output projection + AdaptiveWrapper output gate + residual:
  *   y = [A | A2] W^T + bias ;  x_out = x_res + y * (cond_row[m] >= 0 ? zgate[cond_row[m]] : layerscale + 1)
@@ -73,6 +75,14 @@ int tfx_attn_fwd_tc(const void* q, const void* k, const void* v, long long ld_q,
                     const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
                     void* o, long long ld_o, float* lse, int M, int M_kv /* rows of k / v when they are a kv cache (T.py:969-972); 0 = M */, float scale, float softcap,
                     const float* fast_params, void* stream);
+/* Persistent forward of the same path (attention_fwd_sm100.cu): one CTA per SM walks (pair of adjacent 128-row query tiles, head) items; the two
+ * tiles of a pair share one 4-stage K / V TMA ring and ping-pong on two S accumulators; P stays in TMEM (tcgen05.st + TS-form tcgen05.mma).
+ * `pairs[n_pairs]`: (index of the pair's first tile in the tile_* tables) * 2 + (1 if the next tile belongs to the same sequence and is the
+ * pair's second tile), sorted by cost (key tiles), heaviest first.  Replaces the same ATen calls as tfx_attn_fwd_tc (T.py:998-1027). */
+int tfx_attn_fwd_ts(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
+                    const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
+                    const int* pairs, int n_pairs, void* o, long long ld_o, float* lse, int M, int M_kv, float scale, float softcap,
+                    const float* fast_params, void* stream);
 /* dq_zero (optional): fp32 [M][H*64] accumulator of tfx_attn_bwd, cleared here in the same pass */
 int tfx_attn_bwd_prep(const void* do_gated, const void* o_gated, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, float* dq_zero, int M, int H, void* stream);
 int tfx_attn_bwd(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
@@ -89,6 +99,21 @@ int tfx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* do_
 int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const void* k_bf16, const float* qk_inv, const float* q_gamma, const float* k_gamma,
                     const int* rope_pos, const float* rope_cs, const float* gates, const float* dsum_mh, void* dqkvg_bf16, long long out_ld,
                     float* dq_gamma, float* dk_gamma, int M, int H, void* stream);
+
+/* ---------------------------------------------------------------- optional attention variants (attn_variants.cu), HBM-bound row kernels
+ * LASER (T.py:981-983, 1021-1022): v' = exp(c tanh(v / c)) before the attention, att = log(o') * sigmoid(gate) after it; `rows` (optional) maps token m to its
+ * kv-cache row (raw values stay in the cache, T.py:976-977; the transformed copy is a second slab).  Backward: tfx_laser_bwd_prep replaces tfx_attn_bwd_prep
+ * (dO' = dAtt sg / o', D = sum_d dAtt sg, gate sums = sum_d dAtt att), tfx_laser_v_bwd turns dv' into dv in place. */
+int tfx_laser_v_fwd(const void* v, long long ld_v, const int* rows, void* v_laser, long long ld_vl, int M, int H, float clamp, void* stream);
+int tfx_laser_out_fwd(const void* o_laser, const float* gates, void* att, int M, int H, void* stream);
+int tfx_laser_bwd_prep(const void* d_att, const void* o_laser, const float* gates, void* do_pre, float* dsum_hm, float* dsum_mh, float* dq_zero, int M, int H, void* stream);
+int tfx_laser_v_bwd(void* dv_inout, long long ld_dv, const void* v, long long ld_v, int M, int H, float clamp, void* stream);
+/* learned value residual (T.py:956-960, 1234): v = v mix + v_first (1 - mix), mix = sigmoid(mix_pre + bias) per token and head, in place (also on cache rows).
+ * Backward (dv_inout: d v_mixed -> d v_raw): dv_first_acc (fp32 [M][H*64]) += d v_mixed (1 - mix); d mix_pre -> bf16 column block of the packed dqkvg matrix. */
+int tfx_vmix_fwd(void* v_inout, long long ld_v, const int* rows, const void* v_first, long long ld_v0, const float* mix_pre, const float* mix_bias, int M, int H, void* stream);
+int tfx_vmix_bwd(void* dv_inout, long long ld_dv, const void* v_mixed, long long ld_v, const void* v_first, long long ld_v0, const float* mix_pre, const float* mix_bias,
+                 float* dv_first_acc, void* dmix_bf16, long long ld_dmix, int M, int H, void* stream);
+int tfx_add_f32_into_bf16(void* dst_bf16, long long ld_dst, const float* src, long long ld_src, int M, int N, void* stream);
 
 /* ---------------------------------------------------------------- warp-per-token kernels (D = model dim, multiple of 128, <= 1024)
  * AdaptiveWrapper input side (T.py:747-755, text-only 677-679): u = isM ? LN(x)(gamma_c+1)+beta_c : LN(x)(g+1).

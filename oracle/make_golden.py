@@ -244,6 +244,29 @@ def run_sampling_sized(ref, name, ctor, seed, n_each, mod_len, steps, max_length
         print(f'  sample {i}:', [tuple(p.shape) if torch.is_tensor(p) else ('mod', p[0], tuple(p[1].shape)) for p in s], 'min margin %.4f' % min(margins[i], default = float('nan')))
 
 
+def run_velocity(ref, name, ctor, batch, times, seed, delta = 1e-3):
+    """velocity-consistency training step (T.py:2965-2971, 3084-3088, 3383-3418) with an EMA teacher whose parameters differ from the student's.
+    randn_like calls: student draw(s) first, then the teacher's (one per modality type each) - both injected."""
+    torch.manual_seed(0)
+    model = ref.Transfusion(**ctor, modality_processing = 'flat')
+    synth.fill_parameters_(model, seed = seed)
+    model.eval()
+    ema = model.create_ema(0.99)
+    synth.fill_parameters_(ema.ema_model, seed = seed + 5)
+    calls = []
+    def fake_randn_like(t):
+        e = noise_for(t.shape[0], t.shape[1], 9000 + len(calls) + 17 * seed)
+        calls.append(tuple(t.shape))
+        return e.to(t)
+    with mock.patch('torch.randn_like', side_effect = fake_randn_like):
+        loss, breakdown = model(batch, times = times, velocity_consistency_ema_model = ema, velocity_consistency_delta_time = delta, return_breakdown = True)
+    loss.backward()
+    fx = dict(name = name, ctor = ctor, seed = seed, times = times, delta = delta, noise_shapes = calls, loss = loss.detach().double(), text_loss = breakdown.text.detach().double(),
+              flow_losses = [f.detach().double() for f in breakdown.flow], velocity_losses = [v.detach().double() for v in breakdown.velocity], grads = grad_fingerprint(model))
+    torch.save(compact(fx), os.path.join(GOLDEN, f'{name}.pt'))
+    print(f'{name}: loss {loss.item():.6f} flow {[round(f.item(), 6) for f in breakdown.flow]} velocity {[round(v.item(), 6) for v in breakdown.velocity]} draws {calls}')
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok = True)
     ref = load_reference()
@@ -266,6 +289,20 @@ def main():
     if only in ('', 'config1'):
         ctor = dict(num_text_tokens = 256, transformer = dict(dim = 128, depth = 2))
         run_text_only(ref, 'config1_text_only', ctor, synth.text_batch(4, 257, seed = 3), seed = 3)
+    if only in ('', 'velocity'):
+        ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), transformer = dict(dim = 128, depth = 2, heads = 2))
+        batch = synth.small_batch(3, seed = 1, dim_latent = 32, text_vocab = 64)
+        times = torch.rand(3, count_modalities(batch), generator = torch.Generator().manual_seed(5))
+        run_velocity(ref, 'small_velocity', ctor, batch, times, seed = 1)
+    if only in ('', 'variants'):
+        # optional attention variants of SURVEY 8(f) rank 4: LASER (T.py:981-983, 1021-1022; config 1's own script uses it, train_text_only.py:70) and
+        # the learned value residual (T.py:956-960, 1234)
+        ctor = dict(num_text_tokens = 256, transformer = dict(dim = 128, depth = 2, attn_laser = True))
+        run_text_only(ref, 'config1_laser', ctor, synth.text_batch(4, 257, seed = 3), seed = 3)
+        ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), transformer = dict(dim = 128, depth = 4, heads = 2, attn_laser = True, use_value_residual = True))
+        batch = synth.small_batch(3, seed = 1, dim_latent = 32, text_vocab = 64)
+        times = torch.rand(3, count_modalities(batch), generator = torch.Generator().manual_seed(5))
+        run_interleaved(ref, 'small_laser_vres', ctor, batch, times, seed = 1)
     if only:
         return
 

@@ -168,6 +168,46 @@ def test_attention_tcgen05_fast_path_vs_dense(ops, lens, spans):
     assert fp[0].item() == 0.0
 
 
+@pytest.mark.parametrize('lens,spans', [([1024, 1024], [(0, 206, 256), (0, 668, 256), (1, 100, 700)]), ([77, 130, 5, 300], [(0, 10, 40), (1, 64, 64), (1, 128, 2), (3, 120, 150)]), ([64], []),
+                                        ([128, 129, 127], [(1, 0, 129)]), ([1024] * 40, [(b, 206, 256) for b in range(40)] + [(b, 668, 256) for b in range(40)]),
+                                        ([385, 1000, 257, 640, 129, 900, 31], [(1, 100, 800), (3, 0, 640), (5, 300, 77), (5, 500, 300)])])
+def test_attention_persistent_ts_forward_vs_dense(ops, lens, spans):
+    """persistent two-warpgroup forward with P in TMEM (attention_fwd_sm100.cu) vs the dense fp32 attention and vs the round-1 tcgen05 kernel;
+    the 40-sequence case gives every CTA several work items (Q double buffering, K / V ring wrap-around, group drift across items)"""
+    H, cap, scale = 4, 50., 0.125
+    rb = make_rb(lens, spans)
+    M = rb.M
+    g = torch.Generator(device = 'cuda').manual_seed(1)
+    def unit(x):
+        x = x.reshape(M, H, 64)
+        return (torch.nn.functional.normalize(x, dim = -1) * 8.).reshape(M, H * 64).to(BF16)
+    q, k = (unit(torch.randn(M, H * 64, device = 'cuda', generator = g)) for _ in range(2))
+    q[: M // 2] = k[: M // 2]
+    v = (torch.randn(M, H * 64, device = 'cuda', generator = g) * 2).to(BF16)
+    gates = torch.randn(M, H, device = 'cuda', generator = g)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    kvl = dev(rb.kv_limit)
+    fp = torch.zeros(8, device = 'cuda')
+    zeros = torch.zeros(64, device = 'cuda')
+    ops.attn_fast_params(zeros, zeros, 64, scale, cap, fp)
+    t2 = [dev(getattr(rb, n)) for n in ('t2_q0', 't2_qend', 't2_kv0', 't2_kvend')]
+    # pair table: every 128-row tile appears exactly once
+    seen = sorted([c >> 1 for c in rb.p2.tolist()] + [(c >> 1) + 1 for c in rb.p2.tolist() if c & 1])
+    assert seen == list(range(len(rb.t2_q0)))
+    o = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16); lse = torch.zeros(H, M, device = 'cuda')
+    for _ in range(2):                              # twice: a relaunch must not depend on leftover state
+        o.zero_(); lse.zero_()
+        ops.attn_fwd_ts(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, *t2, len(rb.t2_q0), dev(rb.p2), len(rb.p2), o, H * 64, lse, M, 0, scale, cap, fp)
+    o1 = torch.zeros_like(o); lse1 = torch.zeros_like(lse)
+    ops.attn_fwd_tc(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, *t2, len(rb.t2_q0), o1, H * 64, lse1, M, 0, scale, cap, fp)
+    torch.cuda.synchronize()
+    assert torch.allclose(lse, lse1, atol = 1e-4, rtol = 1e-5)
+    assert torch.allclose(o.float(), o1.float(), atol = 1e-2, rtol = 1e-2)
+    if M <= 4096:
+        ref = dense_attention(q.float(), k.float(), v.float(), gates, kvl.long(), rb.cu.tolist(), scale, cap)
+        assert torch.allclose(o.float(), ref, atol = 3e-2, rtol = 3e-2)
+
+
 def test_rowops_vs_torch(ops):
     M, D, nc = 777, 512, 5
     g = torch.Generator(device = 'cuda').manual_seed(2)
@@ -240,7 +280,7 @@ def test_gemm_qkvg_epilogue_vs_torch(ops, M, H, D):
     freqs, t, tt = _rope_tables(ops, 1024)
     q, k, v = (torch.zeros(M, HI, device = 'cuda', dtype = BF16) for _ in range(3))
     gates = torch.zeros(M, H, device = 'cuda'); inv = torch.zeros(M, 2 * H, device = 'cuda')
-    ops.gemm_qkvg(u, D, W, D, M, H, D, q, k, v, gates, inv, gq, gk, pos, tt, 1024, None)
+    ops.gemm_qkvg(u, D, W, D, M, H, D, q, k, v, gates, inv, gq, gk, pos, tt, 1024, None, None)
     y = u.float() @ W.float().t()
     rms = lambda x, gm: torch.nn.functional.normalize(x, dim = -1) * 8. * (gm + 1.)
     qr = _rope_ref(rms(y[:, :HI].reshape(M, H, 64), gq), pos, freqs).reshape(M, HI)
@@ -255,7 +295,7 @@ def test_gemm_qkvg_epilogue_vs_torch(ops, M, H, D):
     rows = torch.randperm(2 * M + 50, device = 'cuda', generator = g)[:M].to(torch.int32)
     kc = torch.zeros(2 * M + 50, HI, device = 'cuda', dtype = BF16); vc = torch.zeros_like(kc)
     q2 = torch.zeros_like(q)
-    ops.gemm_qkvg(u, D, W, D, M, H, D, q2, kc, vc, gates, inv, gq, gk, pos, tt, 1024, rows)
+    ops.gemm_qkvg(u, D, W, D, M, H, D, q2, kc, vc, gates, inv, gq, gk, pos, tt, 1024, rows, None)
     torch.cuda.synchronize()
     assert torch.equal(q2, q) and torch.equal(kc[rows.long()], k) and torch.equal(vc[rows.long()], v)
     untouched = torch.ones(2 * M + 50, dtype = torch.bool, device = 'cuda'); untouched[rows.long()] = False

@@ -12,7 +12,7 @@ from test_ops_gpu import make_rb
 
 def main():
     ops = _lib.Ops()
-    B, H, cap, scale = 32, 8, 50., 0.125
+    B, H, cap, scale = int(os.environ.get('BATCH', 32)), 8, 50., 0.125
     lens = [1024] * B
     spans = [(b, off, 256) for b in range(B) for off in (206, 668)]
     rb = make_rb(lens, spans)
@@ -31,10 +31,14 @@ def main():
     o = torch.zeros(M, H * 64, device = 'cuda', dtype = torch.bfloat16); lse = torch.zeros(H, M, device = 'cuda')
     do = torch.randn(M, H * 64, device = 'cuda', generator = g).to(torch.bfloat16)
     dsum = torch.zeros(H, M, device = 'cuda'); dq = torch.zeros(M, H * 64, device = 'cuda'); dk = torch.zeros_like(dq); dv = torch.zeros_like(o)
-    def fwd(): ops.attn_fwd_tc(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, *t2, len(rb.t2_q0), o, H * 64, lse, M, scale, cap, fp)
+    p2 = dev(rb.p2)
+    def fwd(): ops.attn_fwd_tc(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, *t2, len(rb.t2_q0), o, H * 64, lse, M, 0, scale, cap, fp)
+    def fwd_ts(): ops.attn_fwd_ts(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, *t2, len(rb.t2_q0), p2, len(rb.p2), o, H * 64, lse, M, 0, scale, cap, fp)
     def bwd(): ops.attn_bwd_tc(q, k, v, do, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, *k2, len(rb.k2_kv0), dq, dk, dv, H * 64, M, H, scale, cap, fp)
     big = torch.empty(256 << 20, dtype = torch.uint8, device = 'cuda')
-    for name, fn in (('fwd', fwd), ('bwd', bwd)):
+    pairs = float((rb.kv_limit.astype('int64') - rb.cu[:-1].repeat(rb.seq_lens) + 1).sum())
+    flops = dict(fwd = 4.0 * pairs * 64 * H, fwd_ts = 4.0 * pairs * 64 * H, bwd = 10.0 * pairs * 64 * H)
+    for name, fn in (('fwd', fwd), ('fwd_ts', fwd_ts), ('bwd', bwd)):
         for _ in range(3): fn()
         ts = []
         for _ in range(10):
@@ -42,6 +46,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
-        print(f'{os.environ.get("TFX_LIB", "default"):40s} {name}: median {sorted(ts)[5]:8.1f} us  min {min(ts):8.1f} us')
+        med = sorted(ts)[5]
+        print(f'{os.environ.get("TFX_LIB", "default"):24s} B={B} {name:7s}: median {med:8.1f} us  min {min(ts):8.1f} us  {flops[name] / med / 1e6:7.1f} TFLOP/s algorithmic')
 if __name__ == '__main__':
     main()

@@ -20,11 +20,12 @@ VP, I, LL, F, ULL = c_void_p, c_int, c_longlong, c_float, c_ulonglong
 SIGNATURES = {
     'tfx_init': [I],
     'tfx_gemm_store': [VP, LL, I, VP, LL, I, I, I, I, VP, LL, VP, LL, VP, VP, F, I, I, VP],
-    'tfx_gemm_qkvg': [VP, LL, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, I, VP, VP],
+    'tfx_gemm_qkvg': [VP, LL, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP],
     'tfx_gemm_resid': [VP, LL, VP, LL, I, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, LL, VP, VP],
     'tfx_gemm_geglu': [VP, LL, VP, LL, VP, I, I, I, VP, VP, VP],
     'tfx_attn_fwd': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, LL, VP, I, F, F, VP, VP],
     'tfx_attn_fwd_tc': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, LL, VP, I, I, F, F, VP, VP],
+    'tfx_attn_fwd_ts': [VP, VP, VP, LL, LL, LL, VP, I, VP, VP, VP, VP, VP, I, VP, I, VP, LL, VP, I, I, F, F, VP, VP],
     'tfx_attn_fast_params': [VP, VP, I, F, F, VP, VP],
     'tfx_attn_bwd_prep': [VP, VP, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_attn_bwd': [VP, VP, VP, VP, LL, LL, LL, LL, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP, LL, I, I, F, F, VP, VP],
@@ -63,6 +64,13 @@ SIGNATURES = {
     'tfx_ode_pre': [VP, VP, VP, LL, I, VP, VP, VP, I, VP],
     'tfx_ode_post': [VP, VP, VP, VP, F, LL, VP, VP, VP],
     'tfx_counter_inc': [VP, VP],
+    'tfx_laser_v_fwd': [VP, LL, VP, VP, LL, I, I, F, VP],
+    'tfx_laser_out_fwd': [VP, VP, VP, I, I, VP],
+    'tfx_laser_bwd_prep': [VP, VP, VP, VP, VP, VP, VP, I, I, VP],
+    'tfx_laser_v_bwd': [VP, LL, VP, LL, I, I, F, VP],
+    'tfx_vmix_fwd': [VP, LL, VP, VP, LL, VP, VP, I, I, VP],
+    'tfx_vmix_bwd': [VP, LL, VP, LL, VP, LL, VP, VP, VP, VP, LL, I, I, VP],
+    'tfx_add_f32_into_bf16': [VP, LL, VP, LL, I, I, VP],
 }
 
 EXPORTED = ['tfx_last_error', 'tfx_version', 'tfx_geglu_bwd_rows_per_block', 'tfx_attn_residual_bwd_workspace_floats'] + list(SIGNATURES)

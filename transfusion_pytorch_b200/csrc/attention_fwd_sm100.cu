@@ -1,0 +1,361 @@
+// Persistent tcgen05 / TMEM / TMA forward of the span-masked, soft-capped attention (bounded-logit path; semantics and the
+// polynomial-tanh / fixed-maximum softmax are those of attention_sm100.cu; reference transfusion.py:998-1027, mask :452-470).
+//
+// What changed against the round-1 forward (one CTA per (128-row tile, head), 2 CTAs / SM, K / V single-buffered, P through shared memory):
+// the per-tile chain TMA -> S MMA -> softmax -> P (smem, proxy fence) -> PV MMA was latency bound (a K / V load was only issued after the
+// previous tile's MMA had retired, ~1 us of exposed load latency per key tile).  Here
+//   * ONE persistent CTA per SM walks a cost-sorted list of work items; an item = (PAIR of adjacent 128-row query tiles of one sequence, head):
+//     both tiles stream the SAME K / V tiles through a 4-stage TMA ring (prefetch distance 3 tiles, also across items); Q is double-buffered
+//     across items, so the next item's first S = Q K^T is issued while the current item drains;
+//   * two softmax warpgroups (one per query tile of the pair) ping-pong on two S accumulators in TMEM: while one group exponentiates, the
+//     tensor core computes the other group's S / PV.  The two groups are independent consumers of the shared tile stream and may drift apart by
+//     up to ring-depth tiles (a tile pair rarely has the same number of visible key tiles);
+//   * P never touches shared memory: the softmax threads write bf16 P straight into TMEM (tcgen05.st) and the PV product is a TS-form
+//     tcgen05.mma (A = P from TMEM, B = V from smem).  TMEM: S0 S1 [0,256) | O0 O1 [256,384) | P0 P1 [384,512) - all 512 columns;
+//   * the MMA lane is a small polling state machine over both groups' next S / PV operation, so neither group is blocked behind the other.
+//
+//   warp 0   : TMA producer (Q pair per item, K_j | V_j per key tile)
+//   warp 1   : tcgen05.mma issuer + TMEM owner
+//   warps 2-5: softmax group 0 (query tile A), thread <-> query row          warps 6-9: softmax group 1 (query tile B)
+#include "sm100_ptx.cuh"
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "../../include/tfx_b200.h"
+#include <limits.h>
+
+namespace tfx {
+
+int num_sms();
+
+constexpr int F2_THREADS = 320;
+constexpr int F2_STAGES = 4;                       // K / V ring depth (32 KB per stage: K tile | V tile)
+constexpr int F2_SMEM = 2 * 32768 + F2_STAGES * 32768 + 1024 /*align*/ + 512 /*barriers*/;
+
+// tanh(y) ~= y * (C0 + C1 u + C2 u^2 + C3 u^3 + C4 u^4), u = y^2, |y| <= 0.75 (same fit as attention_sm100.cu)
+#define F2_C0 9.9999722832e-01f
+#define F2_C1 -3.3323076483e-01f
+#define F2_C2 1.3226091649e-01f
+#define F2_C3 -4.9280448379e-02f
+#define F2_C4 1.2318833231e-02f
+
+__device__ __forceinline__ float f2_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+struct F2Item { int q0[2], qend[2], n[2]; int kv0, nmax, head; };
+
+// work item k of this CTA (static snake schedule over the cost-sorted pair list, heaviest first)
+__device__ __forceinline__ bool f2_item(int k, int n_items, int H, const int* __restrict__ pairs, const int* __restrict__ t_q0, const int* __restrict__ t_qend,
+                                        const int* __restrict__ t_kv0, const int* __restrict__ t_kvend, F2Item& it) {
+  const int G = gridDim.x;
+  const int pos = (k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+  const int idx = k * G + pos;
+  if (idx >= n_items) return false;
+  const int pr = idx / H;
+  it.head = idx - pr * H;
+  const int code = pairs[pr];
+  const int ta = code >> 1;
+  it.kv0 = t_kv0[ta];
+  it.q0[0] = t_q0[ta]; it.qend[0] = t_qend[ta];
+  it.n[0] = (t_kvend[ta] - it.kv0 + 127) >> 7;
+  if (code & 1) {
+    it.q0[1] = t_q0[ta + 1]; it.qend[1] = t_qend[ta + 1];
+    it.n[1] = (t_kvend[ta + 1] - it.kv0 + 127) >> 7;
+  } else {
+    it.q0[1] = it.q0[0]; it.qend[1] = it.q0[0]; it.n[1] = 0;
+  }
+  it.nmax = it.n[0] > it.n[1] ? it.n[0] : it.n[1];
+  return true;
+}
+
+__device__ __forceinline__ bool f2_has(int k, int n_items) {
+  const int G = gridDim.x;
+  return k * G + ((k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x) < n_items;
+}
+
+// MMA-lane cursor of one softmax group over its operation stream: (item, key tile) of the next S (or PV) product
+struct F2Cur {
+  int k;            // item index of this CTA
+  int j;            // key tile inside the item
+  int n;            // key tiles this group needs in the item
+  uint32_t tb;      // global tile-stream index of the item's first key tile (K / V ring position)
+  int nmax;         // key tiles of the item (both groups)
+  bool ok;
+};
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+              const float* __restrict__ gates, int H, const int* __restrict__ kv_limit, const int* __restrict__ t_q0, const int* __restrict__ t_qend,
+              const int* __restrict__ t_kv0, const int* __restrict__ t_kvend, const int* __restrict__ pairs, int n_items,
+              __nv_bfloat16* __restrict__ o, long long ld_o, float* __restrict__ lse, int M, float scale, float cap, const float* __restrict__ fast) {
+  if (fast[0] == 0.f) return;                       // precondition of this path does not hold: the general kernel does the work
+  extern __shared__ uint8_t f2_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(f2_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // [2 item slots][tile A 16 KB | tile B 16 KB]
+  uint8_t* sKV = smem + 65536;                       // [F2_STAGES][K 16 KB | V 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + F2_STAGES * 32768);
+  uint64_t *q_full = bars, *q_empty = bars + 2, *kv_full = bars + 4, *kv_empty = bars + 4 + F2_STAGES, *s_full = bars + 4 + 2 * F2_STAGES, *s_empty = s_full + 2,
+           *p_full = s_full + 4, *p_empty = s_full + 6, *o_full = s_full + 8, *o_empty = s_full + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1); mbar_init(&q_empty[b], 1);
+      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4); mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);
+    }
+    for (int s = 0; s < F2_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      F2Item it;
+      uint32_t t = 0;
+      for (int k = 0; f2_item(k, n_items, H, pairs, t_q0, t_qend, t_kv0, t_kvend, it); ++k) {
+        const int qs = k & 1;
+        mbar_wait(&q_empty[qs], ((k >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], it.n[1] > 0 ? 32768 : 16384);
+        tma_load_2d(&tmQ, &q_full[qs], sQ + qs * 32768, it.head * 64, it.q0[0]);
+        if (it.n[1] > 0) tma_load_2d(&tmQ, &q_full[qs], sQ + qs * 32768 + 16384, it.head * 64, it.q0[1]);
+        for (int j = 0; j < it.nmax; ++j, ++t) {
+          const int st = t & (F2_STAGES - 1);
+          mbar_wait(&kv_empty[st], ((t / F2_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 32768);
+          tma_load_2d(&tmK, &kv_full[st], sKV + st * 32768, it.head * 64, it.kv0 + j * 128);
+          tma_load_2d(&tmV, &kv_full[st], sKV + st * 32768 + 16384, it.head * 64, it.kv0 + j * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer: polling state machine over both groups' next S / PV product
+    if (lane == 0) {
+      constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);       // S = Q K^T : A, B K-major
+      constexpr uint32_t idO = umma_idesc_bf16(128, 64, 0, 1);        // O += P V  : A = P (TMEM), B = V MN-major
+      F2Cur cs[2], cp[2];
+      uint32_t gs[2] = {0, 0}, gp[2] = {0, 0}, oc[2] = {0, 0};
+      F2Item it;
+      auto seek = [&](F2Cur& c, int w, int k_from, uint32_t tb_from) {   // first item >= k_from in which group w has work
+        c.k = k_from; c.tb = tb_from; c.j = 0; c.ok = false;
+        while (f2_item(c.k, n_items, H, pairs, t_q0, t_qend, t_kv0, t_kvend, it)) {
+          c.n = it.n[w]; c.nmax = it.nmax;
+          if (c.n > 0) { c.ok = true; return; }
+          c.tb += it.nmax; ++c.k;
+        }
+      };
+      auto advance = [&](F2Cur& c, int w) { if (++c.j == c.n) seek(c, w, c.k + 1, c.tb + c.nmax); };
+      for (int w = 0; w < 2; ++w) { seek(cs[w], w, 0, 0); cp[w] = cs[w]; }
+      int q_rel = 0;                 // items whose Q slot has been handed back to the producer
+      uint32_t kv_rel = 0;           // key tiles (stream index) handed back
+      const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
+      while (cs[0].ok || cs[1].ok || cp[0].ok || cp[1].ok) {
+        bool progress = false;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          // ---- S_w(item, j) = Q_w K_j^T
+          if (cs[w].ok) {
+            F2Cur& c = cs[w];
+            const uint32_t t = c.tb + c.j;
+            const int st = t & (F2_STAGES - 1);
+            bool ready = mbar_test_wait(&kv_full[st], (t / F2_STAGES) & 1);
+            if (ready && c.j == 0) ready = mbar_test_wait(&q_full[c.k & 1], (c.k >> 1) & 1);
+            if (ready && gs[w] > 0) ready = mbar_test_wait(&s_empty[w], (gs[w] - 1) & 1);
+            if (ready) {
+              tc_fence_after();
+              const uint32_t a = aQ + (c.k & 1) * 32768 + w * 16384, b = aKV + st * 32768;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16_ss(tmem_base + w * 128, umma_smem_desc_sw128(a + kk * 32, 0, 1024), umma_smem_desc_sw128(b + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
+              umma_commit(&s_full[w]);
+              ++gs[w];
+              advance(c, w);
+              // Q slots: released (in item order) once both groups have issued their last S product of the item
+              for (;;) {
+                const int k0 = cs[0].ok ? cs[0].k : INT_MAX, k1 = cs[1].ok ? cs[1].k : INT_MAX;
+                if (q_rel < (k0 < k1 ? k0 : k1) && f2_has(q_rel, n_items)) { umma_commit(&q_empty[q_rel & 1]); ++q_rel; }
+                else break;
+              }
+              progress = true;
+            }
+          }
+          // ---- O_w (+)= P_w(item, j) V_j
+          if (cp[w].ok) {
+            F2Cur& c = cp[w];
+            bool ready = mbar_test_wait(&p_full[w], gp[w] & 1);
+            if (ready && c.j == 0 && oc[w] > 0) ready = mbar_test_wait(&o_empty[w], (oc[w] - 1) & 1);
+            if (ready) {
+              tc_fence_after();
+              const uint32_t t = c.tb + c.j;
+              const uint32_t bV = aKV + (t & (F2_STAGES - 1)) * 32768 + 16384;
+              const uint32_t tO = tmem_base + 256 + w * 64, tP = tmem_base + 384 + w * 64;
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_bf16_ts(tO, tP + kk * 8, umma_smem_desc_sw128(bV + kk * 2048, 8192, 1024), idO, (c.j > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(&p_empty[w]);
+              ++gp[w];
+              if (c.j == c.n - 1) { umma_commit(&o_full[w]); ++oc[w]; }
+              advance(c, w);
+              // K / V ring: a stage goes back once every group that needs the tile has issued its PV product
+              for (;;) {
+                const uint32_t n0 = cp[0].ok ? cp[0].tb + cp[0].j : 0xffffffffu, n1 = cp[1].ok ? cp[1].tb + cp[1].j : 0xffffffffu;
+                const uint32_t nmin = n0 < n1 ? n0 : n1;
+                // when both groups are finished everything issued so far may go back; the producer never waits on those phases
+                if (kv_rel < nmin && (cp[0].ok || cp[1].ok)) { umma_commit(&kv_empty[kv_rel & (F2_STAGES - 1)]); ++kv_rel; }
+                else break;
+              }
+              progress = true;
+            }
+          }
+        }
+        if (!progress) __nanosleep(20);
+      }
+    }
+  } else {
+    // ===================================================== softmax groups (thread <-> query row)
+    const int w = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const uint32_t tS = tmem_base + w * 128 + lane_addr, tO = tmem_base + 256 + w * 64 + lane_addr, tP = tmem_base + 384 + w * 64 + lane_addr;
+    const float k1 = scale / cap;                    // y = x * k1
+    const float KL = cap * 1.4426950408889634f;      // exponent (base 2) = KL * tanh(y) - m2
+    const float m2 = fast[1] * 1.4426950408889634f;
+    const float k2 = k1 * k1;
+    const float a0 = KL * k1 * F2_C0, a1 = KL * k1 * k2 * F2_C1, a2 = KL * k1 * k2 * k2 * F2_C2, a3 = KL * k1 * k2 * k2 * k2 * F2_C3,
+                a4 = KL * k1 * k2 * k2 * k2 * k2 * F2_C4;
+    const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), A3 = make_float2(a3, a3), A4 = make_float2(a4, a4),
+                 NM2 = make_float2(-m2, -m2);
+    uint32_t g = 0, oc = 0;
+    F2Item it;
+    for (int k = 0; f2_item(k, n_items, H, pairs, t_q0, t_qend, t_kv0, t_kvend, it); ++k) {
+      const int n = it.n[w];
+      if (n == 0) continue;
+      const int grow = it.q0[w] + row;
+      const bool valid = grow < it.qend[w];
+      const int lim = valid ? kv_limit[grow] : -1;
+      const int wmin = __reduce_min_sync(0xffffffffu, valid ? lim : INT_MAX);   // key tiles entirely below it need no mask (per warp)
+      float gate = 1.f;
+      if (valid && gates) gate = 1.f / (1.f + __expf(-gates[(long long)grow * H + it.head]));
+      float2 l2 = make_float2(0.f, 0.f);
+      for (int j = 0; j < n; ++j, ++g) {
+        const int key0 = it.kv0 + j * 128;
+        const bool all_visible = key0 + 127 <= wmin;
+        uint32_t pk[64];
+        mbar_wait(&s_full[w], g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(tS + hf * 64, r0);
+          tmem_ld_32x32b_x32(tS + hf * 64 + 32, r1);
+          tmem_ld_wait();
+          if (hf == 1) {                               // S is in registers: the accumulator may be overwritten by the next S product
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[w]);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t* r = c ? r1 : r0;
+            const int kbase = key0 + hf * 64 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {          // packed fp32x2 FMAs (FFMA2): two scores per instruction
+              const float2 x = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+              const float2 X = __fmul2_rn(x, x);
+              float2 gq = __ffma2_rn(A4, X, A3);
+              gq = __ffma2_rn(gq, X, A2);
+              gq = __ffma2_rn(gq, X, A1);
+              gq = __ffma2_rn(gq, X, A0);
+              const float2 e = __ffma2_rn(x, gq, NM2);
+              float p0 = f2_ex2(e.x), p1 = f2_ex2(e.y);
+              if (!all_visible) { p0 = (kbase + i <= lim) ? p0 : 0.f; p1 = (kbase + i + 1 <= lim) ? p1 : 0.f; }
+              l2 = __fadd2_rn(l2, make_float2(p0, p1));
+              pk[hf * 32 + c * 16 + (i >> 1)] = pack_bf16(p0, p1);
+            }
+          }
+        }
+        if (g > 0) mbar_wait(&p_empty[w], (g - 1) & 1);    // the previous PV product has consumed the P buffer
+        tc_fence_after();
+        tmem_st_32x32b_x32(tP, pk);
+        tmem_st_32x32b_x32(tP + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[w]);
+      }
+      // ---- epilogue of the item: O / l * sigmoid(gate) -> bf16
+      mbar_wait(&o_full[w], oc & 1);
+      ++oc;
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(tO, r0);
+      tmem_ld_32x32b_x32(tO + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[w]);
+      const float l = l2.x + l2.y;
+      const float gsc = (l > 0.f ? 1.f / l : 0.f) * gate;
+      if (valid) {
+        __nv_bfloat16* dst = o + (long long)grow * ld_o + it.head * 64;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const uint32_t* r = hf ? r1 : r0;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint32_t wv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) wv[e] = pack_bf16(__uint_as_float(r[qd * 8 + 2 * e]) * gsc, __uint_as_float(r[qd * 8 + 2 * e + 1]) * gsc);
+            *reinterpret_cast<uint4*>(dst + hf * 32 + qd * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          }
+        }
+        if (lse) lse[(long long)it.head * M + grow] = fast[1] + logf(l);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace tfx
+
+using namespace tfx;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int tfx_attn_fwd_ts(const void* q, const void* k, const void* v, long long ld_q, long long ld_k, long long ld_v, const float* gates, int H,
+                    const int* kv_limit, const int* tile_q0, const int* tile_qend, const int* tile_kv0, const int* tile_kvend, int n_tiles,
+                    const int* pairs, int n_pairs, void* o, long long ld_o, float* lse, int M, int M_kv, float scale, float softcap, const float* fast_params,
+                    void* stream) {
+  if (n_pairs <= 0 || n_tiles <= 0) return 0;
+  if (M_kv <= 0) M_kv = M;
+  TFX_REQUIRE(fast_params != nullptr && pairs != nullptr, "attn_fwd_ts: fast_params (from tfx_attn_fast_params) and the tile-pair list are required");
+  TFX_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 8 == 0, "attn_fwd_ts: row pitches must be multiples of 8 bf16");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bf16(&tq, q, (long long)H * 64, M, ld_q, 128)) || (rc = make_tmap_bf16(&tk, k, (long long)H * 64, M_kv, ld_k, 128)) ||
+      (rc = make_tmap_bf16(&tv, v, (long long)H * 64, M_kv, ld_v, 128))) {
+    set_error("attn_fwd_ts: cuTensorMapEncodeTiled failed (%d)", rc);
+    return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_fwd_ts_k, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM) != cudaSuccess) { set_error("attn_fwd_ts: cannot raise dynamic smem"); return -2; }
+    attr_set = true;
+  }
+  const int n_items = n_pairs * H;
+  const int grid = n_items < num_sms() ? n_items : num_sms();          // persistent: one CTA per SM
+  attn_fwd_ts_k<<<grid, F2_THREADS, F2_SMEM, ST(stream)>>>(tq, tk, tv, gates, H, kv_limit, tile_q0, tile_qend, tile_kv0, tile_kvend, pairs, n_items, (__nv_bfloat16*)o, ld_o, lse, M,
+                                                          scale, softcap, fast_params);
+  return check_launch("attn_fwd_ts");
+}
+
+}  // extern "C"

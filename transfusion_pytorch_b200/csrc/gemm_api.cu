@@ -51,14 +51,15 @@ int tfx_gemm_store(const void* A, long long lda, int a_mn_major, const void* B, 
 }
 
 int tfx_gemm_qkvg(const void* u, long long ldu, const void* W, long long ldw, int M, int H, int D, void* q, void* k, void* v, float* gates, float* qk_inv,
-                  const float* q_gamma, const float* k_gamma, const int* rope_pos, const float* rope_cs_t, int rope_len, const int* kv_rows, void* stream) {
+                  const float* q_gamma, const float* k_gamma, const int* rope_pos, const float* rope_cs_t, int rope_len, const int* kv_rows, float* mix_pre, void* stream) {
   if (M <= 0) return 0;
+  TFX_REQUIRE(!mix_pre || H <= 16, "gemm_qkvg: the value-residual mix columns share the 32-column gate slab: heads must be <= 16 (got %d)", H);
   TFX_REQUIRE(H >= 2 && H % 2 == 0 && H <= 32, "gemm_qkvg: heads must be even and in [2, 32] (got %d)", H);
   TFX_REQUIRE(ldu % 8 == 0 && ldw % 8 == 0, "gemm_qkvg: row pitches must be multiples of 8");
   GemmParams p; memset(&p, 0, sizeof(p));
   p.M = M; p.N = 3 * H * 64 + 128; p.K = D; p.k_splits = 1; p.H = H;
   p.q = (__nv_bfloat16*)q; p.k = (__nv_bfloat16*)k; p.v = (__nv_bfloat16*)v; p.gates = gates; p.qk_inv = qk_inv;
-  p.q_gamma = q_gamma; p.k_gamma = k_gamma; p.rope_pos = rope_pos; p.rope_cs = (const float2*)rope_cs_t; p.rope_len = rope_len; p.kv_rows = kv_rows;
+  p.q_gamma = q_gamma; p.k_gamma = k_gamma; p.rope_pos = rope_pos; p.rope_cs = (const float2*)rope_cs_t; p.rope_len = rope_len; p.kv_rows = kv_rows; p.mix_pre = mix_pre;
   GemmOperand a{u, ldu, false}, b{W, ldw, false};
   // 256-wide tiles (4 heads per tile, 16 epilogue warps) whenever the head count allows it; 2 heads per 128-wide tile otherwise
   if (H % 4 == 0) return finish(launch_gemm_t<256, false, false, EPI_QKVG>(a, b, p, num_sms(), ST(stream)), "gemm_qkvg");

@@ -42,6 +42,7 @@ struct GemmParams {
   int H;                       // heads (even), head dim 64
   __nv_bfloat16 *q, *k, *v;    // [M][H*64]
   float* gates;                // [M][H]   raw gate logits
+  float* mix_pre;              // [M][H]   optional: columns [H, 2H) of the gate tile = pre-activation of the learned value-residual mix (T.py:956-960)
   float* qk_inv;               // [M][2H]  1/max(|x|,eps) for q heads then k heads
   const float *q_gamma, *k_gamma;   // [64]
   const int* rope_pos;         // [M]
@@ -490,6 +491,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float* dst = p.gates + (long long)row * p.H;
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (j < p.H) dst[j] = __uint_as_float(r[j]);
+            if (p.mix_pre) {
+              float* dm = p.mix_pre + (long long)row * p.H;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j >= p.H && j < 2 * p.H) dm[j - p.H] = __uint_as_float(r[j]);
+            }
           }
         }
       } else if constexpr (EPI == EPI_QKVG) {
@@ -561,6 +567,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float* dst = p.gates + (long long)row * p.H;
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (j < p.H) dst[j] = __uint_as_float(r[j]);
+            if (p.mix_pre) {
+              float* dm = p.mix_pre + (long long)row * p.H;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j >= p.H && j < 2 * p.H) dm[j - p.H] = __uint_as_float(r[j]);
+            }
           }
         }
       } else if constexpr (EPI == EPI_RESID) {

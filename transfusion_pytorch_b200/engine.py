@@ -19,6 +19,7 @@ fp32 accumulation.
 from __future__ import annotations
 
 import math
+import os
 import ctypes
 from dataclasses import dataclass
 
@@ -53,6 +54,8 @@ class KVCache:
         # zero-filled: rows past a slab's filled length are read by whole-tile loads (and multiplied by p = 0): they must be finite
         self.k = torch.zeros(engine.depth, self.rows, engine.HI, device = engine.device, dtype = BF16)
         self.v = torch.zeros(engine.depth, self.rows, engine.HI, device = engine.device, dtype = BF16)
+        # LASER (T.py:981-983): the cache keeps the raw values, attention reads exp(softclamp(v)) from a second slab written in place
+        self.vl = torch.zeros_like(self.v) if engine.laser else None
 
     def slab_start(self, s):
         return np.asarray(s, dtype = np.int64) * self.cap
@@ -73,6 +76,7 @@ class Engine:
         self.Kt = _round_up(self.D + 1, 64)         # padded K of the time-cond Linear
         self.W = 2 * self.depth                     # AdaptiveWrappers
         self.softcap = tr.softcap_value
+        self.laser, self.laser_clamp, self.vres = tr.attn_laser, tr.laser_softclamp_value, tr.use_value_residual
         self.scale = 64 ** -0.5
         self.dls = list(model.dim_latents)
         self.dlp = [_round_up(d, 8) for d in self.dls]
@@ -85,6 +89,7 @@ class Engine:
         self._ptr_arrays = []
         self.launches = 0
         self.graph_pins = None                      # list of retired workspace tensors once any CUDA graph has been captured
+        self.fwd_kernel = os.environ.get('TFX_ATTN_FWD', 'ts')      # 'ts' (persistent, P in TMEM) | 'tc' (round-1 kernel, kept for A/B timing)
         self.frozen = False                         # True inside a sampling session: parameters cannot change, skip the re-pack check
 
     # ------------------------------------------------------------------ parameters
@@ -175,6 +180,8 @@ class Engine:
             r[:2 * HI] = q_off + np.arange(2 * HI) * D
             r[2 * HI:3 * HI] = v_off + np.arange(HI) * D
             r[3 * HI:3 * HI + H] = g_off + np.arange(H) * D
+            if f'{pre}.1.fn.to_learned_value_residual.0.weight' in self.offs:        # value-residual mix Linear: pad rows [3HI + H, 3HI + 2H) of the packed weight
+                r[3 * HI + H:3 * HI + 2 * H] = self.offs[f'{pre}.1.fn.to_learned_value_residual.0.weight'] + np.arange(H) * D
             w2_off = self.offs[f'{pre}.2.fn.net.3.weight']
             w2_rows = torch.from_numpy(w2_off + np.arange(D, dtype = np.int64) * inner).to(dev)
             self.layer_maps.append(dict(w1_rows = w1_rows.contiguous(), b1_cols = b1_cols.contiguous(), qkvg_rows = torch.from_numpy(r).to(dev), w2_rows = w2_rows))
@@ -228,6 +235,8 @@ class Engine:
             job(self.P(f'{pre}.1.fn.to_qk.0.weight'), D, D, None, wq, 2 * HI, D)
             job(self.P(f'{pre}.1.fn.to_v.0.weight'), D, D, None, wq[2 * HI:], HI, D)
             job(self.P(f'{pre}.1.fn.to_gates.0.weight'), D, D, None, wq[3 * HI:], H, D)
+            if f'{pre}.1.fn.to_learned_value_residual.0.weight' in self.named:
+                job(self.P(f'{pre}.1.fn.to_learned_value_residual.0.weight'), D, D, None, wq[3 * HI + H:], H, D)
             job(self.P(f'{pre}.1.fn.to_out.1.weight'), HI, HI, None, dst(f'wo{i}', D, HI), D, HI)
             job(self.P(f'{pre}.2.fn.net.0.weight'), D, D, self.w1_row_src, dst(f'w1{i}', 2 * Ip, D), 2 * Ip, D)
             job(self.P(f'{pre}.2.fn.net.3.weight'), inner, inner, None, dst(f'w2{i}', D, Ip), D, Ip)
@@ -287,7 +296,7 @@ class Engine:
 
     # ------------------------------------------------------------------ descriptor upload
     META_NAMES = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
-                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order', 'kv_row']
+                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order', 'kv_row', 'p2']
 
     def stage_meta(self, rb: RaggedBatch):
         """All per-token / per-tile int32 metadata and the float metadata of a batch in ONE pooled pinned buffer.
@@ -349,7 +358,8 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, rb: RaggedBatch, latents: list | None, eps: list | None, *, train: bool, want_logits = False, vlimit = 0,
-                text_loss_weight = 1., flow_loss_weight = 1., modality_only = False, cache: KVCache | None = None, want_preds = None):
+                text_loss_weight = 1., flow_loss_weight = 1., modality_only = False, cache: KVCache | None = None, want_preds = None,
+                vel_targets = None, vel_weight = 0.):
         """Runs the block stack over a ragged batch.  `latents[t]`: fp32 [S_t, dl_t] device tensors (clean latents when
         `eps` is given, already-noised / decode-time latents otherwise).  With train=True activations are kept for
         `backward()` and the fused loss heads produce the loss scalars and the head gradients in the same pass."""
@@ -450,21 +460,39 @@ class Engine:
             if cache is not None:
                 k, v = cache.k[i], cache.v[i]
             else:
-                k = self.buf(f'{lt}k', (M, HI), BF16); v = self.buf(f'{lt}v', (M, HI), BF16)
+                # inference shares one buffer set across layers, but the value residual reads the FIRST layer's values in every later layer
+                k = self.buf(f'{lt}k', (M, HI), BF16); v = self.buf(f'{lt}v0' if (self.vres and i == 0) else f'{lt}v', (M, HI), BF16)
             gates = self.buf(f'{lt}g', (M, H), F32); qk_inv = self.buf(f'{lt}qi', (M, 2 * H), F32)
+            has_mix = self.vres and i > 0
+            mixpre = self.buf(f'{lt}mix', (M, H), F32) if has_mix else None
             o.gemm_qkvg(uA, D, pk[f'qkvg{i}'], D, M, H, D, q, k, v, gates, qk_inv, self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'),
-                        dv['rope_pos'], self.ws['rope_cs_t'], int(self.ws['rope_cs_t'].shape[1]), kv_rows)
+                        dv['rope_pos'], self.ws['rope_cs_t'], int(self.ws['rope_cs_t'].shape[1]), kv_rows, mixpre)
+            if has_mix:                                  # learned value residual (T.py:956-960): v = v mix + v_first_layer (1 - mix), in place (also on the cache rows)
+                v_first = cache.v[0] if cache is not None else st['layers'][0]['v']
+                o.vmix_fwd(v, HI, kv_rows, v_first, HI, mixpre, self.P(f'{pre}.1.fn.to_learned_value_residual.0.bias'), M, H)
+            v_att, att_gates = v, gates
+            if self.laser:                               # LASER (T.py:981-983): attention runs on exp(softclamp(v)); log + gate follow it
+                v_att = cache.vl[i] if cache is not None else self.buf(f'{lt}vl', (M, HI), BF16)
+                o.laser_v_fwd(v, HI, kv_rows, v_att, HI, M, H, self.laser_clamp)
+                att_gates = None
             att = self.buf(f'{lt}o', (M, HI), BF16); lse = self.buf(f'{lt}lse', (H, M), F32)
+            o_l = self.buf(f'{lt}ol', (M, HI), BF16) if self.laser else att
             fp = self.fastp[i]
             if getattr(rb, 'single_row_tiles', False):
                 # text decode: one query row per sample against its cache slab (split-KV decode kernel)
-                o.attn_decode(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_kv0'], dv['tile_kvend'], n_tiles, att, HI, self.scale, self.softcap)
+                o.attn_decode(q, k, v_att, HI, HI, HI, att_gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_kv0'], dv['tile_kvend'], n_tiles, o_l, HI, self.scale, self.softcap)
             else:
                 # both kernels are enqueued; the one whose precondition (read from `fp` on the device) fails returns immediately
-                o.attn_fwd_tc(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['t2_q0'], dv['t2_qend'], dv['t2_kv0'], dv['t2_kvend'], int(rb.t2_q0.shape[0]),
-                              att, HI, lse, M, M_kv, self.scale, self.softcap, fp)
-                o.attn_fwd(q, k, v, HI, HI, HI, gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_qend'], dv['tile_kv0'], dv['tile_kvend'], n_tiles,
-                           att, HI, lse, M, self.scale, self.softcap, fp)
+                if self.fwd_kernel == 'ts':      # persistent two-warpgroup forward, P in TMEM (attention_fwd_sm100.cu)
+                    o.attn_fwd_ts(q, k, v_att, HI, HI, HI, att_gates, H, dv['kv_limit'], dv['t2_q0'], dv['t2_qend'], dv['t2_kv0'], dv['t2_kvend'], int(rb.t2_q0.shape[0]),
+                                  dv['p2'], int(rb.p2.shape[0]), o_l, HI, lse, M, M_kv, self.scale, self.softcap, fp)
+                else:                            # round-1 forward: one CTA per (query tile, head), P through shared memory
+                    o.attn_fwd_tc(q, k, v_att, HI, HI, HI, att_gates, H, dv['kv_limit'], dv['t2_q0'], dv['t2_qend'], dv['t2_kv0'], dv['t2_kvend'], int(rb.t2_q0.shape[0]),
+                                  o_l, HI, lse, M, M_kv, self.scale, self.softcap, fp)
+                o.attn_fwd(q, k, v_att, HI, HI, HI, att_gates, H, dv['kv_limit'], dv['tile_q0'], dv['tile_qend'], dv['tile_kv0'], dv['tile_kvend'], n_tiles,
+                           o_l, HI, lse, M, self.scale, self.softcap, fp)
+            if self.laser:
+                o.laser_out_fwd(o_l, gates, att, M, H)
             x_b = self.buf(f'{lt}xb', (M, D), F32); yA = self.buf(f'{lt}yA', (M, D), BF16) if train else None
             o.gemm_resid(att, HI, None, 0, 0, pk[f'wo{i}'], HI, M, D, HI, None, x_a, x_b, None, yA, cond_row, zgA, zg_ld, self.P(f'{pre}.1.layerscale'))
             uF = self.buf(f'{lt}uF', (M, D), BF16); statsF = self.buf(f'{lt}sF', (M, 2), F32)
@@ -478,7 +506,7 @@ class Engine:
             xr = self.buf(f'{tag}xr{i}', (M, D), F32); xrb = self.buf(f'{tag}xrb{i}', (M, D), BF16)
             rlse = self.buf(f'{tag}rlse{i}', (M,), F32) if train else None
             o.attn_residual_fwd(self._ptr_array(hid), len(hid), self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'), xr, xrb, rlse, M, D)
-            L.update(xr = xr, rlse = rlse)
+            L.update(xr = xr, rlse = rlse, mixpre = mixpre, o_l = o_l, v_att = v_att)
             L.update(x_a = x_a, uA = uA, statsA = statsA, q = q, k = k, v = v, gates = gates, qk_inv = qk_inv, att = att, lse = lse, yA = yA, x_b = x_b,
                      uF = uF, statsF = statsF, vg = vg, h = h, yF = yF, x_in = x_in, x_in_b = x_in_b, has_skip = has_skip, first_half = first_half)
             st['layers'].append(L)
@@ -525,6 +553,7 @@ class Engine:
             st['dlogits'] = dlog
             st['dpred'] = []
             flow_terms = []
+            vel_terms = {}
             for t, (s0, s1) in enumerate(rb.type_rows):
                 n = s1 - s0
                 if n == 0 or st['flow'][t] is None:
@@ -534,7 +563,28 @@ class Engine:
                 dpred = self.buf(f'dpred{t}', (n, dlp), BF16)
                 if dlp != dl:
                     dpred[:, dl:].zero_()
-                o.mse_fwd_bwd(preds[t], dl, st['flow'][t], dpred, dlp, 2.0 * flow_loss_weight * wt / (n * dl), acc[1 + t: 2 + t], n, dl)
+                ga = 2.0 * flow_loss_weight * wt / (n * dl)
+                if vel_targets is not None and vel_targets[t] is not None and vel_weight != 0.:
+                    # velocity consistency (T.py:3383-3418): + w_v * wt * mse(pred, ema_pred).  d/dpred of a |p - f|^2 + b |p - e|^2 is
+                    # (a + b) (p - (a f + b e) / (a + b)): ONE gradient pass against the blended target; the two loss values come from two
+                    # loss-only passes (their dpred output is overwritten by the blended pass)
+                    e = vel_targets[t]
+                    assert e.shape == (n, dl) and e.dtype == F32
+                    gb = 2.0 * vel_weight * wt / (n * dl)
+                    vacc = self.buf('velacc', (len(self.dls),), torch.float64)
+                    if t == 0 or not vel_terms:
+                        vacc.zero_()
+                    o.mse_fwd_bwd(preds[t], dl, e, None, dlp, gb, vacc[t: t + 1], n, dl)
+                    o.mse_fwd_bwd(preds[t], dl, st['flow'][t], None, dlp, ga, acc[1 + t: 2 + t], n, dl)
+                    blend = self.buf(f'velblend{t}', (n, dl), F32)
+                    blend.zero_()
+                    o.axpy_f32(blend, st['flow'][t], ga / (ga + gb), n * dl)
+                    o.axpy_f32(blend, e, gb / (ga + gb), n * dl)
+                    scratch = self.buf('velscratch', (1,), torch.float64)
+                    o.mse_fwd_bwd(preds[t], dl, blend, dpred, dlp, ga + gb, scratch, n, dl)
+                    vel_terms[t] = (vacc[t] / (n * dl)).float()
+                else:
+                    o.mse_fwd_bwd(preds[t], dl, st['flow'][t], dpred, dlp, ga, acc[1 + t: 2 + t], n, dl)
                 st['dpred'].append(dpred)
                 flow_terms.append((acc[1 + t] / (n * dl)).float() )
             # loss assembly on a handful of device scalars (no host sync): transfusion.py:3331-3376
@@ -551,7 +601,10 @@ class Engine:
                 for t, f in enumerate(flow_terms):
                     if f is not None:
                         total = total + f * (rb.n_type_tokens[t] / T) * flow_loss_weight
-            res.update(loss_acc = acc, n_valid = nvalid, total = total, text = text, flows = flows)
+                for t, f in vel_terms.items():
+                    total = total + f * (rb.n_type_tokens[t] / T) * vel_weight
+            vel = [vel_terms.get(t, torch.zeros((), device = self.device)) for t in range(len(self.dls))] if vel_terms else None
+            res.update(loss_acc = acc, n_valid = nvalid, total = total, text = text, flows = flows, vel = vel)
         return res
 
     def _prepare_grads(self):
@@ -676,15 +729,32 @@ class Engine:
             wgrad(dy, D, D, L['att'], HI, HI, f'{pre}.1.fn.to_out.1.weight')
             dop = self.buf('dop', (M, HI), BF16); dsum_hm = self.buf('dsum_hm', (H, M), F32); dsum_mh = self.buf('dsum_mh', (M, H), F32)
             dq = self.buf('dq', (M, HI), F32); dk = self.buf('dk', (M, HI), F32)
-            o.attn_bwd_prep(dog, L['att'], L['gates'], dop, dsum_hm, dsum_mh, dq, M, H)
+            if self.laser:
+                o.laser_bwd_prep(dog, L['o_l'], L['gates'], dop, dsum_hm, dsum_mh, dq, M, H)
+            else:
+                o.attn_bwd_prep(dog, L['att'], L['gates'], dop, dsum_hm, dsum_mh, dq, M, H)
             dqkvg = self.buf('dqkvg', (M, self.NQ), BF16)
             if i == self.depth - 1:
                 dqkvg[:, 3 * HI + H:].zero_()   # pad columns are never written by the kernels; cleared once per backward (inside captured graphs too)
             fp = self.fastp[i]
-            o.attn_bwd_tc(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['k2_kv0'], dv['k2_kvend'], dv['k2_q0'], dv['k2_qend'],
+            o.attn_bwd_tc(L['q'], L['k'], L['v_att'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['k2_kv0'], dv['k2_kvend'], dv['k2_q0'], dv['k2_qend'],
                           dv['k2_order'], int(rb.k2_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
-            o.attn_bwd(L['q'], L['k'], L['v'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['kt_kv0'], dv['kt_kvend'], dv['kt_q0'], dv['kt_qend'],
+            o.attn_bwd(L['q'], L['k'], L['v_att'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['kt_kv0'], dv['kt_kvend'], dv['kt_q0'], dv['kt_qend'],
                        int(rb.kt_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
+            dv_cols = dqkvg[:, 2 * HI:]
+            if self.laser:                               # d v' -> d v (v' = exp(softclamp(v)))
+                o.laser_v_bwd(dv_cols, self.NQ, L['v'], HI, M, H, self.laser_clamp)
+            if self.vres:
+                dv0 = self.buf('dv_first', (M, HI), F32)
+                if i == self.depth - 1:
+                    dv0.zero_()
+                if i > 0:                                # d v_mixed -> d v_raw; the first layer's share accumulates in dv0, d mix_pre goes to the packed column block
+                    o.vmix_bwd(dv_cols, self.NQ, L['v'], HI, st['layers'][0]['v'], HI, L['mixpre'], self.P(f'{pre}.1.fn.to_learned_value_residual.0.bias'), dv0,
+                               dqkvg[:, 3 * HI + H:], self.NQ, M, H)
+                    o.colsum_bf16(dqkvg[:, 3 * HI + H:], self.NQ, M, H, None, self.G(f'{pre}.1.fn.to_learned_value_residual.0.bias'))
+                else:
+                    dqkvg[:, 3 * HI + H:3 * HI + 2 * H].zero_()      # the first layer has no mix Linear: its column block must not carry layer 1's values
+                    o.add_f32_into_bf16(dv_cols, self.NQ, dv0, HI, M, HI)
             o.qk_bwd_pack(dq, dk, L['q'], L['k'], L['qk_inv'], self.P(f'{pre}.1.fn.q_norm.gamma'), self.P(f'{pre}.1.fn.k_norm.gamma'), dv['rope_pos'],
                           self.ws['rope_cs'], L['gates'], dsum_mh, dqkvg, self.NQ, self.G(f'{pre}.1.fn.q_norm.gamma'), self.G(f'{pre}.1.fn.k_norm.gamma'), M, H)
             o.gemm_store(dqkvg, self.NQ, 0, pk[f'qkvg{i}'], D, 1, M, D, self.NQ, du, D, None, 0, None, None, 1.0, 0, 1)

@@ -90,6 +90,7 @@ class RaggedBatch:
     k2_kvend: np.ndarray = None
     k2_q0: np.ndarray = None
     k2_qend: np.ndarray = None
+    p2: np.ndarray = None                   # persistent tcgen05 forward: (first tile of a pair of adjacent 128-row query tiles) * 2 + has_second, heaviest pair first
     k2_order: np.ndarray = None             # 128-key tiles sorted by the number of query tiles that see them (persistent attention backward)
     kv_row: np.ndarray = None               # kv-cache forward only: cache row each (new) token's key / value is appended at
     single_row_tiles: bool = False          # every attention tile holds exactly one query row (text decode): use the decode kernel
@@ -128,6 +129,7 @@ def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
             for name in (f'{pre_q}_q0', f'{pre_q}_qend', f'{pre_q}_kv0', f'{pre_q}_kvend', f'{pre_k}_kv0', f'{pre_k}_kvend', f'{pre_k}_q0', f'{pre_k}_qend'):
                 setattr(rb, name, z)
             rb.k2_order = z
+            rb.p2 = z
             continue
         seq = np.repeat(np.arange(rb.B), ntiles)                         # sequence of every tile
         first = np.cumsum(ntiles) - ntiles                               # index of the first tile of each sequence
@@ -143,6 +145,13 @@ def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
             setattr(rb, name, as32(arr))
         if pre_k == 'k2':
             rb.k2_order = as32(np.argsort(-(s + lens[seq] - kq0), kind = 'stable'))
+            # forward work items: tiles (2i, 2i+1) of a sequence share their K / V stream; cost = key tiles of both
+            nkv = (kve - s + T - 1) // T
+            first_of_pair = np.nonzero(tin % 2 == 0)[0]
+            has_b = (tin[first_of_pair] + 1) < ntiles[seq[first_of_pair]]
+            cost = nkv[first_of_pair] + np.where(has_b, nkv[np.minimum(first_of_pair + 1, total - 1)], 0)
+            order = np.argsort(-cost, kind = 'stable')
+            rb.p2 = as32(first_of_pair[order] * 2 + has_b[order])
 
 
 def pack_batch(

@@ -135,9 +135,11 @@ class _Fourier(Module):
 
 
 class _AttentionParams(Module):
-    def __init__(self, dim, dim_head, heads):
+    def __init__(self, dim, dim_head, heads, learned_value_residual_mix = False):
         super().__init__()
         inner = dim_head * heads
+        if learned_value_residual_mix:           # T.py:894-898 (layers after the first, `use_value_residual`)
+            self.to_learned_value_residual = nn.Sequential(nn.Linear(dim, heads), nn.Sigmoid())
         self.to_qk = nn.Sequential(nn.Linear(dim, inner * 2, bias = False))
         self.q_norm, self.k_norm = _Gamma(dim_head), _Gamma(dim_head)
         self.to_v = nn.Sequential(nn.Linear(dim, inner, bias = False))
@@ -191,17 +193,18 @@ class Transformer(Module):
         unsupported = []
         if dim_head != 64: unsupported.append('dim_head != 64')
         if dropout != 0.: unsupported.append('dropout > 0')
-        if attn_laser: unsupported.append('attn_laser')
-        if use_value_residual: unsupported.append('use_value_residual')
+        if use_value_residual and heads > 16: unsupported.append('use_value_residual with heads > 16')
         if not qk_rmsnorm: unsupported.append('qk_rmsnorm = False')
-        extra = set(attn_kwargs) - {'softcap_value'}
+        extra = set(attn_kwargs) - {'softcap_value', 'laser_softclamp_value'}
         if extra: unsupported.append(f'attn_kwargs {sorted(extra)}')
         if ff_kwargs: unsupported.append(f'ff_kwargs {sorted(ff_kwargs)}')
         if unsupported:
             raise NotImplementedError('not implemented by the B200 kernels: ' + ', '.join(unsupported))
         self.dim, self.depth, self.dim_head, self.heads = dim, depth, dim_head, heads
         self.use_flex_attn = use_flex_attn           # accepted: the fused kernel IS the span-aware attention
-        self.use_value_residual = False
+        self.use_value_residual = bool(use_value_residual)
+        self.attn_laser = bool(attn_laser)
+        self.laser_softclamp_value = float(attn_kwargs.get('laser_softclamp_value', 15.))
         self.softcap_value = float(attn_kwargs.get('softcap_value', 50.))
         self.ff_inner = int(dim * ff_expansion_factor * 2 / 3)
 
@@ -209,7 +212,7 @@ class Transformer(Module):
         layers = ModuleList([])
         for ind in range(depth):
             skip_proj = nn.Linear(dim * 2, dim, bias = False) if (ind >= depth / 2 and unet_skips) else None
-            attn = _AdaptiveParams(_AttentionParams(dim, dim_head, heads), dim, dim * 4)
+            attn = _AdaptiveParams(_AttentionParams(dim, dim_head, heads, learned_value_residual_mix = ind > 0 and use_value_residual), dim, dim * 4)
             ff = _AdaptiveParams(_FeedForwardParams(dim, self.ff_inner), dim, dim * 4)
             layers.append(ModuleList([skip_proj, attn, ff, _AttnResidualParams(dim)]))
         self.layers = layers
@@ -228,6 +231,7 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, engine, rb, latents, eps, kw, anchor):
         res = engine.forward(rb, latents, eps, train = True, **kw)
         ctx.engine = engine
+        engine._last_vel = res.get('vel')
         return res['total'], res['text'], res['flows']
 
     @staticmethod
@@ -365,7 +369,9 @@ class Transfusion(SamplingMixin, Module):
         return create_dataloader(*args, **kwargs)
 
     def create_ema(self, beta = 0.99, *ema_kwargs):
-        raise NotImplementedError('EMA is outside the B200 hot path (SURVEY.md section 2, row 21)')
+        """T.py:1681-1699.  The copy's parameters live in a second flat buffer; `ema.update()` is one `tfx_ema_update` launch."""
+        from .ema import EMA
+        return EMA(self, beta = beta, forward_method_names = ('sample', 'sample_one', 'sample_many', 'generate_text_only', 'generate_modality_only'))
 
     @property
     def engine(self):
@@ -446,7 +452,7 @@ class Transfusion(SamplingMixin, Module):
         if train and torch.is_grad_enabled():
             anchor = self.text_embed.weight
             total, text, flows = _TrainStep.apply(eng, rb, latents, eps, kw, anchor)
-            return dict(total = total, text = text, flows = flows)
+            return dict(total = total, text = text, flows = flows, vel = eng._last_vel)
         return eng.forward(rb, latents, eps, train = train, **kw)
 
     def forward_packed(self, rb: RaggedBatch, latents: list, noise: list | None = None, return_breakdown = False):
@@ -487,7 +493,8 @@ class Transfusion(SamplingMixin, Module):
                                   cap = kv.cache.cap)
             res = eng.forward(rb, None, None, train = False, want_logits = True, cache = kv.cache)
             kv.length += n
-        out = res['embed'].reshape(B, n, -1) if return_embed else res['logits'][:, :V].reshape(B, n, -1)
+        # fresh tensors: the engine's result buffers are workspaces that the next call overwrites (callers keep logits across decode steps)
+        out = res['embed'].reshape(B, n, -1).clone() if return_embed else res['logits'][:, :V].reshape(B, n, -1).clone()
         ret = (out,)
         if return_kv_cache:
             ret = (*ret, (kv, tokens_seen + n))
@@ -640,9 +647,8 @@ class Transfusion(SamplingMixin, Module):
         return_times = False,
         prob_uncond = None,
         noise = None,            # extension: list (per type) of [S_t, dim_latent] noise for deterministic parity runs
+        velocity_consistency_noise = None,      # extension: same, for the EMA teacher's own draw (T.py:3388-3392 draws it with randn_like)
     ):
-        assert not exists(velocity_consistency_ema_model), 'velocity consistency is outside the B200 hot path'
-        assert not return_only_pred_flows, 'return_only_pred_flows is not provided by the fused engine'
         is_decoding = exists(decoding_text_or_modality)
         if is_int_tensor(modalities):
             return self.forward_text(modalities, return_loss = return_loss and not return_embed, return_embed = return_embed, cache = cache,
@@ -653,6 +659,27 @@ class Transfusion(SamplingMixin, Module):
         return_loss = return_loss and not (return_embed or is_decoding)
         assert not exists(cache) and not return_kv_cache, 'interleaved decoding against the kv cache is driven by sample() / sample_many() (engine.KVCache); `forward_text` takes / returns a cache'
 
+        # ---- velocity consistency (T.py:2965-2971, 3003-3008, 3084-3088, 3383-3418): the EMA model predicts the flow at t + delta from its own
+        # noise draw; the student is trained at t (1 - delta) and pulled towards that prediction
+        ema = velocity_consistency_ema_model
+        if exists(ema) and hasattr(ema, 'ema_model'):
+            assert isinstance(ema.ema_model, Transfusion)
+            if hasattr(ema, '_engines'):
+                ema._engines()
+            ema = ema.ema_model
+        need_velocity = not is_decoding and exists(ema)
+        vel_targets = None
+        if need_velocity:
+            assert return_loss, 'velocity consistency is a training loss'
+            velocity_modalities = [list(m) if isinstance(m, list) else m for m in modalities]
+            if times is None:
+                n_mods = tensor([sum(1 for part in m if isinstance(part, tuple) or (is_tensor(part) and part.is_floating_point())) for m in modalities])
+                times = default(num_modalities_to_times_fn, default_modality_length_to_time_fn)(n_mods)
+            orig_times = times.clone()
+            times = times * (1. - velocity_consistency_delta_time)
+            with torch.no_grad():
+                ema.eval()
+                vel_targets = ema(velocity_modalities, times = orig_times + velocity_consistency_delta_time, return_only_pred_flows = '_compact', noise = velocity_consistency_noise)
 
         rb, times = self.pack(modalities, times = times, num_modalities_to_times_fn = num_modalities_to_times_fn, prob_uncond = prob_uncond,
                               return_loss = return_loss, return_embed = return_embed, is_decoding = is_decoding)
@@ -662,7 +689,20 @@ class Transfusion(SamplingMixin, Module):
                 eps = [n.reshape(-1, self.dim_latents[t]).float().to(self.device) if exists(n) else None for t, n in enumerate(noise)]
             else:
                 eps = [torch.randn_like(l) if exists(l) else None for l in lat]
-            res = self._run(rb, lat, eps, train = True, text_loss_weight = self.text_loss_weight, flow_loss_weight = self.flow_loss_weight)
+            if return_only_pred_flows:
+                # early return used by the velocity-consistency teacher (T.py:3313-3316): noise inject + block stack + flow head, no loss
+                res = self.engine.forward(rb, lat, eps, train = False, want_logits = False, want_preds = True)
+                self._last_batch = rb
+                compact = [p.clone() if exists(p) else None for p in res.get('preds', [None] * self.num_modalities)]
+                if return_only_pred_flows == '_compact':
+                    return compact
+                out = [[] for _ in range(self.num_modalities)]
+                for inst in rb.instances:                 # per type, per instance, in scan order (the reference's `pred_flows` layout)
+                    t = inst.modality_type
+                    out[t].append(compact[t][inst.row0: inst.row0 + inst.length])
+                return out
+            kw = dict(vel_targets = vel_targets, vel_weight = self.velocity_consistency_loss_weight) if need_velocity else {}
+            res = self._run(rb, lat, eps, train = True, text_loss_weight = self.text_loss_weight, flow_loss_weight = self.flow_loss_weight, **kw)
             total = res['total']
             self._last_batch = rb
             if not return_breakdown and not return_hiddens and not return_times:
@@ -670,7 +710,8 @@ class Transfusion(SamplingMixin, Module):
             ret = (total,)
             if return_breakdown:
                 flows = [res['flows'][t] for t in range(self.num_modalities) if rb.type_rows[t][1] > rb.type_rows[t][0]]
-                ret = (*ret, LossBreakdown(total, res['text'], flows, None, [[] for _ in range(self.num_modalities)]))
+                vel = [res['vel'][t] for t in range(self.num_modalities) if rb.type_rows[t][1] > rb.type_rows[t][0]] if need_velocity else None
+                ret = (*ret, LossBreakdown(total, res['text'], flows, vel, [[] for _ in range(self.num_modalities)]))
             if return_hiddens:
                 ret = (*ret, self._hiddens_padded(rb))
             if return_times:

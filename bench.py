@@ -166,7 +166,7 @@ def family_model(name, args_, eng, rb):
         return 'attention', 4.0 * pairs * 64 * H, 8.0 * M * HI
     if name == 'attn_fwd':
         return 'attention', 0, 0          # general kernel: returns at once when the tcgen05 path is active (flops credited to attn_fwd_tc)
-    if name == 'attn_bwd_tc':
+    if name in ('attn_bwd_tc', 'attn_bwd_ts'):
         return 'attention', 10.0 * pairs * 64 * H, 8.0 * M * HI + 8.0 * M * HI + 2.0 * M * HI      # q k v dO in; dq dk fp32 + dv bf16 out
     if name == 'attn_bwd':
         return 'attention', 0, 0

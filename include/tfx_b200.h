@@ -95,6 +95,13 @@ int tfx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* do_
                     const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
                     const int* kt_order /* optional: key-tile indices, most query tiles first (load balance of the persistent grid) */,
                     int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* fast_params, void* stream);
+/* Same contract as tfx_attn_bwd_tc, transposed-score formulation (attention_bwd_sm100.cu): S^T = K Q^T and dP^T = V dO^T put the keys on the TMEM lanes, so
+ * P^T and dS^T are written back to TMEM (tcgen05.st) and feed dV += P^T dO, dK += dS^T Q as TS-form tcgen05.mma; only dS^T also goes to shared memory (A operand
+ * of dQ = dS K); Q / dO arrive through a 3-stage TMA ring. */
+int tfx_attn_bwd_ts(const void* q, const void* k, const void* v, const void* do_pre, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
+                    const float* lse, const float* dsum_hm, const int* kv_limit, const int* kt_kv0, const int* kt_kvend, const int* kt_q0, const int* kt_qend,
+                    const int* kt_order, int n_kv_tiles, float* dq, float* dk, void* dv, long long ld_dv, int M, int H, float scale, float softcap, const float* fast_params,
+                    void* stream);
 /* backward of the qk-RMSNorm + RoPE epilogue; packs d[q | k | (v written by attn_bwd) | gates] bf16 [M][out_ld] */
 int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const void* k_bf16, const float* qk_inv, const float* q_gamma, const float* k_gamma,
                     const int* rope_pos, const float* rope_cs, const float* gates, const float* dsum_mh, void* dqkvg_bf16, long long out_ld,
@@ -140,6 +147,10 @@ int tfx_rmsnorm_bwd(const float* dout, const float* x, const float* gamma, float
 /* token assemble: where(is_modality, modality_token, text_embed[id]) (T.py:3173-3184) and its backward */
 int tfx_embed_assemble(const int* text_id, const float* emb, const float* modtok, const int* slot, float* x0, void* x0_bf16, int M, int D, void* stream);
 int tfx_embed_bwd(const float* dx0, const int* text_id, const int* slot, float* demb, void* dmodtok_bf16, int M, int D, void* stream);
+/* model_output_clean (MP.py:100-126, 790-793; T.py:2454-2455): omod[s] = (out[row_token[s]] - modtok[s]) / max(1 - t, eps), t = cond_times[cond_row[token]];
+ * backward: dmod *= 1 / max(1 - t, eps) in place (then scattered into d out), dmodtok_neg = -dmod (added to the modality-token gradient) */
+int tfx_clean_flow_fwd(const float* out, const int* row_token, const float* modtok, const float* cond_times, const int* cond_row, float eps, void* omod_bf16, int S, int D, void* stream);
+int tfx_clean_flow_bwd(float* dmod_inout, float* dmodtok_neg, const int* row_token, const float* cond_times, const int* cond_row, float eps, int S, int D, void* stream);
 int tfx_scatter_add_rows(float* dst, const float* src, const int* row_map, int S, int D, void* stream);
 
 /* ---------------------------------------------------------------- elementwise / reductions

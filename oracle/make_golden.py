@@ -303,6 +303,10 @@ def main():
         batch = synth.small_batch(3, seed = 1, dim_latent = 32, text_vocab = 64)
         times = torch.rand(3, count_modalities(batch), generator = torch.Generator().manual_seed(5))
         run_interleaved(ref, 'small_laser_vres', ctor, batch, times, seed = 1)
+        # model_output_clean (MP.py:100-126): the model predicts the clean modality in model space; times pushed towards 1 so that the eps clamp is exercised
+        ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), model_output_clean = True, transformer = dict(dim = 128, depth = 2, heads = 2))
+        times = (torch.rand(3, count_modalities(batch), generator = torch.Generator().manual_seed(7)) * 1.2).clamp(max = 0.999)
+        run_interleaved(ref, 'small_clean', ctor, batch, times, seed = 1)
     if only:
         return
 

@@ -198,6 +198,19 @@ def test_pack_is_the_host_half_of_forward_and_tile_tables_cover_the_mask():
         assert ke - k0 <= 128 and q0 <= first and (q0 - rb.cu[b]) % 128 == 0 and qe == rb.cu[b + 1]
     work = (rb.k2_qend - rb.k2_q0)[rb.k2_order]
     assert sorted(rb.k2_order.tolist()) == list(range(len(rb.k2_kv0))) and (np.diff(work) <= 0).all()
+    # forward work items of the persistent kernel: pairs of adjacent 128-row tiles of ONE sequence, every tile exactly once, heaviest pair first
+    first, has_b = rb.p2 >> 1, rb.p2 & 1
+    covered = sorted(first.tolist() + (first[has_b == 1] + 1).tolist())
+    assert covered == list(range(len(rb.t2_q0)))
+    for a, hb in zip(first, has_b):
+        assert (rb.t2_q0[a] - rb.cu[seq_of[rb.t2_q0[a]]]) % 256 == 0
+        if hb:
+            assert seq_of[rb.t2_q0[a + 1]] == seq_of[rb.t2_q0[a]] and rb.t2_kv0[a + 1] == rb.t2_kv0[a] and rb.t2_q0[a + 1] == rb.t2_q0[a] + 128
+        else:
+            assert a + 1 == len(rb.t2_q0) or seq_of[rb.t2_q0[a + 1]] != seq_of[rb.t2_q0[a]]
+    nkv = lambda t: (rb.t2_kvend[t] - rb.t2_kv0[t] + 127) // 128
+    cost = np.array([nkv(a) + (nkv(a + 1) if hb else 0) for a, hb in zip(first, has_b)])
+    assert (np.diff(cost) <= 0).all()
 
 
 def test_step_graph_signature_ignores_data_but_not_shape():

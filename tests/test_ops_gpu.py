@@ -109,7 +109,7 @@ def test_attention_forward_backward_vs_dense(ops, lens, spans):
 
 
 @pytest.mark.parametrize('lens,spans', [([1024, 1024], [(0, 206, 256), (0, 668, 256), (1, 100, 700)]), ([77, 130, 5, 300], [(0, 10, 40), (1, 64, 64), (1, 128, 2), (3, 120, 150)]), ([64], []),
-                                        ([128, 129, 127], [(1, 0, 129)])])
+                                        ([128, 129, 127], [(1, 0, 129)]), ([640] * 6 + [385, 1000, 257], [(b, 100, 300) for b in range(6)] + [(7, 100, 800)])])
 def test_attention_tcgen05_fast_path_vs_dense(ops, lens, spans):
     """bounded-logit tcgen05 forward (attention_sm100.cu): RMS-normalised q/k as the QKVG epilogue produces them"""
     H, cap, scale = 4, 50., 0.125
@@ -157,8 +157,15 @@ def test_attention_tcgen05_fast_path_vs_dense(ops, lens, spans):
     dq2 = torch.zeros(M, H * 64, device = 'cuda'); dk2 = torch.zeros(M, H * 64, device = 'cuda'); dv2 = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
     ops.attn_bwd(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.kt_kv0), dev(rb.kt_kvend), dev(rb.kt_q0), dev(rb.kt_qend), len(rb.kt_kv0), dq2, dk2, dv2, H * 64,
                  M, H, scale, cap, None)
+    # transposed-score kernel (attention_bwd_sm100.cu): same contract, P^T / dS^T as TMEM operands
+    dq3 = torch.zeros(M, H * 64, device = 'cuda'); dk3 = torch.full((M, H * 64), 3., device = 'cuda'); dv3 = torch.zeros(M, H * 64, device = 'cuda', dtype = BF16)
+    for _ in range(2):                              # twice: relaunch on dirty outputs (dq accumulates and is cleared by the caller, dk / dv are overwritten)
+        dq3.zero_()
+        ops.attn_bwd_ts(q, k, v, dop, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, dev(rb.k2_kv0), dev(rb.k2_kvend), dev(rb.k2_q0), dev(rb.k2_qend), dev(rb.k2_order), len(rb.k2_kv0), dq3, dk3, dv3,
+                        H * 64, M, H, scale, cap, fp)
     torch.cuda.synchronize()
-    for ours, gen, want, name in ((dq, dq2, qf.grad, 'dq'), (dk, dk2, kf.grad, 'dk'), (dv.float(), dv2.float(), vf.grad, 'dv')):
+    for ours, gen, want, name in ((dq, dq2, qf.grad, 'dq'), (dk, dk2, kf.grad, 'dk'), (dv.float(), dv2.float(), vf.grad, 'dv'),
+                                  (dq3, dq2, qf.grad, 'dq_ts'), (dk3, dk2, kf.grad, 'dk_ts'), (dv3.float(), dv2.float(), vf.grad, 'dv_ts')):
         err = (ours - want).abs().max().item() / want.abs().max().item()
         err2 = (ours - gen).abs().max().item() / want.abs().max().item()
         assert err < 4e-2 and err2 < 4e-2, (name, err, err2)

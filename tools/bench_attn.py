@@ -34,11 +34,12 @@ def main():
     p2 = dev(rb.p2)
     def fwd(): ops.attn_fwd_tc(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, *t2, len(rb.t2_q0), o, H * 64, lse, M, 0, scale, cap, fp)
     def fwd_ts(): ops.attn_fwd_ts(q, k, v, H * 64, H * 64, H * 64, gates, H, kvl, *t2, len(rb.t2_q0), p2, len(rb.p2), o, H * 64, lse, M, 0, scale, cap, fp)
+    def bwd_ts(): ops.attn_bwd_ts(q, k, v, do, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, *k2, len(rb.k2_kv0), dq, dk, dv, H * 64, M, H, scale, cap, fp)
     def bwd(): ops.attn_bwd_tc(q, k, v, do, H * 64, H * 64, H * 64, H * 64, lse, dsum, kvl, *k2, len(rb.k2_kv0), dq, dk, dv, H * 64, M, H, scale, cap, fp)
     big = torch.empty(256 << 20, dtype = torch.uint8, device = 'cuda')
     pairs = float((rb.kv_limit.astype('int64') - rb.cu[:-1].repeat(rb.seq_lens) + 1).sum())
-    flops = dict(fwd = 4.0 * pairs * 64 * H, fwd_ts = 4.0 * pairs * 64 * H, bwd = 10.0 * pairs * 64 * H)
-    for name, fn in (('fwd', fwd), ('fwd_ts', fwd_ts), ('bwd', bwd)):
+    flops = dict(fwd = 4.0 * pairs * 64 * H, fwd_ts = 4.0 * pairs * 64 * H, bwd = 10.0 * pairs * 64 * H, bwd_ts = 10.0 * pairs * 64 * H)
+    for name, fn in (('fwd', fwd), ('fwd_ts', fwd_ts), ('bwd', bwd), ('bwd_ts', bwd_ts)):
         for _ in range(3): fn()
         ts = []
         for _ in range(10):

@@ -30,6 +30,7 @@ SIGNATURES = {
     'tfx_attn_bwd_prep': [VP, VP, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_attn_bwd': [VP, VP, VP, VP, LL, LL, LL, LL, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP, LL, I, I, F, F, VP, VP],
     'tfx_attn_bwd_tc': [VP, VP, VP, VP, LL, LL, LL, LL, VP, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP, LL, I, I, F, F, VP, VP],
+    'tfx_attn_bwd_ts': [VP, VP, VP, VP, LL, LL, LL, LL, VP, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP, LL, I, I, F, F, VP, VP],
     'tfx_qk_bwd_pack': [VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, LL, VP, VP, I, I, VP],
     'tfx_adaln_fwd': [VP, VP, VP, LL, VP, VP, VP, I, I, VP],
     'tfx_adaln_bwd': [VP, VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, I, I, VP],
@@ -64,6 +65,8 @@ SIGNATURES = {
     'tfx_ode_pre': [VP, VP, VP, LL, I, VP, VP, VP, I, VP],
     'tfx_ode_post': [VP, VP, VP, VP, F, LL, VP, VP, VP],
     'tfx_counter_inc': [VP, VP],
+    'tfx_clean_flow_fwd': [VP, VP, VP, VP, VP, F, VP, I, I, VP],
+    'tfx_clean_flow_bwd': [VP, VP, VP, VP, VP, F, I, I, VP],
     'tfx_laser_v_fwd': [VP, LL, VP, VP, LL, I, I, F, VP],
     'tfx_laser_out_fwd': [VP, VP, VP, I, I, VP],
     'tfx_laser_bwd_prep': [VP, VP, VP, VP, VP, VP, VP, I, I, VP],

@@ -81,6 +81,7 @@ struct F2Cur {
   bool ok;
 };
 
+// 10 warps are allocated as 12 (warp allocation granularity 4): 65536 / 384 = 170 registers per thread is the real ceiling, not 204
 __global__ void __launch_bounds__(F2_THREADS, 1)
 attn_fwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
               const float* __restrict__ gates, int H, const int* __restrict__ kv_limit, const int* __restrict__ t_q0, const int* __restrict__ t_qend,

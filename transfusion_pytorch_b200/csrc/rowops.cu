@@ -446,6 +446,50 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_add_rows_k(float* __restr
   }
 }
 
+// model_output_clean (MP.py:100-126, 790-793; T.py:2454-2455): the transformer predicts the clean modality in MODEL space, the flow is
+//   (embed - noised_model_tokens) / max(1 - t, eps)   before model_to_latent.  Compact modality rows: omod[s] = (out[row_token[s]] - modtok[s]) * inv(t).
+// t of a row = cond_times[cond_row[token]] (device-resident: the ODE loop rewrites cond_times in place).
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) clean_flow_fwd_k(const float* __restrict__ out, const int* __restrict__ row_token, const float* __restrict__ modtok,
+                                                               const float* __restrict__ cond_times, const int* __restrict__ cond_row, float eps, __nv_bfloat16* __restrict__ omod, int S) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = warp0; s < S; s += nwarps) {
+    const int r = row_token[s];
+    float a[NCH * 4], b[NCH * 4];
+    if (r < 0) {
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) a[i] = 0.f;
+    } else {
+      const float inv = 1.f / fmaxf(1.f - cond_times[cond_row[r]], eps);
+      load_row_f32<NCH>(out + (long long)r * D, lane, a);
+      load_row_f32<NCH>(modtok + (long long)s * D, lane, b);
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) a[i] = (a[i] - b[i]) * inv;
+    }
+    store_row_bf16<NCH>(omod + (long long)s * D, lane, a);
+  }
+}
+// backward: d(out rows) = dmod * inv (in place, scattered by the caller), d(modtok) = -dmod * inv
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS) clean_flow_bwd_k(float* __restrict__ dmod, float* __restrict__ dneg, const int* __restrict__ row_token, const float* __restrict__ cond_times,
+                                                               const int* __restrict__ cond_row, float eps, int S) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = warp0; s < S; s += nwarps) {
+    const int r = row_token[s];
+    float a[NCH * 4], b[NCH * 4];
+    const float inv = r < 0 ? 0.f : 1.f / fmaxf(1.f - cond_times[cond_row[r]], eps);
+    load_row_f32<NCH>(dmod + (long long)s * D, lane, a);
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) { a[i] *= inv; b[i] = -a[i]; }
+    store_row_f32<NCH>(dmod + (long long)s * D, lane, a);
+    store_row_f32<NCH>(dneg + (long long)s * D, lane, b);
+  }
+}
+
 // ------------------------------------------------------------------------------------ qk RMSNorm + RoPE backward, packs d[q|k|.|gates]
 // forward (GEMM epilogue): xhat = x*inv;  y = xhat*8*(gamma+1);  q = R(pos) y (interleaved pairs)   (T.py:950-965)
 // One warp per token; 8 lanes share a head (lane owns 8 consecutive dims = 4 rope pairs: 32 B fp32 / 16 B bf16 accesses),
@@ -647,6 +691,18 @@ int tfx_scatter_add_rows(float* dst, const float* src, const int* row_map, int S
   if (S <= 0) return 0;
   TFX_DISPATCH_NCH(D, (scatter_add_rows_k<NCH><<<row_grid(S, num_sms()), ROW_THREADS, 0, ST(stream)>>>(dst, src, row_map, S)));
   return check_launch("scatter_add_rows");
+}
+
+int tfx_clean_flow_fwd(const float* out, const int* row_token, const float* modtok, const float* cond_times, const int* cond_row, float eps, void* omod_bf16, int S, int D, void* stream) {
+  if (S <= 0) return 0;
+  TFX_DISPATCH_NCH(D, (clean_flow_fwd_k<NCH><<<row_grid(S, num_sms()), ROW_THREADS, 0, ST(stream)>>>(out, row_token, modtok, cond_times, cond_row, eps, (__nv_bfloat16*)omod_bf16, S)));
+  return check_launch("clean_flow_fwd");
+}
+
+int tfx_clean_flow_bwd(float* dmod_inout, float* dmodtok_neg, const int* row_token, const float* cond_times, const int* cond_row, float eps, int S, int D, void* stream) {
+  if (S <= 0) return 0;
+  TFX_DISPATCH_NCH(D, (clean_flow_bwd_k<NCH><<<row_grid(S, num_sms()), ROW_THREADS, 0, ST(stream)>>>(dmod_inout, dmodtok_neg, row_token, cond_times, cond_row, eps, S)));
+  return check_launch("clean_flow_bwd");
 }
 
 int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const void* k_bf16, const float* qk_inv, const float* q_gamma, const float* k_gamma,

@@ -77,6 +77,7 @@ class Engine:
         self.W = 2 * self.depth                     # AdaptiveWrappers
         self.softcap = tr.softcap_value
         self.laser, self.laser_clamp, self.vres = tr.attn_laser, tr.laser_softclamp_value, tr.use_value_residual
+        self.clean, self.clean_eps = bool(getattr(model, 'model_output_clean', False)), float(getattr(model, 'eps', 1e-2))
         self.scale = 64 ** -0.5
         self.dls = list(model.dim_latents)
         self.dlp = [_round_up(d, 8) for d in self.dls]
@@ -89,6 +90,7 @@ class Engine:
         self._ptr_arrays = []
         self.launches = 0
         self.graph_pins = None                      # list of retired workspace tensors once any CUDA graph has been captured
+        self.bwd_kernel = os.environ.get('TFX_ATTN_BWD', 'ts')      # 'ts' (transposed scores, P^T / dS^T in TMEM) | 'tc' (round-1 kernel)
         self.fwd_kernel = os.environ.get('TFX_ATTN_FWD', 'ts')      # 'ts' (persistent, P in TMEM) | 'tc' (round-1 kernel, kept for A/B timing)
         self.frozen = False                         # True inside a sampling session: parameters cannot change, skip the re-pack check
 
@@ -519,6 +521,8 @@ class Engine:
         outb = self.buf(f'{tag}outb', (M, D), BF16)
         omod = self.buf(f'{tag}omod', (max(S, 1), D), BF16)
         o.rmsnorm_fwd(x_in, self.P('transformer.norm.gamma'), out, outb, dv['slot'] if S > 0 else None, omod if S > 0 else None, M, D)
+        if self.clean and S > 0:                        # model predicts the clean modality in model space (MP.py:100-126): flow = (embed - noised tokens) / max(1 - t, eps)
+            o.clean_flow_fwd(out, dv['row_token'], modtok, dv['cond_times'], dv['cond_row'], self.clean_eps, omod, S, D)
         st.update(out = out, outb = outb, omod = omod)
         res = dict(embed = out)
 
@@ -682,6 +686,10 @@ class Engine:
                 dl, dlp = self.dls[t], self.dlp[t]
                 o.gemm_store(dp, dlp, 0, pk[f'wm2l{t}'], D, 1, n, D, dl, dmod[s0:s1], D, None, 0, None, None, 1.0, 0, 1)
                 wgrad(dp, dlp, dl, st['omod'][s0:s1], D, D, f'model_to_latent_projs.{t}.weight', K = n)
+            dneg = None
+            if any_flow and self.clean:
+                dneg = self.buf('dmod_neg', (S, D), F32)
+                o.clean_flow_bwd(dmod, dneg, dv['row_token'], dv['cond_times'], dv['cond_row'], self.clean_eps, S, D)
             if any_flow:
                 o.scatter_add_rows(d_out, dmod, dv['row_token'], S, D)
         g = self.buf('gx', (M, D), F32)
@@ -737,7 +745,7 @@ class Engine:
             if i == self.depth - 1:
                 dqkvg[:, 3 * HI + H:].zero_()   # pad columns are never written by the kernels; cleared once per backward (inside captured graphs too)
             fp = self.fastp[i]
-            o.attn_bwd_tc(L['q'], L['k'], L['v_att'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['k2_kv0'], dv['k2_kvend'], dv['k2_q0'], dv['k2_qend'],
+            (o.attn_bwd_ts if self.bwd_kernel == 'ts' else o.attn_bwd_tc)(L['q'], L['k'], L['v_att'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['k2_kv0'], dv['k2_kvend'], dv['k2_q0'], dv['k2_qend'],
                           dv['k2_order'], int(rb.k2_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
             o.attn_bwd(L['q'], L['k'], L['v_att'], dop, HI, HI, HI, HI, L['lse'], dsum_hm, dv['kv_limit'], dv['kt_kv0'], dv['kt_kvend'], dv['kt_q0'], dv['kt_qend'],
                        int(rb.kt_kv0.shape[0]), dq, dk, dqkvg[:, 2 * HI:], self.NQ, M, H, self.scale, self.softcap, fp)
@@ -783,6 +791,8 @@ class Engine:
         dmodtok = self.buf('dmodtok', (max(S, 1), D), BF16)
         o.embed_bwd(g, dv['text_id'], dv['slot'] if S > 0 else None, self.G('text_embed.weight'), dmodtok if S > 0 else None, M, D)
         if S > 0:
+            if self.clean and dneg is not None:           # the clean-prediction flow also depends on the (projected) noised tokens
+                o.add_f32_into_bf16(dmodtok, D, dneg, D, S, D)
             for t, (s0, s1) in enumerate(rb.type_rows):
                 n = s1 - s0
                 if n == 0 or f'latent_to_model_projs.{t}.weight' not in self.named:

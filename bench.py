@@ -474,6 +474,12 @@ def run_sample_many(args):
         times_ms.append((1e3 * (time.perf_counter() - t0), e0.elapsed_time(e1)))
     sampler.stop_flag = True
     launches = (eng.ops.launches - l0) // args.steps
+    # one more (untimed) call with CUDA events around every text loop / modality round: where the wall time goes
+    model._sampling_timer = {}
+    model.sample_many(copy.deepcopy(prompts), **kw)
+    torch.cuda.synchronize()
+    phases = {k: dict(calls = len(v), ms = round(sum(a.elapsed_time(b) for a, b in v), 2)) for k, v in model._sampling_timer.items()}
+    model._sampling_timer = None
     wall_ms = sorted(t[0] for t in times_ms)[len(times_ms) // 2]
     # generated tokens: the 256 modality positions + every sampled text token of every sample
     prep = [model.prepare_prompt_sample(copy.deepcopy(p), kw['force_modality_at_start'])[0] for p in prompts]
@@ -500,7 +506,7 @@ def run_sample_many(args):
                 e2e = dict(value = n_gen / (wall_ms / 1e3), unit = 'tokens/s', wall_ms = wall_ms, device_ms = sorted(t[1] for t in times_ms)[len(times_ms) // 2],
                            h2d_bytes_per_step = int(sum(p[1].numel() * 4 for pr in prompts for p in ([pr] if isinstance(pr, tuple) else (pr if isinstance(pr, list) else [])) if isinstance(p, tuple)) + noise.numel() * 4),
                            d2h_bytes_per_step = int(n_prompts * Lm * 384 * 4 + 4 * sum(text_tokens))),
-                gpu_launches = int(launches), generated = dict(total = n_gen, text = int(sum(text_tokens)), latent_positions = n_prompts * Lm),
+                phases_ms = phases, gpu_launches = int(launches), generated = dict(total = n_gen, text = int(sum(text_tokens)), latent_positions = n_prompts * Lm),
                 transformer_token_forwards = dict(kv_cache = int(cached), prefix_recompute = int(recompute), saving = round(recompute / cached, 1)),
                 roofline = dict(bound = 'hbm', kernel = 'attn_decode (text loop, kv read)', achieved = None, peak = pk['hbm'], unit = 'GB/s', frac = None,
                                 traffic = None, kv_bytes_text_loop = int(kv_bytes), note = 'the text loop is launch / latency bound at 32 samples: see text_loop_ms'),

@@ -15,7 +15,8 @@
 //
 //   warp 0   : TMA producer (K | V per item - K double-buffered, V single; Q | dO per step, ring of 3)
 //   warp 1   : tcgen05.mma issuer + TMEM owner
-//   warps 2-9: softmax / gradient warps; warp = (TMEM lane quadrant = 32 keys, query-column half)
+//   warps 4-19: softmax / gradient warps; warp = (TMEM lane quadrant = 32 keys, query-column quarter = 32 queries): 4 warps per scheduler hide the
+//              TMEM-load / MUFU / barrier latencies that left the 8-warp version at 0.32 IPC
 //   TMEM: S^T [0,128) | dP^T [128,256) (dS^T bf16 written back over each warp's own columns) | dV [256,320) | dK [320,384) | dQ [384,448) | P^T bf16 [448,512)
 #include "sm100_ptx.cuh"
 #include "common.cuh"
@@ -27,11 +28,11 @@ namespace tfx {
 
 int num_sms();
 
-constexpr int B2_THREADS = 320;
+constexpr int B2_THREADS = 640;                     // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4..19 softmax / gradient (65536 / 640 -> 96 registers)
 constexpr int B2_QST = 3;                           // Q / dO ring depth
 constexpr int B2_OFF_K = 0, B2_OFF_V = 32768, B2_OFF_QDO = 49152, B2_OFF_DS = B2_OFF_QDO + B2_QST * 32768, B2_OFF_DQ = B2_OFF_DS + 32768,
               B2_OFF_META = B2_OFF_DQ + 32768, B2_OFF_BARS = B2_OFF_META + 2 * 2048;
-constexpr int B2_SMEM = B2_OFF_BARS + 512 + 1024 /*align*/;
+constexpr int B2_SMEM = B2_OFF_BARS + 512;
 
 #define B2_C0 9.9999722832e-01f
 #define B2_C1 -3.3323076483e-01f
@@ -47,7 +48,43 @@ __device__ __forceinline__ void b2_tma_reduce_add_2d(const CUtensorMap* m, const
 __device__ __forceinline__ void b2_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void b2_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void b2_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void b2_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void b2_bar1() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void b2_bar2() { asm volatile("bar.sync 2, 512;" ::: "memory"); }
+
+// p & ((a - b) >> 31): keeps p iff a < b.  Opaque PTX: written as C the compiler turns it back into compare + select and parks the predicates
+// of a whole unrolled chunk in a register bit mask (PLOP3 / LOP3 chains, measured in the SASS).
+__device__ __forceinline__ float b2_keep_if_less(float p, int a, int b) {
+  uint32_t r;
+  asm("{\n\t.reg .s32 t;\n\tsub.s32 t, %2, %3;\n\tshr.s32 t, t, 31;\n\tand.b32 %0, %1, t;\n\t}" : "=r"(r) : "r"(__float_as_uint(p)), "r"(a), "r"(b));
+  return __uint_as_float(r);
+}
+
+// 32 transposed scores (one key row x 32 queries) -> e = cap log2e tanh(y) (kept for the 1 - tanh^2 factor) and bf16 pairs of p = 2^(e - lse2[q]).
+// nl: -lse2 per query, lim1: visibility limit + 1 per query (warp-uniform shared-memory addresses: broadcast loads).
+// MASKED: query q sees this key iff key < lim1[q]; arithmetic AND on the bits of p instead of compare + select (no predicate pressure).
+template <bool MASKED>
+__device__ __forceinline__ void b2_exp_chunk(const uint32_t (&rs)[16], const float* __restrict__ nl, const int* __restrict__ lim1, int key, float2 A0, float2 A1, float2 A2,
+                                             float2 A3, float2 A4, float2 (&ee)[8], uint32_t (&wp)[8]) {
+#pragma unroll
+  for (int e2 = 0; e2 < 16; e2 += 2) {
+    const float2 x = make_float2(__uint_as_float(rs[e2]), __uint_as_float(rs[e2 + 1]));
+    const float2 X = __fmul2_rn(x, x);
+    float2 gp = __ffma2_rn(A4, X, A3);
+    gp = __ffma2_rn(gp, X, A2);
+    gp = __ffma2_rn(gp, X, A1);
+    gp = __ffma2_rn(gp, X, A0);
+    const float2 e = __fmul2_rn(x, gp);
+    const float2 pe = __fadd2_rn(e, *reinterpret_cast<const float2*>(nl + e2));
+    float p0 = b2_ex2(pe.x), p1 = b2_ex2(pe.y);
+    if (MASKED) {
+      const int2 lm = *reinterpret_cast<const int2*>(lim1 + e2);
+      p0 = b2_keep_if_less(p0, key, lm.x);
+      p1 = b2_keep_if_less(p1, key, lm.y);
+    }
+    ee[e2 >> 1] = e;
+    wp[e2 >> 1] = pack_bf16(p0, p1);
+  }
+}
 
 struct B2Item { int kv0, kv_end, q_begin, q_end, n_q, head; };
 
@@ -73,8 +110,8 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               const int* __restrict__ kt_order, int n_items,
               float* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long ld_dv, int M, int H, float scale, float cap, const float* __restrict__ fast) {
   if (fast[0] == 0.f) return;
-  extern __shared__ uint8_t b2_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(b2_smem_raw) + 1023) & ~uintptr_t(1023));
+  // declared 1024-byte aligned and used directly: the compiler keeps the shared address space (LDS / STS instead of generic LD / ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem + B2_OFF_K;                     // [2][16 KB]
   uint8_t* sV = smem + B2_OFF_V;                     // [16 KB]
   uint8_t* sQDO = smem + B2_OFF_QDO;                 // [B2_QST][Q 16 KB | dO 16 KB]
@@ -89,12 +126,13 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) { printf("tfx: attn_bwd_ts dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
     for (int b = 0; b < 2; ++b) { mbar_init(&k_full[b], 1); mbar_init(&k_empty[b], 1); }
     mbar_init(v_full, 1); mbar_init(v_empty, 1);
     for (int b = 0; b < B2_QST; ++b) { mbar_init(&qdo_full[b], 1); mbar_init(&qdo_empty[b], 1); }
-    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(s_free, 8); mbar_init(pt_full, 8); mbar_init(ds_full, 8); mbar_init(grad_done, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_free, 8); mbar_init(dkv_full, 1); mbar_init(dkv_free, 8);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(s_free, 16); mbar_init(pt_full, 16); mbar_init(ds_full, 16); mbar_init(grad_done, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 16); mbar_init(dkv_full, 1); mbar_init(dkv_free, 16);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -185,7 +223,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tc_fence_after();
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq)
-          umma_bf16_ts(tDK, tDP + (kq >> 2) * 64 + (kq & 3) * 8, umma_smem_desc_sw128(aQ + kq * 2048, 8192, 1024), idT, (ib_i > 0 || kq > 0) ? 1u : 0u);
+          umma_bf16_ts(tDK, tDP + (kq >> 1) * 32 + (kq & 1) * 8, umma_smem_desc_sw128(aQ + kq * 2048, 8192, 1024), idT, (ib_i > 0 || kq > 0) ? 1u : 0u);      // dS^T of query quarter qc sits at dP^T + qc * 32 + [0, 16)
         if (gb >= 1) { mbar_wait(dq_free, (gb - 1) & 1); tc_fence_after(); }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)               // contraction over the 128 keys (rows of the dS^T tile)
@@ -203,12 +241,12 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (has_a) issue_dP();                      // dP^T of the next step (its TMEM columns held dS^T of this one until dK above)
       }
     }
-  } else {
-    // ===================================================== softmax / gradient warps (thread <-> key row)
+  } else if (warp >= 4) {
+    // ===================================================== softmax / gradient warps (thread <-> key row x 32 queries)
     const int quad = warp & 3;
-    const int hf = (warp - 2) >> 2;                  // query-column half of S^T / dP^T; dQ column half in the read-out
+    const int qc = (warp - 4) >> 2;                  // query-column quarter of S^T / dP^T; dQ / dK / dV column quarter in the read-outs
     const int row = quad * 32 + lane;                // key row of the tile (S^T, dP^T, dK, dV) / query row (dQ read-out)
-    const int tid = threadIdx.x - 64;                // 0 .. 255
+    const int tid = threadIdx.x - 128;               // 0 .. 511
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     const float k1 = scale / cap;
     const float KL = cap * 1.4426950408889634f;
@@ -219,27 +257,27 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), A3 = make_float2(a3, a3), A4 = make_float2(a4, a4),
                  OC = make_float2(oms_c, oms_c), SC = make_float2(scale, scale);
     const int swz_row = (row >> 3) * 1024 + (row & 7) * 128;
-    const bool elected = (warp == 2 && lane == 0);
+    const bool elected = (warp == 4 && lane == 0);
     uint32_t g = 0;
 
-    // dQ of step g_done: TMEM -> smem -> TMA reduce-add into global (lanes = query rows here)
+    // dQ of step g_done: TMEM -> smem -> TMA reduce-add into global (lanes = query rows here; this warp moves 16 of the 64 columns)
     auto dq_readout = [&](uint32_t g_done, int qrow0, int hd) {
       mbar_wait(dq_full, g_done & 1);
       tc_fence_after();
       if (elected) b2_bulk_wait_read0();             // the previous reduce has finished reading sDQ
-      b2_bar(1);
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tDQ + lane_addr + hf * 32, r);
+      b2_bar1();
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tDQ + lane_addr + qc * 16, r);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
-      uint8_t* dst = sDQ + hf * 16384 + swz_row;
+      uint8_t* dst = sDQ + (qc >> 1) * 16384 + swz_row;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(dst + ((((qc & 1) * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
       fence_proxy_async_smem();
-      b2_bar(1);
+      b2_bar1();
       if (elected) {
         b2_tma_reduce_add_2d(&tmDQ, sDQ, hd * 64, qrow0);
         b2_tma_reduce_add_2d(&tmDQ, sDQ + 16384, hd * 64 + 32, qrow0);
@@ -247,21 +285,21 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     };
 
-    // per-query statistics of step (item im, query tile i) -> registers of threads 0..127 (one query each); written to smem buffer `buf` by stage_meta
+    // per-query statistics of a step: fetched into registers of threads 0..127 (one query each) one step ahead, written to shared memory by stage_meta
     float m_lse = 0.f, m_D = 0.f; int m_lim = -1;
     auto fetch_meta = [&](const B2Item& im, int i) {
       if (tid < 128) {
         const int gr = im.q_begin + i * 128 + tid;
         const bool ok = gr < im.q_end;
         m_lim = ok ? kv_limit[gr] : -1;
-        m_lse = ok ? -lse[(long long)im.head * M + gr] * 1.4426950408889634f : 0.f;      // stored negated: the consumers only add
-        m_D = ok ? -dsum[(long long)im.head * M + gr] : 0.f;
+        m_lse = ok ? lse[(long long)im.head * M + gr] : 0.f;
+        m_D = ok ? dsum[(long long)im.head * M + gr] : 0.f;
       }
     };
-    auto stage_meta = [&](int buf) {
+    auto stage_meta = [&](int buf) {                 // stored negated (the consumers only add) and as limit + 1 (the mask is `key < limit + 1`)
       float* mb = sMeta + buf * 512;
       if (tid < 128) {
-        mb[tid] = m_lse; mb[128 + tid] = m_D; reinterpret_cast<int*>(mb)[256 + tid] = m_lim;
+        mb[tid] = -m_lse * 1.4426950408889634f; mb[128 + tid] = -m_D; reinterpret_cast<int*>(mb)[256 + tid] = m_lim + 1;
         const int wmin = __reduce_min_sync(0xffffffffu, m_lim);
         if ((tid & 31) == 0) reinterpret_cast<int*>(mb)[384 + (tid >> 5)] = wmin;
       }
@@ -270,7 +308,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     B2Item it, nx;
     bool has = b2_item(0, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, it);
     if (has) { fetch_meta(it, 0); stage_meta(0); }
-    b2_bar(2);
+    b2_bar2();
     int prev_qrow0 = 0, prev_head = 0;
     bool pending = false;
     for (int k = 0; has; ++k) {
@@ -284,41 +322,26 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (i + 1 < it.n_q) fetch_meta(it, i + 1); else if (has_n) fetch_meta(nx, 0);
         const int min_lim = min(min(mbi[384], mbi[385]), min(mbi[386], mbi[387]));
         const bool all_visible = kv0 + 127 <= min_lim;      // every query of the tile sees every key of the tile: no mask
-        // Per 32-query chunk: exponentials from S^T (dP^T of this step may still be in flight), P^T back to TMEM, then dS^T from dP^T.
-        uint32_t wd[32];                                    // dS^T of this thread's key row x 64 queries, bf16 pairs
+        // Per 16-query chunk: exponentials from S^T (dP^T of this step may still be in flight), P^T back to TMEM, then dS^T from dP^T.
+        uint32_t wd[16];                                    // dS^T of this thread's key row x 32 queries, bf16 pairs
         mbar_wait(s_full, g & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t wp[16];                                  // P^T chunk, bf16 pairs
-          float2 ee[16];                                    // cap * log2e * tanh(y) of the same scores (for the 1 - tanh^2 factor)
+          const int col0 = qc * 32 + c * 16;
+          uint32_t wp[8];                                   // P^T chunk, bf16 pairs
+          float2 ee[8];                                     // cap * log2e * tanh(y) of the same scores (for the 1 - tanh^2 factor)
           {
-            uint32_t rs[32];
-            tmem_ld_32x32b_x32(tS + lane_addr + hf * 64 + c * 32, rs);
+            uint32_t rs[16];
+            tmem_ld_32x32b_x16(tS + lane_addr + col0, rs);
             tmem_ld_wait();
             if (c == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(s_free); }      // S^T is in registers: S^T of the next step may be issued
-#pragma unroll
-            for (int e2 = 0; e2 < 32; e2 += 2) {
-              const int col = hf * 64 + c * 32 + e2;
-              const float2 x = make_float2(__uint_as_float(rs[e2]), __uint_as_float(rs[e2 + 1]));
-              const float2 X = __fmul2_rn(x, x);
-              float2 gp = __ffma2_rn(A4, X, A3);
-              gp = __ffma2_rn(gp, X, A2);
-              gp = __ffma2_rn(gp, X, A1);
-              gp = __ffma2_rn(gp, X, A0);
-              const float2 e = __fmul2_rn(x, gp);
-              const float2 pe = __fadd2_rn(e, *reinterpret_cast<const float2*>(mb + col));      // + (-lse2): warp-uniform address, broadcast
-              float p0 = b2_ex2(pe.x), p1 = b2_ex2(pe.y);
-              if (!all_visible) {
-                const int2 lm = *reinterpret_cast<const int2*>(mbi + 256 + col);
-                p0 = (key <= lm.x) ? p0 : 0.f; p1 = (key <= lm.y) ? p1 : 0.f;
-              }
-              ee[e2 >> 1] = e;
-              wp[e2 >> 1] = pack_bf16(p0, p1);
-            }
+            // the visibility mask is only needed on diagonal / span-boundary tiles: two specialised code paths (see attention_fwd_sm100.cu)
+            if (all_visible) b2_exp_chunk<false>(rs, mb + col0, mbi + 256 + col0, key, A0, A1, A2, A3, A4, ee, wp);
+            else b2_exp_chunk<true>(rs, mb + col0, mbi + 256 + col0, key, A0, A1, A2, A3, A4, ee, wp);
           }
           if (c == 0 && g > 0) { mbar_wait(grad_done, (g - 1) & 1); tc_fence_after(); }    // dV / dK / dQ of the previous step have consumed P^T, dS^T (TMEM and smem)
-          tmem_st_32x32b_x16(tPT + lane_addr + hf * 32 + c * 16, wp);
+          tmem_st_32x32b_x8(tPT + lane_addr + qc * 16 + c * 8, wp);
           if (c == 1) {                                     // P^T complete: dV may start while dS^T is still being computed
             tmem_st_wait();
             tc_fence_before();
@@ -326,28 +349,27 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (lane == 0) mbar_arrive(pt_full);
           }
           if (c == 0) { mbar_wait(dp_full, g & 1); tc_fence_after(); }
-          uint32_t rp[32];
-          tmem_ld_32x32b_x32(tDP + lane_addr + hf * 64 + c * 32, rp);
+          uint32_t rp[16];
+          tmem_ld_32x32b_x16(tDP + lane_addr + col0, rp);
           tmem_ld_wait();
 #pragma unroll
-          for (int e2 = 0; e2 < 32; e2 += 2) {
-            const int col = hf * 64 + c * 32 + e2;
+          for (int e2 = 0; e2 < 16; e2 += 2) {
             const int j = e2 >> 1;
             const float2 e = ee[j];
             const float2 pf = unpack2_bf16(wp[j]);                                                // the SAME bf16 P^T the dV product sees
             const float2 oms = __ffma2_rn(__fmul2_rn(e, e), OC, SC);
-            const float2 dpd = __fadd2_rn(make_float2(__uint_as_float(rp[e2]), __uint_as_float(rp[e2 + 1])), *reinterpret_cast<const float2*>(mb + 128 + col));   // + (-D)
+            const float2 dpd = __fadd2_rn(make_float2(__uint_as_float(rp[e2]), __uint_as_float(rp[e2 + 1])), *reinterpret_cast<const float2*>(mb + 128 + col0 + e2));   // + (-D)
             const float2 d = __fmul2_rn(__fmul2_rn(pf, dpd), oms);
-            wd[c * 16 + j] = pack_bf16(d.x, d.y);
+            wd[c * 8 + j] = pack_bf16(d.x, d.y);
           }
         }
         // dS^T over this warp's own dP^T columns (TS operand of dK) and into the shared tile (MN-major A operand of dQ)
-        tmem_st_32x32b_x32(tDP + lane_addr + hf * 64, wd);
+        tmem_st_32x32b_x16(tDP + lane_addr + qc * 32, wd);
         {
-          uint8_t* db = sDS + hf * 16384 + swz_row;
+          uint8_t* db = sDS + (qc >> 1) * 16384 + swz_row;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            *reinterpret_cast<uint4*>(db + ((ch ^ (row & 7)) << 4)) = make_uint4(wd[4 * ch], wd[4 * ch + 1], wd[4 * ch + 2], wd[4 * ch + 3]);
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(db + ((((qc & 1) * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(wd[4 * ch], wd[4 * ch + 1], wd[4 * ch + 2], wd[4 * ch + 3]);
         }
         tmem_st_wait();
         fence_proxy_async_smem();
@@ -357,26 +379,26 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
         prev_qrow0 = it.q_begin + i * 128; prev_head = it.head; pending = true;
         stage_meta((g + 1) & 1);                             // statistics of the next step (fetched above); the buffer was last read in step g - 1
-        b2_bar(2);
+        b2_bar2();
       }
-      // ---- dK (fp32) and dV (bf16) of this key tile
+      // ---- dK (fp32) and dV (bf16) of this key tile: 16 of the 64 columns per warp
       mbar_wait(dkv_full, k & 1);
       tc_fence_after();
       {
-        uint32_t r[32], r2[32];
-        tmem_ld_32x32b_x32(tDK + lane_addr + hf * 32, r);
-        tmem_ld_32x32b_x32(tDV + lane_addr + hf * 32, r2);
+        uint32_t r[16], r2[16];
+        tmem_ld_32x32b_x16(tDK + lane_addr + qc * 16, r);
+        tmem_ld_32x32b_x16(tDV + lane_addr + qc * 16, r2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dkv_free);        // the accumulators may be overwritten by the next item
         if (key < it.kv_end) {
-          float* dst = dk + (long long)key * H * 64 + it.head * 64 + hf * 32;
+          float* dst = dk + (long long)key * H * 64 + it.head * 64 + qc * 16;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + ch * 4) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
-          __nv_bfloat16* dst2 = dv + (long long)key * ld_dv + it.head * 64 + hf * 32;
+          for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst + ch * 4) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+          __nv_bfloat16* dst2 = dv + (long long)key * ld_dv + it.head * 64 + qc * 16;
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
+          for (int qd = 0; qd < 2; ++qd) {
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(r2[qd * 8 + 2 * e]), __uint_as_float(r2[qd * 8 + 2 * e + 1]));

@@ -27,9 +27,9 @@ namespace tfx {
 
 int num_sms();
 
-constexpr int F2_THREADS = 320;
+constexpr int F2_THREADS = 640;
 constexpr int F2_STAGES = 4;                       // K / V ring depth (32 KB per stage: K tile | V tile)
-constexpr int F2_SMEM = 2 * 32768 + F2_STAGES * 32768 + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int F2_SMEM = 2 * 32768 + F2_STAGES * 32768 + 512 /*barriers*/ + 4096 /*softmax denominators*/;
 
 // tanh(y) ~= y * (C0 + C1 u + C2 u^2 + C3 u^3 + C4 u^4), u = y^2, |y| <= 0.75 (same fit as attention_sm100.cu)
 #define F2_C0 9.9999722832e-01f
@@ -39,6 +39,38 @@ constexpr int F2_SMEM = 2 * 32768 + F2_STAGES * 32768 + 1024 /*align*/ + 512 /*b
 #define F2_C4 1.2318833231e-02f
 
 __device__ __forceinline__ float f2_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// p & ((a - b) >> 31): keeps p iff a < b.  Opaque PTX: written as C the compiler turns it back into compare + select and parks the predicates
+// of a whole unrolled chunk in a register bit mask (PLOP3 / LOP3 chains, measured in the SASS).
+__device__ __forceinline__ float f2_keep_if_less(float p, int a, int b) {
+  uint32_t r;
+  asm("{\n\t.reg .s32 t;\n\tsub.s32 t, %2, %3;\n\tshr.s32 t, t, 31;\n\tand.b32 %0, %1, t;\n\t}" : "=r"(r) : "r"(__float_as_uint(p)), "r"(a), "r"(b));
+  return __uint_as_float(r);
+}
+
+// 32 scores of one query row -> 16 bf16 pairs of p = 2^(x poly(x^2) - m2); packed fp32x2 FMAs (FFMA2): two scores per instruction.
+// MASKED: key i of the chunk is visible iff i < nvis; the mask is an arithmetic AND on the bits of p (no predicates: a compare + select per
+// score made ptxas park 32 predicates in a register bit mask - 4 LOP3 per score, measured in the round-1 SASS).
+template <bool MASKED>
+__device__ __forceinline__ void f2_softmax_chunk(const uint32_t (&r)[32], int nvis, float2 A0, float2 A1, float2 A2, float2 A3, float2 A4, float2 NM2, float2& l2, uint32_t* out) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float2 x = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+    const float2 X = __fmul2_rn(x, x);
+    float2 gq = __ffma2_rn(A4, X, A3);
+    gq = __ffma2_rn(gq, X, A2);
+    gq = __ffma2_rn(gq, X, A1);
+    gq = __ffma2_rn(gq, X, A0);
+    const float2 e = __ffma2_rn(x, gq, NM2);
+    float p0 = f2_ex2(e.x), p1 = f2_ex2(e.y);
+    if (MASKED) {
+      p0 = f2_keep_if_less(p0, i, nvis);
+      p1 = f2_keep_if_less(p1, i + 1, nvis);
+    }
+    l2 = __fadd2_rn(l2, make_float2(p0, p1));
+    out[i >> 1] = pack_bf16(p0, p1);
+  }
+}
 
 struct F2Item { int q0[2], qend[2], n[2]; int kv0, nmax, head; };
 
@@ -66,45 +98,33 @@ __device__ __forceinline__ bool f2_item(int k, int n_items, int H, const int* __
   return true;
 }
 
-__device__ __forceinline__ bool f2_has(int k, int n_items) {
-  const int G = gridDim.x;
-  return k * G + ((k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x) < n_items;
-}
-
-// MMA-lane cursor of one softmax group over its operation stream: (item, key tile) of the next S (or PV) product
-struct F2Cur {
-  int k;            // item index of this CTA
-  int j;            // key tile inside the item
-  int n;            // key tiles this group needs in the item
-  uint32_t tb;      // global tile-stream index of the item's first key tile (K / V ring position)
-  int nmax;         // key tiles of the item (both groups)
-  bool ok;
-};
-
-// 10 warps are allocated as 12 (warp allocation granularity 4): 65536 / 384 = 170 registers per thread is the real ceiling, not 204
+// 20 warps: warp 0 TMA producer, warps 1 / 2 MMA issuers of query tile A / B, warp 3 idle, warps 4..19 softmax
+// (query tile, 64-key column half, TMEM lane quadrant).  65536 / 640 threads -> 96 registers per thread.
 __global__ void __launch_bounds__(F2_THREADS, 1)
 attn_fwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
               const float* __restrict__ gates, int H, const int* __restrict__ kv_limit, const int* __restrict__ t_q0, const int* __restrict__ t_qend,
               const int* __restrict__ t_kv0, const int* __restrict__ t_kvend, const int* __restrict__ pairs, int n_items,
               __nv_bfloat16* __restrict__ o, long long ld_o, float* __restrict__ lse, int M, float scale, float cap, const float* __restrict__ fast) {
   if (fast[0] == 0.f) return;                       // precondition of this path does not hold: the general kernel does the work
-  extern __shared__ uint8_t f2_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(f2_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                // [2 item slots][tile A 16 KB | tile B 16 KB]
-  uint8_t* sKV = smem + 65536;                       // [F2_STAGES][K 16 KB | V 16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + F2_STAGES * 32768);
+  // declared 1024-byte aligned (SWIZZLE_128B tiles) and used directly, so that the compiler keeps the shared address space (LDS / STS, not generic LD / ST)
+  extern __shared__ __align__(1024) uint8_t f2_smem[];
+  uint8_t* sQ = f2_smem;                             // [2 item slots][tile A 16 KB | tile B 16 KB]
+  uint8_t* sKV = f2_smem + 65536;                    // [F2_STAGES][K 16 KB | V 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(f2_smem + 65536 + F2_STAGES * 32768);
   uint64_t *q_full = bars, *q_empty = bars + 2, *kv_full = bars + 4, *kv_empty = bars + 4 + F2_STAGES, *s_full = bars + 4 + 2 * F2_STAGES, *s_empty = s_full + 2,
            *p_full = s_full + 4, *p_empty = s_full + 6, *o_full = s_full + 8, *o_empty = s_full + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 12);
+  float* sL = reinterpret_cast<float*>(s_full + 14);  // [2 item parities][2 tiles][2 column halves][128 rows] partial softmax denominators
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    if (smem_u32(f2_smem) & 1023u) { printf("tfx: attn_fwd_ts dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&q_full[b], 1); mbar_init(&q_empty[b], 1);
-      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4); mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);
+      mbar_init(&q_full[b], 1); mbar_init(&q_empty[b], 2);
+      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8); mbar_init(&p_full[b], 8); mbar_init(&p_empty[b], 1); mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 8);
     }
-    for (int s = 0; s < F2_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < F2_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -133,96 +153,73 @@ attn_fwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer: polling state machine over both groups' next S / PV product
+  } else if (warp == 1 || warp == 2) {
+    // ===================================================== MMA issuer of query tile w: S(0), then per key tile [S(j+1)] PV(j).  Blocking mbarrier waits
+    // (hardware-suspended try_wait, ~60 cycles wake-up) - a single polling lane for both tiles with __nanosleep between sweeps slept ~1 us per hand-off.
+    // Both issuers hand K / V stages and Q slots back through count-2 barriers; a tile / item the group does not need is acknowledged once it has LANDED
+    // (an earlier plain arrive could complete the previous phase of the stage while the other group still reads it).
     if (lane == 0) {
+      const int w = warp - 1;
       constexpr uint32_t idS = umma_idesc_bf16(128, 128, 0, 0);       // S = Q K^T : A, B K-major
       constexpr uint32_t idO = umma_idesc_bf16(128, 64, 0, 1);        // O += P V  : A = P (TMEM), B = V MN-major
-      F2Cur cs[2], cp[2];
-      uint32_t gs[2] = {0, 0}, gp[2] = {0, 0}, oc[2] = {0, 0};
-      F2Item it;
-      auto seek = [&](F2Cur& c, int w, int k_from, uint32_t tb_from) {   // first item >= k_from in which group w has work
-        c.k = k_from; c.tb = tb_from; c.j = 0; c.ok = false;
-        while (f2_item(c.k, n_items, H, pairs, t_q0, t_qend, t_kv0, t_kvend, it)) {
-          c.n = it.n[w]; c.nmax = it.nmax;
-          if (c.n > 0) { c.ok = true; return; }
-          c.tb += it.nmax; ++c.k;
-        }
-      };
-      auto advance = [&](F2Cur& c, int w) { if (++c.j == c.n) seek(c, w, c.k + 1, c.tb + c.nmax); };
-      for (int w = 0; w < 2; ++w) { seek(cs[w], w, 0, 0); cp[w] = cs[w]; }
-      int q_rel = 0;                 // items whose Q slot has been handed back to the producer
-      uint32_t kv_rel = 0;           // key tiles (stream index) handed back
       const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
-      while (cs[0].ok || cs[1].ok || cp[0].ok || cp[1].ok) {
-        bool progress = false;
+      const uint32_t tS = tmem_base + w * 128, tO = tmem_base + 256 + w * 64, tP = tmem_base + 384 + w * 64;
+      uint32_t gs = 0, gp = 0, oc = 0, tb = 0;
+      F2Item it;
+      for (int k = 0; f2_item(k, n_items, H, pairs, t_q0, t_qend, t_kv0, t_kvend, it); ++k) {
+        const int qs = k & 1, n = it.n[w], nmax = it.nmax;
+        mbar_wait(&q_full[qs], (k >> 1) & 1);
+        auto issue_S = [&](int j) {
+          const uint32_t t = tb + j;
+          const int st = t & (F2_STAGES - 1);
+          mbar_wait(&kv_full[st], (t / F2_STAGES) & 1);
+          if (gs > 0) mbar_wait(&s_empty[w], (gs - 1) & 1);            // the softmax group has pulled the previous S out of TMEM
+          tc_fence_after();
+          const uint32_t a = aQ + qs * 32768 + w * 16384, b = aKV + st * 32768;
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          // ---- S_w(item, j) = Q_w K_j^T
-          if (cs[w].ok) {
-            F2Cur& c = cs[w];
-            const uint32_t t = c.tb + c.j;
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tS, umma_smem_desc_sw128(a + kk * 32, 0, 1024), umma_smem_desc_sw128(b + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
+          umma_commit(&s_full[w]);
+          ++gs;
+          if (j == n - 1) umma_commit(&q_empty[qs]);                    // last S product of the item: this group is done with the Q slot
+        };
+        if (n > 0) {
+          issue_S(0);
+          for (int j = 0; j < n; ++j) {
+            if (j + 1 < n) issue_S(j + 1);                              // runs ahead: overlaps the softmax of tile j
+            const uint32_t t = tb + j;
             const int st = t & (F2_STAGES - 1);
-            bool ready = mbar_test_wait(&kv_full[st], (t / F2_STAGES) & 1);
-            if (ready && c.j == 0) ready = mbar_test_wait(&q_full[c.k & 1], (c.k >> 1) & 1);
-            if (ready && gs[w] > 0) ready = mbar_test_wait(&s_empty[w], (gs[w] - 1) & 1);
-            if (ready) {
-              tc_fence_after();
-              const uint32_t a = aQ + (c.k & 1) * 32768 + w * 16384, b = aKV + st * 32768;
+            mbar_wait(&p_full[w], gp & 1);
+            if (j == 0 && oc > 0) mbar_wait(&o_empty[w], (oc - 1) & 1);  // the previous item's O has been read out
+            tc_fence_after();
+            const uint32_t bV = aKV + st * 32768 + 16384;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_bf16_ss(tmem_base + w * 128, umma_smem_desc_sw128(a + kk * 32, 0, 1024), umma_smem_desc_sw128(b + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
-              umma_commit(&s_full[w]);
-              ++gs[w];
-              advance(c, w);
-              // Q slots: released (in item order) once both groups have issued their last S product of the item
-              for (;;) {
-                const int k0 = cs[0].ok ? cs[0].k : INT_MAX, k1 = cs[1].ok ? cs[1].k : INT_MAX;
-                if (q_rel < (k0 < k1 ? k0 : k1) && f2_has(q_rel, n_items)) { umma_commit(&q_empty[q_rel & 1]); ++q_rel; }
-                else break;
-              }
-              progress = true;
-            }
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ts(tO, tP + kk * 8, umma_smem_desc_sw128(bV + kk * 2048, 8192, 1024), idO, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&p_empty[w]);
+            umma_commit(&kv_empty[st]);
+            ++gp;
+            if (j == n - 1) { umma_commit(&o_full[w]); ++oc; }
           }
-          // ---- O_w (+)= P_w(item, j) V_j
-          if (cp[w].ok) {
-            F2Cur& c = cp[w];
-            bool ready = mbar_test_wait(&p_full[w], gp[w] & 1);
-            if (ready && c.j == 0 && oc[w] > 0) ready = mbar_test_wait(&o_empty[w], (oc[w] - 1) & 1);
-            if (ready) {
-              tc_fence_after();
-              const uint32_t t = c.tb + c.j;
-              const uint32_t bV = aKV + (t & (F2_STAGES - 1)) * 32768 + 16384;
-              const uint32_t tO = tmem_base + 256 + w * 64, tP = tmem_base + 384 + w * 64;
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk)
-                umma_bf16_ts(tO, tP + kk * 8, umma_smem_desc_sw128(bV + kk * 2048, 8192, 1024), idO, (c.j > 0 || kk > 0) ? 1u : 0u);
-              umma_commit(&p_empty[w]);
-              ++gp[w];
-              if (c.j == c.n - 1) { umma_commit(&o_full[w]); ++oc[w]; }
-              advance(c, w);
-              // K / V ring: a stage goes back once every group that needs the tile has issued its PV product
-              for (;;) {
-                const uint32_t n0 = cp[0].ok ? cp[0].tb + cp[0].j : 0xffffffffu, n1 = cp[1].ok ? cp[1].tb + cp[1].j : 0xffffffffu;
-                const uint32_t nmin = n0 < n1 ? n0 : n1;
-                // when both groups are finished everything issued so far may go back; the producer never waits on those phases
-                if (kv_rel < nmin && (cp[0].ok || cp[1].ok)) { umma_commit(&kv_empty[kv_rel & (F2_STAGES - 1)]); ++kv_rel; }
-                else break;
-              }
-              progress = true;
-            }
-          }
+        } else {
+          mbar_arrive(&q_empty[qs]);
         }
-        if (!progress) __nanosleep(20);
+        for (int j = n; j < nmax; ++j) {                                 // key tiles only the other group needs
+          const uint32_t t = tb + j;
+          const int st = t & (F2_STAGES - 1);
+          mbar_wait(&kv_full[st], (t / F2_STAGES) & 1);
+          mbar_arrive(&kv_empty[st]);
+        }
+        tb += nmax;
       }
     }
-  } else {
-    // ===================================================== softmax groups (thread <-> query row)
-    const int w = (warp - 2) >> 2;
-    const int quad = warp & 3;
+  } else if (warp >= 4) {
+    // ===================================================== softmax warps (thread <-> query row, 64 of the tile's 128 keys)
+    const int idx = warp - 4;
+    const int w = idx >> 3, ch = (idx >> 2) & 1, quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    const uint32_t tS = tmem_base + w * 128 + lane_addr, tO = tmem_base + 256 + w * 64 + lane_addr, tP = tmem_base + 384 + w * 64 + lane_addr;
+    const uint32_t tS = tmem_base + w * 128 + ch * 64 + lane_addr, tO = tmem_base + 256 + w * 64 + ch * 32 + lane_addr, tP = tmem_base + 384 + w * 64 + ch * 32 + lane_addr;
     const float k1 = scale / cap;                    // y = x * k1
     const float KL = cap * 1.4426950408889634f;      // exponent (base 2) = KL * tanh(y) - m2
     const float m2 = fast[1] * 1.4426950408889634f;
@@ -239,83 +236,61 @@ attn_fwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int grow = it.q0[w] + row;
       const bool valid = grow < it.qend[w];
       const int lim = valid ? kv_limit[grow] : -1;
-      const int wmin = __reduce_min_sync(0xffffffffu, valid ? lim : INT_MAX);   // key tiles entirely below it need no mask (per warp)
+      const int wmin = __reduce_min_sync(0xffffffffu, valid ? lim : INT_MAX);   // key columns entirely below it need no mask (per warp)
       float gate = 1.f;
       if (valid && gates) gate = 1.f / (1.f + __expf(-gates[(long long)grow * H + it.head]));
       float2 l2 = make_float2(0.f, 0.f);
       for (int j = 0; j < n; ++j, ++g) {
-        const int key0 = it.kv0 + j * 128;
-        const bool all_visible = key0 + 127 <= wmin;
-        uint32_t pk[64];
+        const int key0 = it.kv0 + j * 128 + ch * 64;                      // first key of this warp's column half
+        const bool all_visible = key0 + 63 <= wmin;
         mbar_wait(&s_full[w], g & 1);
         tc_fence_after();
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32b_x32(tS + hf * 64, r0);
-          tmem_ld_32x32b_x32(tS + hf * 64 + 32, r1);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32], pk[16];
+          tmem_ld_32x32b_x32(tS + c * 32, r);
           tmem_ld_wait();
-          if (hf == 1) {                               // S is in registers: the accumulator may be overwritten by the next S product
+          if (c == 1) {                                // this warp's part of S is in registers
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[w]);
           }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t* r = c ? r1 : r0;
-            const int kbase = key0 + hf * 64 + c * 32;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {          // packed fp32x2 FMAs (FFMA2): two scores per instruction
-              const float2 x = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-              const float2 X = __fmul2_rn(x, x);
-              float2 gq = __ffma2_rn(A4, X, A3);
-              gq = __ffma2_rn(gq, X, A2);
-              gq = __ffma2_rn(gq, X, A1);
-              gq = __ffma2_rn(gq, X, A0);
-              const float2 e = __ffma2_rn(x, gq, NM2);
-              float p0 = f2_ex2(e.x), p1 = f2_ex2(e.y);
-              if (!all_visible) { p0 = (kbase + i <= lim) ? p0 : 0.f; p1 = (kbase + i + 1 <= lim) ? p1 : 0.f; }
-              l2 = __fadd2_rn(l2, make_float2(p0, p1));
-              pk[hf * 32 + c * 16 + (i >> 1)] = pack_bf16(p0, p1);
-            }
-          }
+          // the mask costs 3 integer instructions per score and is only needed on diagonal / span-boundary tiles: two specialised code paths, chosen per warp
+          if (all_visible) f2_softmax_chunk<false>(r, 0, A0, A1, A2, A3, A4, NM2, l2, pk);
+          else f2_softmax_chunk<true>(r, lim - (key0 + c * 32) + 1, A0, A1, A2, A3, A4, NM2, l2, pk);
+          if (c == 0 && g > 0) { mbar_wait(&p_empty[w], (g - 1) & 1); tc_fence_after(); }    // the previous PV product has consumed the P buffer
+          tmem_st_32x32b_x16(tP + c * 16, pk);
         }
-        if (g > 0) mbar_wait(&p_empty[w], (g - 1) & 1);    // the previous PV product has consumed the P buffer
-        tc_fence_after();
-        tmem_st_32x32b_x32(tP, pk);
-        tmem_st_32x32b_x32(tP + 32, pk + 32);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[w]);
       }
-      // ---- epilogue of the item: O / l * sigmoid(gate) -> bf16
+      // ---- epilogue of the item: the two column halves add their denominators, each writes 32 of the 64 output columns
+      float* sl = sL + (oc & 1) * 512 + w * 256;
+      sl[ch * 128 + row] = l2.x + l2.y;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+      const float l = sl[row] + sl[128 + row];
       mbar_wait(&o_full[w], oc & 1);
       ++oc;
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(tO, r0);
-      tmem_ld_32x32b_x32(tO + 32, r1);
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tO, r);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[w]);
-      const float l = l2.x + l2.y;
       const float gsc = (l > 0.f ? 1.f / l : 0.f) * gate;
       if (valid) {
-        __nv_bfloat16* dst = o + (long long)grow * ld_o + it.head * 64;
+        __nv_bfloat16* dst = o + (long long)grow * ld_o + it.head * 64 + ch * 32;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const uint32_t* r = hf ? r1 : r0;
+        for (int qd = 0; qd < 4; ++qd) {
+          uint32_t wv[4];
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint32_t wv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) wv[e] = pack_bf16(__uint_as_float(r[qd * 8 + 2 * e]) * gsc, __uint_as_float(r[qd * 8 + 2 * e + 1]) * gsc);
-            *reinterpret_cast<uint4*>(dst + hf * 32 + qd * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          }
+          for (int e = 0; e < 4; ++e) wv[e] = pack_bf16(__uint_as_float(r[qd * 8 + 2 * e]) * gsc, __uint_as_float(r[qd * 8 + 2 * e + 1]) * gsc);
+          *reinterpret_cast<uint4*>(dst + qd * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
-        if (lse) lse[(long long)it.head * M + grow] = fast[1] + logf(l);
+        if (lse && ch == 0) lse[(long long)it.head * M + grow] = fast[1] + logf(l);
       }
     }
   }

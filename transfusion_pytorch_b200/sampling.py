@@ -303,12 +303,20 @@ class SamplingMixin:
                     st.num_past_modalities += 1
                     st.phase = 'done' if st.num_tokens > max_length else 'text'
 
+            # optional phase timing (bench.py: `model._sampling_timer = {}`): CUDA events around every text loop / modality round
+            timer = getattr(self, '_sampling_timer', None)
+            def timed(name, fn, *a):
+                if timer is None:
+                    return fn(*a)
+                e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
+                e0.record(); fn(*a); e1.record()
+                timer.setdefault(name, []).append((e0, e1))
             while not all(st.phase == 'done' for st in states):
                 if any(st.phase == 'text' for st in states):
-                    text_loop()
+                    timed('text_loop', text_loop)
                 group = [st for st in states if st.phase == 'modality']
                 if group:
-                    step_modality(group)
+                    timed('modality_round', step_modality, group)
 
             samples = [st.sample for st in states]
             if return_unprocessed_modalities:

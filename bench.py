@@ -176,6 +176,8 @@ def family_model(name, args_, eng, rb):
     elif name == 'adaln_bwd': by = M * (4 * D + 4 * D + 8 * D + 8)
     elif name == 'resid_bwd': by = M * (4 * D + 2 * D + 2 * D) if a[1] is not None else M * (4 * D + 2 * D)
     elif name == 'attn_residual_fwd': by = M * (a[1] * 4 * D + 4 * D + 2 * D)
+    elif name == 'attn_residual_fwd_h16': by = M * (a[1] * 2 * D + 4 * D + 2 * D)
+    elif name == 'attn_residual_bwd_h16': by = M * (a[2] * 2 * D + a[2] * (4 * D if a[-1] else 8 * D) + 8 * D)
     elif name == 'attn_residual_bwd': by = M * (a[2] * 4 * D + a[2] * (4 * D if a[-1] else 8 * D) + 8 * D)
     elif name == 'geglu_bwd': by = M * (2 * Ip + 4 * Ip + 4 * Ip)
     elif name == 'qk_bwd_pack': by = M * (8 * HI + 4 * HI + 4 * HI + 16 * H)

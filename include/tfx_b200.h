@@ -141,6 +141,13 @@ long long tfx_attn_residual_bwd_workspace_floats(int M, int D);   /* fp32 scratc
 int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
                           const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D,
                           int init /* 1: dhiddens are overwritten, not accumulated */, void* stream);
+/* same two kernels reading bf16 COPIES of the hiddens (engine option hid_bf16: the AttentionResidual read traffic - the largest HBM term of the step - halves;
+ * gradients w.r.t. the hiddens stay fp32) */
+int tfx_attn_residual_fwd_h16(const void* const* hiddens_bf16, int n_hiddens, const float* gamma, const float* pseudo_query,
+                              float* x_out, void* x_out_bf16, float* lse_out, int M, int D, void* stream);
+int tfx_attn_residual_bwd_h16(const void* const* hiddens_bf16, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                              const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, int init,
+                              void* stream);
 /* final RMSNorm (T.py:1250, 785-786) (+ compaction of modality rows for the flow head) */
 int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream);
 int tfx_rmsnorm_bwd(const float* dout, const float* x, const float* gamma, float* dx, float* dgamma, int M, int D, void* stream);

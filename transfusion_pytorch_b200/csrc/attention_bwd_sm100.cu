@@ -48,8 +48,6 @@ __device__ __forceinline__ void b2_tma_reduce_add_2d(const CUtensorMap* m, const
 __device__ __forceinline__ void b2_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void b2_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void b2_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void b2_bar1() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-__device__ __forceinline__ void b2_bar2() { asm volatile("bar.sync 2, 512;" ::: "memory"); }
 
 // p & ((a - b) >> 31): keeps p iff a < b.  Opaque PTX: written as C the compiler turns it back into compare + select and parks the predicates
 // of a whole unrolled chunk in a register bit mask (PLOP3 / LOP3 chains, measured in the SASS).
@@ -116,12 +114,12 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* sV = smem + B2_OFF_V;                     // [16 KB]
   uint8_t* sQDO = smem + B2_OFF_QDO;                 // [B2_QST][Q 16 KB | dO 16 KB]
   uint8_t* sDS = smem + B2_OFF_DS;                   // dS^T: [2 query halves][128 key rows][128 B]
-  uint8_t* sDQ = smem + B2_OFF_DQ;                   // [2 column halves][128 rows][128 B] fp32
+  uint8_t* sDQ = smem + B2_OFF_DQ;                   // [16 warps][32 query rows][16 fp32]: one dQ slab per softmax warp
   float* sMeta = reinterpret_cast<float*>(smem + B2_OFF_META);      // [2 buffers][lse2 128 | D 128 | lim 128 (int) | min lim]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BARS);
   uint64_t *k_full = bars /*[2]*/, *k_empty = bars + 2 /*[2]*/, *v_full = bars + 4, *v_empty = bars + 5, *qdo_full = bars + 6 /*[3]*/, *qdo_empty = bars + 9 /*[3]*/,
            *s_full = bars + 12, *dp_full = bars + 13, *s_free = bars + 14, *dp_free = bars + 15, *pt_full = bars + 16, *ds_full = bars + 17, *grad_done = bars + 18,
-           *dq_full = bars + 19, *dq_free = bars + 20, *dkv_full = bars + 21, *dkv_free = bars + 22;
+           *dq_full = bars + 19, *dq_free = bars + 20, *dkv_full = bars + 21, *dkv_free = bars + 22, *meta_full = bars + 26 /*[2]*/;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -132,7 +130,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     mbar_init(v_full, 1); mbar_init(v_empty, 1);
     for (int b = 0; b < B2_QST; ++b) { mbar_init(&qdo_full[b], 1); mbar_init(&qdo_empty[b], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(s_free, 16); mbar_init(pt_full, 16); mbar_init(ds_full, 16); mbar_init(grad_done, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_free, 16); mbar_init(dkv_full, 1); mbar_init(dkv_free, 16);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 16); mbar_init(dkv_full, 1); mbar_init(dkv_free, 16); mbar_init(&meta_full[0], 4); mbar_init(&meta_full[1], 4);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -257,58 +255,59 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), A3 = make_float2(a3, a3), A4 = make_float2(a4, a4),
                  OC = make_float2(oms_c, oms_c), SC = make_float2(scale, scale);
     const int swz_row = (row >> 3) * 1024 + (row & 7) * 128;
-    const bool elected = (warp == 4 && lane == 0);
     uint32_t g = 0;
 
-    // dQ of step g_done: TMEM -> smem -> TMA reduce-add into global (lanes = query rows here; this warp moves 16 of the 64 columns)
+    // dQ of step g_done: TMEM -> this warp's own 2 KB slab ([32 query rows][16 fp32], unswizzled) -> ONE TMA reduce-add per warp into global.
+    // Every warp owns its slab and its bulk group: no CTA-wide barrier on the dQ path (the 8-warp version spent 20 % of its stall cycles in bar.sync).
+    uint8_t* my_dq = sDQ + (warp - 4) * 2048;
     auto dq_readout = [&](uint32_t g_done, int qrow0, int hd) {
       mbar_wait(dq_full, g_done & 1);
       tc_fence_after();
-      if (elected) b2_bulk_wait_read0();             // the previous reduce has finished reading sDQ
-      b2_bar1();
       uint32_t r[16];
       tmem_ld_32x32b_x16(tDQ + lane_addr + qc * 16, r);
+      if (lane == 0) b2_bulk_wait_read0();           // this warp's previous reduce has finished reading the slab
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
-      uint8_t* dst = sDQ + (qc >> 1) * 16384 + swz_row;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(dst + ((((qc & 1) * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+        *reinterpret_cast<uint4*>(my_dq + lane * 64 + ch * 16) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
       fence_proxy_async_smem();
-      b2_bar1();
-      if (elected) {
-        b2_tma_reduce_add_2d(&tmDQ, sDQ, hd * 64, qrow0);
-        b2_tma_reduce_add_2d(&tmDQ, sDQ + 16384, hd * 64 + 32, qrow0);
+      __syncwarp();
+      if (lane == 0) {
+        b2_tma_reduce_add_2d(&tmDQ, my_dq, hd * 64 + qc * 16, qrow0 + quad * 32);
         b2_bulk_commit();
       }
     };
 
-    // per-query statistics of a step: fetched into registers of threads 0..127 (one query each) one step ahead, written to shared memory by stage_meta
+    // per-query statistics of a step: fetched into registers of threads 0..127 (one query each) one step ahead, published in shared memory through
+    // an mbarrier (meta_full): no CTA-wide barrier.  Reuse of a buffer two steps later is ordered by the ds_full -> grad_done chain (every warp
+    // has finished reading step g - 1's statistics before any warp passes the grad_done wait of step g).
     float m_lse = 0.f, m_D = 0.f; int m_lim = -1;
-    auto fetch_meta = [&](const B2Item& im, int i) {
+    auto fetch_meta = [&](int q_begin, int q_end, int head, int i) {
       if (tid < 128) {
-        const int gr = im.q_begin + i * 128 + tid;
-        const bool ok = gr < im.q_end;
+        const int gr = q_begin + i * 128 + tid;
+        const bool ok = gr < q_end;
         m_lim = ok ? kv_limit[gr] : -1;
-        m_lse = ok ? lse[(long long)im.head * M + gr] : 0.f;
-        m_D = ok ? dsum[(long long)im.head * M + gr] : 0.f;
+        m_lse = ok ? lse[(long long)head * M + gr] : 0.f;
+        m_D = ok ? dsum[(long long)head * M + gr] : 0.f;
       }
     };
     auto stage_meta = [&](int buf) {                 // stored negated (the consumers only add) and as limit + 1 (the mask is `key < limit + 1`)
-      float* mb = sMeta + buf * 512;
       if (tid < 128) {
+        float* mb = sMeta + buf * 512;
         mb[tid] = -m_lse * 1.4426950408889634f; mb[128 + tid] = -m_D; reinterpret_cast<int*>(mb)[256 + tid] = m_lim + 1;
         const int wmin = __reduce_min_sync(0xffffffffu, m_lim);
-        if ((tid & 31) == 0) reinterpret_cast<int*>(mb)[384 + (tid >> 5)] = wmin;
+        if (lane == 0) { reinterpret_cast<int*>(mb)[384 + (tid >> 5)] = wmin; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&meta_full[buf]);
       }
     };
 
     B2Item it, nx;
     bool has = b2_item(0, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, it);
-    if (has) { fetch_meta(it, 0); stage_meta(0); }
-    b2_bar2();
+    if (has) { fetch_meta(it.q_begin, it.q_end, it.head, 0); stage_meta(0); }
     int prev_qrow0 = 0, prev_head = 0;
     bool pending = false;
     for (int k = 0; has; ++k) {
@@ -319,7 +318,8 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const float* mb = sMeta + (g & 1) * 512;
         const int* mbi = reinterpret_cast<const int*>(mb);
         // statistics of the NEXT step travel through registers while this one is processed
-        if (i + 1 < it.n_q) fetch_meta(it, i + 1); else if (has_n) fetch_meta(nx, 0);
+        if (i + 1 < it.n_q) fetch_meta(it.q_begin, it.q_end, it.head, i + 1); else if (has_n) fetch_meta(nx.q_begin, nx.q_end, nx.head, 0);
+        mbar_wait(&meta_full[g & 1], (g >> 1) & 1);
         const int min_lim = min(min(mbi[384], mbi[385]), min(mbi[386], mbi[387]));
         const bool all_visible = kv0 + 127 <= min_lim;      // every query of the tile sees every key of the tile: no mask
         // Per 16-query chunk: exponentials from S^T (dP^T of this step may still be in flight), P^T back to TMEM, then dS^T from dP^T.
@@ -379,7 +379,6 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
         prev_qrow0 = it.q_begin + i * 128; prev_head = it.head; pending = true;
         stage_meta((g + 1) & 1);                             // statistics of the next step (fetched above); the buffer was last read in step g - 1
-        b2_bar2();
       }
       // ---- dK (fp32) and dV (bf16) of this key tile: 16 of the 64 columns per warp
       mbar_wait(dkv_full, k & 1);
@@ -409,7 +408,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       it = nx; has = has_n;
     }
     if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
-    if (elected) b2_bulk_wait0();                    // all dQ reductions have been performed before the CTA retires
+    if (lane == 0) b2_bulk_wait0();                  // this warp's dQ reductions have been performed before the CTA retires
   }
 
   tc_fence_before();
@@ -420,16 +419,16 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }  // namespace tfx
 
 namespace tfx {
-// fp32 2-D tensor map with a 32-float (128 B, swizzled) x box_rows box - the destination of the dQ TMA reduce-add
-static int b2_make_tmap_f32_sw128(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
+// fp32 2-D tensor map with a 16-float (64 B, unswizzled) x box_rows box - the destination of the per-warp dQ TMA reduce-add
+static int b2_make_tmap_f32_box16(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 }  // namespace tfx
@@ -450,7 +449,7 @@ int tfx_attn_bwd_ts(const void* q, const void* k, const void* v, const void* do_
   int rc;
   if ((rc = make_tmap_bf16(&tq, q, (long long)H * 64, M, ld_q, 128)) || (rc = make_tmap_bf16(&tk, k, (long long)H * 64, M, ld_k, 128)) ||
       (rc = make_tmap_bf16(&tv, v, (long long)H * 64, M, ld_v, 128)) || (rc = make_tmap_bf16(&tdo, do_pre, (long long)H * 64, M, ld_do, 128)) ||
-      (rc = b2_make_tmap_f32_sw128(&tdq, dq, (long long)H * 64, M, (long long)H * 64, 128))) {
+      (rc = b2_make_tmap_f32_box16(&tdq, dq, (long long)H * 64, M, (long long)H * 64, 32))) {
     set_error("attn_bwd_ts: cuTensorMapEncodeTiled failed (%d)", rc);
     return rc;
   }

@@ -72,6 +72,7 @@ int tfx_gemm_resid(const void* A, long long lda, const void* A2, long long lda2,
   if (M <= 0) return 0;
   TFX_REQUIRE(N % 32 == 0, "gemm_resid: N (%d) must be a multiple of 32", N);
   TFX_REQUIRE(!A2 || K1 % 64 == 0, "gemm_resid: K1 (%d) must be a multiple of 64", K1);
+  TFX_REQUIRE(x_out || x_out_bf16, "gemm_resid: at least one of x_out (fp32) / x_out_bf16 is required");
   GemmParams p; memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.k_splits = 1; p.K1 = A2 ? K1 : K; p.bias = bias;
   p.x_res = x_res; p.x_out = x_out; p.x_out_bf16 = (__nv_bfloat16*)x_out_bf16; p.y_bf16 = (__nv_bfloat16*)y_bf16;

@@ -621,7 +621,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(xrv[j]);
             }
           }
-          // x_out (fp32) leaves in two 16-column passes through the 64-byte-pitch tile
+          // x_out (fp32, optional when only the bf16 copy is kept) leaves in two 16-column passes through the 64-byte-pitch tile
+          if (p.x_out)
 #pragma unroll
           for (int hfc = 0; hfc < 2; ++hfc) {
             uint32_t w16[16];

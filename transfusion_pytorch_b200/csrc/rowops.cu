@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restri
 // ------------------------------------------------------------------------------------ AttentionResidual forward
 // sim_l = <h_l, (gamma+1)*pq> / max(|h_l|, eps)   (sqrt(D) of the RMSNorm cancels the D^-1/2 scale)
 // x = sum_l softmax_l(sim) h_l           (T.py:803-829)   single pass, online softmax over depth.
-template <int NCH>
+template <int NCH, bool HB>
 __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
                                                              float* __restrict__ xo, __nv_bfloat16* __restrict__ xb, float* __restrict__ lse_out, int M) {
   constexpr int D = NCH * 128;
@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
     float m = -INFINITY, l = 0.f;
     for (int k = 0; k < L1; ++k) {
       float h[NCH * 4];
-      load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
+      if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[k]) + (long long)row * D, lane, h);      // bf16 copies of the hiddens: half the read traffic
+      else load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
       float ss = 0.f, dot = 0.f;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; }
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
 // dh_l += alpha_l*dx + dsim_l*(w/|h| - <h,w> h/|h|^3);   dw += dsim_l*h/|h|   (dw -> d gamma, d pq)
 // Single pass over the hiddens: alpha_l = exp(sim_l - lse) uses the log-sum-exp saved by the forward, and the softmax-backward
 // mean  sum_k alpha_k <h_k, dx>  equals <x_out, dx> (x_out is the saved forward output) - so every h_l is read exactly once.
-template <int NCH>
+template <int NCH, bool HB>
 __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd_k(PtrList hid, PtrList dhid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
                                                                 const float* __restrict__ dxo, const float* __restrict__ xo, const float* __restrict__ lse,
                                                                 float* __restrict__ partials, int M, int tpw, int init) {
@@ -274,10 +275,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd_k(PtrList hid, Pt
     for (int i = 0; i < NCH * 4; ++i) mean_da += h[i] * dxv[i];
     mean_da = warp_sum(mean_da);
     const float lse_r = lse[row];
-    load_row_f32<NCH>(hid.p[0] + (long long)row * D, lane, h);
+    if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[0]) + (long long)row * D, lane, h);
+    else load_row_f32<NCH>(hid.p[0] + (long long)row * D, lane, h);
     for (int k = 0; k < L1; ++k) {
       float hn[NCH * 4], g[NCH * 4];
-      if (k + 1 < L1) load_row_f32<NCH>(hid.p[k + 1] + (long long)row * D, lane, hn);      // prefetch the next hidden
+      if (k + 1 < L1) {                                                                    // prefetch the next hidden
+        if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[k + 1]) + (long long)row * D, lane, hn);
+        else load_row_f32<NCH>(hid.p[k + 1] + (long long)row * D, lane, hn);
+      }
       if (!init) load_row_f32<NCH>(dhid.p[k] + (long long)row * D, lane, g);
       else {
 #pragma unroll
@@ -632,34 +637,54 @@ int tfx_resid_bwd(const float* dx, const void* y_bf16, const int* cond_row, cons
   return check_launch("resid_bwd");
 }
 
-int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          float* x_out, void* x_out_bf16, float* lse_out, int M, int D, void* stream) {
+static int attn_residual_fwd_impl(const void* const* hiddens, bool hb, int n_hiddens, const float* gamma, const float* pseudo_query,
+                                  float* x_out, void* x_out_bf16, float* lse_out, int M, int D, void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
   PtrList pl;
-  for (int i = 0; i < n_hiddens; ++i) pl.p[i] = const_cast<float*>(hiddens[i]);
-  TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, lse_out, M)));
+  for (int i = 0; i < n_hiddens; ++i) pl.p[i] = reinterpret_cast<float*>(const_cast<void*>(hiddens[i]));
+  if (hb) TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH, true><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, lse_out, M)));
+  else TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH, false><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, lse_out, M)));
   return check_launch("attn_residual_fwd");
+}
+int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                          float* x_out, void* x_out_bf16, float* lse_out, int M, int D, void* stream) {
+  return attn_residual_fwd_impl(reinterpret_cast<const void* const*>(hiddens), false, n_hiddens, gamma, pseudo_query, x_out, x_out_bf16, lse_out, M, D, stream);
+}
+int tfx_attn_residual_fwd_h16(const void* const* hiddens_bf16, int n_hiddens, const float* gamma, const float* pseudo_query,
+                              float* x_out, void* x_out_bf16, float* lse_out, int M, int D, void* stream) {
+  return attn_residual_fwd_impl(hiddens_bf16, true, n_hiddens, gamma, pseudo_query, x_out, x_out_bf16, lse_out, M, D, stream);
 }
 
 static const int ATTN_RES_BWD_TPW = 4;
 long long tfx_attn_residual_bwd_workspace_floats(int M, int D) { return (long long)chunk_grid(M, ATTN_RES_BWD_TPW) * D; }
 
-int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
-                          const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, int init,
-                          void* stream) {
+static int attn_residual_bwd_impl(const void* const* hiddens, bool hb, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                                  const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, int init,
+                                  void* stream) {
   if (M <= 0) return 0;
   TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
   TFX_REQUIRE(workspace != nullptr, "attn_residual_bwd: workspace of tfx_attn_residual_bwd_workspace_floats(M, D) floats is required");
   PtrList pl, dl;
-  for (int i = 0; i < n_hiddens; ++i) { pl.p[i] = const_cast<float*>(hiddens[i]); dl.p[i] = dhiddens[i]; }
+  for (int i = 0; i < n_hiddens; ++i) { pl.p[i] = reinterpret_cast<float*>(const_cast<void*>(hiddens[i])); dl.p[i] = dhiddens[i]; }
   const int tpw = ATTN_RES_BWD_TPW;
   const int blocks = chunk_grid(M, tpw);
-  TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH><<<blocks, ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, workspace, M, tpw, init)));
+  if (hb) TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH, true><<<blocks, ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, workspace, M, tpw, init)));
+  else TFX_DISPATCH_NCH(D, (attn_res_bwd_k<NCH, false><<<blocks, ROW_THREADS, 0, ST(stream)>>>(pl, dl, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, workspace, M, tpw, init)));
   if (int rc = check_launch("attn_residual_bwd")) return rc;
   const int rpb = 16;
   attn_res_bwd_finish_k<<<dim3((D + 127) / 128, (blocks + rpb - 1) / rpb), 128, 0, ST(stream)>>>(workspace, blocks, D, gamma, pseudo_query, dgamma, dpseudo_query, rpb);
   return check_launch("attn_residual_bwd_finish");
+}
+int tfx_attn_residual_bwd(const float* const* hiddens, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                          const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, int init,
+                          void* stream) {
+  return attn_residual_bwd_impl(reinterpret_cast<const void* const*>(hiddens), false, dhiddens, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, dgamma, dpseudo_query, workspace, M, D, init, stream);
+}
+int tfx_attn_residual_bwd_h16(const void* const* hiddens_bf16, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
+                              const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, int init,
+                              void* stream) {
+  return attn_residual_bwd_impl(hiddens_bf16, true, dhiddens, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, dgamma, dpseudo_query, workspace, M, D, init, stream);
 }
 
 int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream) {

@@ -90,6 +90,8 @@ class Engine:
         self._ptr_arrays = []
         self.launches = 0
         self.graph_pins = None                      # list of retired workspace tensors once any CUDA graph has been captured
+        # bf16 copies of the per-layer hiddens for AttentionResidual (the residual-stream x_c is then ONLY kept in bf16): halves the largest HBM term of the step
+        self.hid_bf16 = os.environ.get('TFX_HIDDEN_BF16', '0') == '1'
         self.bwd_kernel = os.environ.get('TFX_ATTN_BWD', 'ts')      # 'ts' (transposed scores, P^T / dS^T in TMEM) | 'tc' (round-1 kernel)
         self.fwd_kernel = os.environ.get('TFX_ATTN_FWD', 'ts')      # 'ts' (persistent, P in TMEM) | 'tc' (round-1 kernel, kept for A/B timing)
         self.frozen = False                         # True inside a sampling session: parameters cannot change, skip the re-pack check
@@ -431,7 +433,7 @@ class Engine:
         o.embed_assemble(dv['text_id'], self.P('text_embed.weight'), modtok, dv['slot'] if S > 0 else None, x0, x0b, M, D)
 
         # ---- block stack
-        hid = [x0]
+        hid = [x0b if self.hid_bf16 else x0]
         skips = []
         x_in, x_in_b = x0, x0b
         n_tiles = int(rb.tile_q0.shape[0])
@@ -501,13 +503,20 @@ class Engine:
             o.adaln_fwd(x_b, cond_row, filmF, tab_ld, self.P(f'{pre}.2.layernorm_gamma'), uF, statsF, M, D)
             vg = self.buf(f'{lt}vg', (M, 2 * Ip), BF16); h = self.buf(f'{lt}h', (M, Ip), BF16)
             o.gemm_geglu(uF, D, pk[f'w1{i}'], D, pk[f'b1{i}'], M, 2 * Ip, D, vg, h)
-            x_c = self.buf(f'{tag}H{i + 1}', (M, D), F32); yF = self.buf(f'{lt}yF', (M, D), BF16) if train else None
-            o.gemm_resid(h, Ip, None, 0, 0, pk[f'w2{i}'], Ip, M, D, Ip, self.P(f'{pre}.2.fn.net.3.bias'), x_b, x_c, None, yF, cond_row, zgF, zg_ld,
-                         self.P(f'{pre}.2.layerscale'))
+            yF = self.buf(f'{lt}yF', (M, D), BF16) if train else None
+            if self.hid_bf16:                                # x_c feeds nothing but the AttentionResiduals: keep the bf16 copy only
+                x_c = self.buf(f'{tag}Hb{i + 1}', (M, D), BF16)
+                o.gemm_resid(h, Ip, None, 0, 0, pk[f'w2{i}'], Ip, M, D, Ip, self.P(f'{pre}.2.fn.net.3.bias'), x_b, None, x_c, yF, cond_row, zgF, zg_ld,
+                             self.P(f'{pre}.2.layerscale'))
+            else:
+                x_c = self.buf(f'{tag}H{i + 1}', (M, D), F32)
+                o.gemm_resid(h, Ip, None, 0, 0, pk[f'w2{i}'], Ip, M, D, Ip, self.P(f'{pre}.2.fn.net.3.bias'), x_b, x_c, None, yF, cond_row, zgF, zg_ld,
+                             self.P(f'{pre}.2.layerscale'))
             hid.append(x_c)
             xr = self.buf(f'{tag}xr{i}', (M, D), F32); xrb = self.buf(f'{tag}xrb{i}', (M, D), BF16)
             rlse = self.buf(f'{tag}rlse{i}', (M,), F32) if train else None
-            o.attn_residual_fwd(self._ptr_array(hid), len(hid), self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'), xr, xrb, rlse, M, D)
+            (o.attn_residual_fwd_h16 if self.hid_bf16 else o.attn_residual_fwd)(self._ptr_array(hid), len(hid), self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
+                                                                                 xr, xrb, rlse, M, D)
             L.update(xr = xr, rlse = rlse, mixpre = mixpre, o_l = o_l, v_att = v_att)
             L.update(x_a = x_a, uA = uA, statsA = statsA, q = q, k = k, v = v, gates = gates, qk_inv = qk_inv, att = att, lse = lse, yA = yA, x_b = x_b,
                      uF = uF, statsF = statsF, vg = vg, h = h, yF = yF, x_in = x_in, x_in_b = x_in_b, has_skip = has_skip, first_half = first_half)
@@ -710,7 +719,7 @@ class Engine:
             pre = f'transformer.layers.{i}'
             lm = self.layer_maps[i]
             wA, wF = 2 * i, 2 * i + 1
-            o.attn_residual_bwd(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
+            (o.attn_residual_bwd_h16 if self.hid_bf16 else o.attn_residual_bwd)(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
                                 g, L['xr'], L['rlse'], self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), arws, M, D, 1 if i == self.depth - 1 else 0)
             gx = dH[i + 1]                       # complete gradient w.r.t. x_c of this layer; updated in place below
             # -- feed-forward branch

@@ -87,11 +87,7 @@ def cpu_port_tokens_per_s(batch: int, steps: int, warmup: int):
     import torch
     from transfusion_pytorch_b200 import Transfusion, synth
     from oracle.torch_reference import OracleEngine
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        pass
+    cores = usable_cores()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     model = Transfusion(**CTOR, prob_uncond = 0.)
@@ -111,6 +107,24 @@ def cpu_port_tokens_per_s(batch: int, steps: int, warmup: int):
             times_.append(dt)
     ms = 1e3 * statistics.median(times_)
     return batch * SEQ / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def usable_cores():
+    """host threads the CPU arm may really use: the affinity mask, bounded by the cgroup CPU quota (a 128-thread pool on a container with a smaller
+    quota thrashes: measured 15 tokens/s instead of ~400) """
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max':
+            cores = max(1, min(cores, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    # a 128-thread intra-op pool across two NUMA nodes measured SLOWER (15 tokens/s) than 64 threads (~420 tokens/s) on this pool's hosts: one node's worth
+    return min(cores, int(os.environ.get('TFX_CPU_THREADS', 64)))
 
 
 def numa_note():
@@ -348,7 +362,7 @@ def run_b200_arm(args):
                 ms = e0.elapsed_time(e1)
                 d = fam.setdefault(f, dict(ms = 0., flops = 0., bytes = 0., launches = 0))
                 d['ms'] += ms; d['flops'] += fl; d['bytes'] += by; d['launches'] += 1
-                label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else '')      # per kernel instance (entry point + problem shape)
+                label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else f'[K={a[9]}]' if name == 'gemm_resid' else '')      # per kernel instance (entry point + problem shape)
                 k = inst.setdefault(label, dict(ms = 0., flops = 0., bytes = 0., launches = 0, family = f))
                 k['ms'] += ms; k['flops'] += fl; k['bytes'] += by; k['launches'] += 1
         eng.ops.timing = None
@@ -371,6 +385,8 @@ def run_b200_arm(args):
             if k['flops']:
                 a_ = k['flops'] / (k['ms'] / 1e3) / 1e12
                 row.update(bound = 'tensor', achieved = round(a_, 1), unit = 'TFLOP/s', frac = round(a_ / pk['tf_sustained'], 3))
+                if k['bytes']:      # the fused-epilogue GEMMs move fp32 residual rows: their HBM roofline is reported beside the tensor one
+                    row.update(hbm_gbs = round(k['bytes'] / (k['ms'] / 1e3) / 1e9, 1), hbm_frac = round(k['bytes'] / (k['ms'] / 1e3) / 1e9 / pk['hbm'], 3))
             else:
                 a_ = k['bytes'] / (k['ms'] / 1e3) / 1e9
                 row.update(bound = 'hbm', achieved = round(a_, 1), unit = 'GB/s', frac = round(a_ / pk['hbm'], 3))
@@ -385,7 +401,7 @@ def run_b200_arm(args):
                     flops_model = 'un-padded problem sizes (FFN inner 1365, qkvg rows 1544, time-MLP K 513, vocab 390)',
                     families = {f: fam_row(d) for f, d in fam.items()},
                     whole_step_tflops = whole, whole_step_frac = whole / pk['tf_sustained'], whole_step_frac_of_burst = whole / pk['tf_burst'],
-                    kernels = [inst_row(lbl, k) for lbl, k in ranked[:12]])
+                    kernels = [inst_row(lbl, k) for lbl, k in ranked[:16]])
 
     if rank == 0:
         clocks = sampler.summary() if sampler else None
@@ -523,7 +539,7 @@ def cpu_sample_many(args, prompts, noise):
     import torch
     from transfusion_pytorch_b200 import Transfusion, synth
     from oracle.torch_reference import OracleEngine
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(usable_cores())
     torch.manual_seed(0)
     model = Transfusion(**CTOR).eval()
     synth.fill_parameters_(model, seed = 0)

@@ -114,7 +114,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* sV = smem + B2_OFF_V;                     // [16 KB]
   uint8_t* sQDO = smem + B2_OFF_QDO;                 // [B2_QST][Q 16 KB | dO 16 KB]
   uint8_t* sDS = smem + B2_OFF_DS;                   // dS^T: [2 query halves][128 key rows][128 B]
-  uint8_t* sDQ = smem + B2_OFF_DQ;                   // [16 warps][32 query rows][16 fp32]: one dQ slab per softmax warp
+  uint8_t* sDQ = smem + B2_OFF_DQ;                   // [2 column halves][128 rows][128 B] fp32
   float* sMeta = reinterpret_cast<float*>(smem + B2_OFF_META);      // [2 buffers][lse2 128 | D 128 | lim 128 (int) | min lim]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BARS);
   uint64_t *k_full = bars /*[2]*/, *k_empty = bars + 2 /*[2]*/, *v_full = bars + 4, *v_empty = bars + 5, *qdo_full = bars + 6 /*[3]*/, *qdo_empty = bars + 9 /*[3]*/,
@@ -257,26 +257,29 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int swz_row = (row >> 3) * 1024 + (row & 7) * 128;
     uint32_t g = 0;
 
-    // dQ of step g_done: TMEM -> this warp's own 2 KB slab ([32 query rows][16 fp32], unswizzled) -> ONE TMA reduce-add per warp into global.
-    // Every warp owns its slab and its bulk group: no CTA-wide barrier on the dQ path (the 8-warp version spent 20 % of its stall cycles in bar.sync).
-    uint8_t* my_dq = sDQ + (warp - 4) * 2048;
+    // dQ of step g_done: TMEM -> smem -> TMA reduce-add into global (lanes = query rows here; this warp moves 16 of the 64 columns).
+    // (One 2 KB slab + one TMA reduce per warp, without the two CTA barriers, measured SLOWER: 295 vs 273 us - sixteen small reduce operations per step.)
+    const bool elected = (warp == 4 && lane == 0);
     auto dq_readout = [&](uint32_t g_done, int qrow0, int hd) {
       mbar_wait(dq_full, g_done & 1);
       tc_fence_after();
+      if (elected) b2_bulk_wait_read0();             // the previous reduce has finished reading sDQ
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       uint32_t r[16];
       tmem_ld_32x32b_x16(tDQ + lane_addr + qc * 16, r);
-      if (lane == 0) b2_bulk_wait_read0();           // this warp's previous reduce has finished reading the slab
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
+      uint8_t* dst = sDQ + (qc >> 1) * 16384 + swz_row;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(my_dq + lane * 64 + ch * 16) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+        *reinterpret_cast<uint4*>(dst + ((((qc & 1) * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        b2_tma_reduce_add_2d(&tmDQ, my_dq, hd * 64 + qc * 16, qrow0 + quad * 32);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (elected) {
+        b2_tma_reduce_add_2d(&tmDQ, sDQ, hd * 64, qrow0);
+        b2_tma_reduce_add_2d(&tmDQ, sDQ + 16384, hd * 64 + 32, qrow0);
         b2_bulk_commit();
       }
     };
@@ -408,7 +411,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       it = nx; has = has_n;
     }
     if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
-    if (lane == 0) b2_bulk_wait0();                  // this warp's dQ reductions have been performed before the CTA retires
+    if (elected) b2_bulk_wait0();                    // all dQ reductions have been performed before the CTA retires
   }
 
   tc_fence_before();
@@ -419,16 +422,16 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }  // namespace tfx
 
 namespace tfx {
-// fp32 2-D tensor map with a 16-float (64 B, unswizzled) x box_rows box - the destination of the per-warp dQ TMA reduce-add
-static int b2_make_tmap_f32_box16(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
+// fp32 2-D tensor map with a 32-float (128 B, swizzled) x box_rows box - the destination of the dQ TMA reduce-add
+static int b2_make_tmap_f32_sw128(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 }  // namespace tfx
@@ -449,7 +452,7 @@ int tfx_attn_bwd_ts(const void* q, const void* k, const void* v, const void* do_
   int rc;
   if ((rc = make_tmap_bf16(&tq, q, (long long)H * 64, M, ld_q, 128)) || (rc = make_tmap_bf16(&tk, k, (long long)H * 64, M, ld_k, 128)) ||
       (rc = make_tmap_bf16(&tv, v, (long long)H * 64, M, ld_v, 128)) || (rc = make_tmap_bf16(&tdo, do_pre, (long long)H * 64, M, ld_do, 128)) ||
-      (rc = b2_make_tmap_f32_box16(&tdq, dq, (long long)H * 64, M, (long long)H * 64, 32))) {
+      (rc = b2_make_tmap_f32_sw128(&tdq, dq, (long long)H * 64, M, (long long)H * 64, 128))) {
     set_error("attn_bwd_ts: cuTensorMapEncodeTiled failed (%d)", rc);
     return rc;
   }

@@ -50,15 +50,11 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // four hardware-suspended probes per iteration of the bounded spin: the watchdog bookkeeping (counter, compare, branch) is amortised - waiting warps
-  // were spending ~20 % of the issued instructions of the attention kernels on it (ncu, round 2)
+  // bounded spin over the hardware-suspended probe (trap instead of hanging the GPU).  Unrolling four probes per watchdog update was tried to
+  // amortise the counter / compare / branch: 3 % SLOWER on the attention kernels (profiles/r02_attn_bench_v4.log) - kept simple.
   uint32_t spins = 0;
-  for (;;) {
-    if (mbar_try_wait(bar, parity)) return;
-    if (mbar_try_wait(bar, parity)) return;
-    if (mbar_try_wait(bar, parity)) return;
-    if (mbar_try_wait(bar, parity)) return;
-    if (++spins > TFX_SPIN_LIMIT / 4) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > TFX_SPIN_LIMIT) {
       printf("tfx: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }

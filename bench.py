@@ -351,6 +351,7 @@ def run_b200_arm(args):
     profiling[0] = True
     if rank == 0:
         eng.ops.timing = {}
+        eng.ops.order = [] if args.dump_launches else None
     step_resident(0)
     barrier()
     if rank == 0:
@@ -365,7 +366,14 @@ def run_b200_arm(args):
                 label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else f'[K={a[9]}]' if name == 'gemm_resid' else '')      # per kernel instance (entry point + problem shape)
                 k = inst.setdefault(label, dict(ms = 0., flops = 0., bytes = 0., launches = 0, family = f))
                 k['ms'] += ms; k['flops'] += fl; k['bytes'] += by; k['launches'] += 1
+        if args.dump_launches:      # entry points of the profiled step in launch order, with the labels of the roofline table (tools/ncu_traffic.py aligns an ncu capture with it)
+            seen, labels = {}, []
+            for name in eng.ops.order:
+                a = eng.ops.timing[name][seen.get(name, 0)][2]; seen[name] = seen.get(name, 0) + 1
+                labels.append(name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else f'[K={a[9]}]' if name == 'gemm_resid' else ''))
+            json.dump(dict(key = f'{args.workload}:b{B}', launches = labels), open(args.dump_launches, 'w'))
         eng.ops.timing = None
+        eng.ops.order = None
         pk = peaks()
         tot = sum(d['ms'] for d in fam.values())
         top = max((f for f in fam if fam[f]['flops'] > 0), key = lambda f: fam[f]['ms'])
@@ -569,6 +577,7 @@ def main():
     ap.add_argument('--scaling', default = 'weak', choices = ['weak', 'strong'], help = 'strong: --batch is the global batch (fixed total work as N grows)')
     ap.add_argument('--no-overlap', action = 'store_true', help = 'N > 1: one all-reduce after backward instead of per-layer buckets overlapped with it')
     ap.add_argument('--no-cpu-baseline', action = 'store_true')
+    ap.add_argument('--dump-launches', default = None, help = 'write the entry points of the profiled step in launch order (JSON) - input of tools/ncu_traffic.py')
     ap.add_argument('--no-graph', action = 'store_true', help = 'eager kernel launches instead of CUDA-graph replay (N = 1)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -132,6 +132,7 @@ class Ops:
         self._torch = torch
         self.launches = 0            # kernels launched through the C ABI (every entry point launches exactly one)
         self.timing = None           # when a dict: name -> list of (start_event, end_event), filled per call
+        self.order = None            # when a list (and timing is on): entry-point names in launch order
 
     def stream(self):
         return self._torch.cuda.current_stream().cuda_stream
@@ -156,6 +157,8 @@ class Ops:
                 rc = fn(*conv, self.stream())
                 e1.record()
                 self.timing.setdefault(name, []).append((e0, e1, args))
+                if self.order is not None:
+                    self.order.append(name)
             else:
                 rc = fn(*conv, self.stream())
             if rc != 0:

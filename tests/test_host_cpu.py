@@ -196,7 +196,7 @@ def test_pack_is_the_host_half_of_forward_and_tile_tables_cover_the_mask():
         rows = np.arange(rb.cu[b], rb.cu[b + 1])
         first = rows[rb.kv_limit[rows] >= k0].min()                  # first query of the sequence that sees a key of this tile
         assert ke - k0 <= 128 and q0 <= first and (q0 - rb.cu[b]) % 128 == 0 and qe == rb.cu[b + 1]
-    work = (rb.k2_qend - rb.k2_q0)[rb.k2_order]
+    work = (rb.k2_qend - rb.k2_q0)[rb.k2_order]           # one L2-locality group here (< 8192 tokens): heaviest first
     assert sorted(rb.k2_order.tolist()) == list(range(len(rb.k2_kv0))) and (np.diff(work) <= 0).all()
     # forward work items of the persistent kernel: pairs of adjacent 128-row tiles of ONE sequence, every tile exactly once, heaviest pair first
     first, has_b = rb.p2 >> 1, rb.p2 & 1

@@ -23,9 +23,18 @@ __global__ void __launch_bounds__(ROW_THREADS) adaln_fwd_k(const float* __restri
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   float gv[NCH * 4];
   load_row_f32<NCH>(g, lane, gv);
+  // the condition row of the NEXT token is fetched one iteration ahead, so that the FiLM rows (whose address depends on it) are requested together with
+  // the token itself instead of one global-load latency later (half of the tokens are modality tokens: 0.61 -> of the HBM roof before)
+  int cr_next = (cond_row && warp0 < M) ? cond_row[warp0] : -1;
   for (int row = warp0; row < M; row += nwarps) {
-    float v[NCH * 4];
+    const int cr = cr_next;
+    float v[NCH * 4], gm[NCH * 4], bt[NCH * 4];
     load_row_f32<NCH>(x + (long long)row * D, lane, v);
+    if (cr >= 0) {
+      load_row_f32<NCH>(film + cr * film_ld, lane, gm);
+      load_row_f32<NCH>(film + cr * film_ld + D, lane, bt);
+    }
+    cr_next = (cond_row && row + nwarps < M) ? cond_row[row + nwarps] : -1;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) s += v[i];
@@ -34,11 +43,7 @@ __global__ void __launch_bounds__(ROW_THREADS) adaln_fwd_k(const float* __restri
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) { v[i] -= mean; q += v[i] * v[i]; }
     const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
-    const int cr = cond_row ? cond_row[row] : -1;
     if (cr >= 0) {
-      float gm[NCH * 4], bt[NCH * 4];
-      load_row_f32<NCH>(film + cr * film_ld, lane, gm);
-      load_row_f32<NCH>(film + cr * film_ld + D, lane, bt);
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) v[i] = v[i] * rstd * (gm[i] + 1.f) + bt[i];
     } else {
@@ -224,10 +229,14 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) acc[i] = 0.f;
     float m = -INFINITY, l = 0.f;
+    float h[NCH * 4], hn[NCH * 4];
+    auto load_h = [&](int k, float (&dst)[NCH * 4]) {
+      if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[k]) + (long long)row * D, lane, dst);      // bf16 copies of the hiddens: half the read traffic
+      else load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, dst);
+    };
+    load_h(0, h);
     for (int k = 0; k < L1; ++k) {
-      float h[NCH * 4];
-      if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[k]) + (long long)row * D, lane, h);      // bf16 copies of the hiddens: half the read traffic
-      else load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
+      if (k + 1 < L1) load_h(k + 1, hn);               // the next hidden is requested before this one's reductions (the depth softmax is a serial chain)
       float ss = 0.f, dot = 0.f;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; }
@@ -238,6 +247,10 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
       l = l * a + b; m = mn;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) acc[i] = acc[i] * a + h[i] * b;
+      if (k + 1 < L1) {
+#pragma unroll
+        for (int i = 0; i < NCH * 4; ++i) h[i] = hn[i];
+      }
     }
     const float inv = 1.f / l;
 #pragma unroll

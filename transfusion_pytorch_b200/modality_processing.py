@@ -126,6 +126,9 @@ def _neg_ids(n: int):
     return _NEG[:n]
 
 
+ATT_GROUP_TOKENS = 8192          # L2-locality group of the attention work lists (8 k tokens x (q, k, v, dO) bf16 x 512 = 32 MB of the 126 MB L2)
+
+
 def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
     """Attention tile tables; tiles never straddle a sequence.  Forward: per query tile the key range [kv0, kv_end) it can see;
     backward: per key tile the query range [q0, q_end) that can see it.  Built for 64-row tiles (general mma.sync kernels) and
@@ -156,13 +159,17 @@ def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
                           (f'{pre_k}_kv0', q0), (f'{pre_k}_kvend', qe), (f'{pre_k}_q0', kq0), (f'{pre_k}_qend', s + lens[seq])):
             setattr(rb, name, as32(arr))
         if pre_k == 'k2':
-            rb.k2_order = as32(np.argsort(-(s + lens[seq] - kq0), kind = 'stable'))
+            # work order of the persistent kernels: heaviest first INSIDE groups of ~8 k consecutive tokens, group after group.  A global cost sort
+            # (round 1) spreads the items of one sequence over the whole launch: its Q / dO (backward) and K / V (forward) tiles were then re-read from
+            # HBM by every item (ncu: 2.4x / 2.0x the algorithmic bytes, profiles/r02_traffic.json); grouped, they are still in the 126 MB L2.
+            group = s // ATT_GROUP_TOKENS
+            rb.k2_order = as32(np.lexsort((-(s + lens[seq] - kq0), group)))
             # forward work items: tiles (2i, 2i+1) of a sequence share their K / V stream; cost = key tiles of both
             nkv = (kve - s + T - 1) // T
             first_of_pair = np.nonzero(tin % 2 == 0)[0]
             has_b = (tin[first_of_pair] + 1) < ntiles[seq[first_of_pair]]
             cost = nkv[first_of_pair] + np.where(has_b, nkv[np.minimum(first_of_pair + 1, total - 1)], 0)
-            order = np.argsort(-cost, kind = 'stable')
+            order = np.lexsort((-cost, group[first_of_pair]))
             rb.p2 = as32(first_of_pair[order] * 2 + has_b[order])
 
 

@@ -229,14 +229,11 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) acc[i] = 0.f;
     float m = -INFINITY, l = 0.f;
-    float h[NCH * 4], hn[NCH * 4];
-    auto load_h = [&](int k, float (&dst)[NCH * 4]) {
-      if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[k]) + (long long)row * D, lane, dst);      // bf16 copies of the hiddens: half the read traffic
-      else load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, dst);
-    };
-    load_h(0, h);
+    // (prefetching the next hidden into a second register set was measured SLOWER - 338 vs 255 us: 88 registers halve the resident warps)
     for (int k = 0; k < L1; ++k) {
-      if (k + 1 < L1) load_h(k + 1, hn);               // the next hidden is requested before this one's reductions (the depth softmax is a serial chain)
+      float h[NCH * 4];
+      if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[k]) + (long long)row * D, lane, h);      // bf16 copies of the hiddens: half the read traffic
+      else load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
       float ss = 0.f, dot = 0.f;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; }
@@ -247,10 +244,6 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
       l = l * a + b; m = mn;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) acc[i] = acc[i] * a + h[i] * b;
-      if (k + 1 < L1) {
-#pragma unroll
-        for (int i = 0; i < NCH * 4; ++i) h[i] = hn[i];
-      }
     }
     const float inv = 1.f / l;
 #pragma unroll

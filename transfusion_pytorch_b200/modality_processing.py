@@ -162,7 +162,9 @@ def build_tiles(rb: RaggedBatch, qfirst: np.ndarray) -> None:
             # work order of the persistent kernels: heaviest first INSIDE groups of ~8 k consecutive tokens, group after group.  A global cost sort
             # (round 1) spreads the items of one sequence over the whole launch: its Q / dO (backward) and K / V (forward) tiles were then re-read from
             # HBM by every item (ncu: 2.4x / 2.0x the algorithmic bytes, profiles/r02_traffic.json); grouped, they are still in the 126 MB L2.
-            group = s // ATT_GROUP_TOKENS
+            # (small batches keep the global sort: with fewer than ~12 groups the static snake schedule loses more to imbalance - 127 vs 111 us at 32 k
+            # tokens - than locality gains, and most of their working set fits the L2 anyway)
+            group = s // ATT_GROUP_TOKENS if rb.M >= 12 * ATT_GROUP_TOKENS else np.zeros_like(s)
             rb.k2_order = as32(np.lexsort((-(s + lens[seq] - kq0), group)))
             # forward work items: tiles (2i, 2i+1) of a sequence share their K / V stream; cost = key tiles of both
             nkv = (kve - s + T - 1) // T

@@ -24,6 +24,12 @@
 #include "../../include/tfx_b200.h"
 #include <limits.h>
 
+// Ablation hooks (tools/bench_attn.py with TFX_LIB=<variant library>; compiled out of the product build): bit 0 no dQ path, bit 1 no dS math, bit 2 no exp math,
+// bit 3 no dV / dK products, bit 4 no S^T / dP^T products
+#ifndef B2_VARIANT
+#define B2_VARIANT 0
+#endif
+
 namespace tfx {
 
 int num_sms();
@@ -119,7 +125,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BARS);
   uint64_t *k_full = bars /*[2]*/, *k_empty = bars + 2 /*[2]*/, *v_full = bars + 4, *v_empty = bars + 5, *qdo_full = bars + 6 /*[3]*/, *qdo_empty = bars + 9 /*[3]*/,
            *s_full = bars + 12, *dp_full = bars + 13, *s_free = bars + 14, *dp_free = bars + 15, *pt_full = bars + 16, *ds_full = bars + 17, *grad_done = bars + 18,
-           *dq_full = bars + 19, *dq_free = bars + 20, *dkv_full = bars + 21, *dkv_free = bars + 22, *meta_full = bars + 26 /*[2]*/;
+           *dq_full = bars + 19, *dq_free = bars + 20, *dkv_full = bars + 21, *dkv_free = bars + 22, *meta_full = bars + 26 /*[2]*/, *dq_staged = bars + 28, *dq_slab_free = bars + 29;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -131,6 +137,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int b = 0; b < B2_QST; ++b) { mbar_init(&qdo_full[b], 1); mbar_init(&qdo_empty[b], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(s_free, 16); mbar_init(pt_full, 16); mbar_init(ds_full, 16); mbar_init(grad_done, 1);
     mbar_init(dq_full, 1); mbar_init(dq_free, 16); mbar_init(dkv_full, 1); mbar_init(dkv_free, 16); mbar_init(&meta_full[0], 4); mbar_init(&meta_full[1], 4);
+    mbar_init(dq_staged, 16); mbar_init(dq_slab_free, 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -184,6 +191,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (ga >= 1) mbar_wait(s_free, (ga - 1) & 1);
         tc_fence_after();
         const uint32_t aQ = smem_u32(sQDO + b * 32768), aK = smem_u32(sK + kvb * 16384);
+        if (!(B2_VARIANT & 16))
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_ss(tS, umma_smem_desc_sw128(aK + kk * 32, 0, 1024), umma_smem_desc_sw128(aQ + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
@@ -194,6 +202,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (ia_i == 0) mbar_wait(v_full, ka & 1);
         tc_fence_after();
         const uint32_t aDO = smem_u32(sQDO + b * 32768 + 16384), aV = smem_u32(sV);
+        if (!(B2_VARIANT & 16))
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_ss(tDP, umma_smem_desc_sw128(aV + kk * 32, 0, 1024), umma_smem_desc_sw128(aDO + kk * 32, 0, 1024), idS, kk > 0 ? 1u : 0u);
@@ -213,16 +222,19 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_wait(pt_full, gb & 1);
         if (ib_i == 0 && kb_ >= 1) mbar_wait(dkv_free, (kb_ - 1) & 1);     // the previous item's dK / dV have been read out of TMEM
         tc_fence_after();
+        if (!(B2_VARIANT & 8))
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq)               // contraction over the 128 queries
           umma_bf16_ts(tDV, tPT + kq * 8, umma_smem_desc_sw128(aDO + kq * 2048, 8192, 1024), idT, (ib_i > 0 || kq > 0) ? 1u : 0u);
         // ---- dK(gb) += dS^T Q ;  dQ(gb) = dS K
         mbar_wait(ds_full, gb & 1);
         tc_fence_after();
+        if (!(B2_VARIANT & 8))
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq)
           umma_bf16_ts(tDK, tDP + (kq >> 1) * 32 + (kq & 1) * 8, umma_smem_desc_sw128(aQ + kq * 2048, 8192, 1024), idT, (ib_i > 0 || kq > 0) ? 1u : 0u);      // dS^T of query quarter qc sits at dP^T + qc * 32 + [0, 16)
-        if (gb >= 1) { mbar_wait(dq_free, (gb - 1) & 1); tc_fence_after(); }
+        if (!(B2_VARIANT & 1)) if (gb >= 1) { mbar_wait(dq_free, (gb - 1) & 1); tc_fence_after(); }
+        if (!(B2_VARIANT & 1))
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)               // contraction over the 128 keys (rows of the dS^T tile)
           umma_bf16_ss(tDQ, umma_smem_desc_sw128(aDS + kk * 2048, 16384, 1024), umma_smem_desc_sw128(aK + kk * 2048, 8192, 1024), idQ, kk > 0 ? 1u : 0u);
@@ -238,6 +250,23 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         if (has_a) issue_dP();                      // dP^T of the next step (its TMEM columns held dS^T of this one until dK above)
       }
+    }
+  } else if (warp == 2) {
+    // ===================================================== dQ store lane: one TMA reduce-add pair per step, issued when all softmax warps have staged their columns
+    if (lane == 0 && !(B2_VARIANT & 1)) {
+      B2Item it;
+      uint32_t g = 0;
+      for (int k = 0; b2_item(k, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, it); ++k) {
+        for (int i = 0; i < it.n_q; ++i, ++g) {
+          mbar_wait(dq_staged, g & 1);
+          b2_tma_reduce_add_2d(&tmDQ, sDQ, it.head * 64, it.q_begin + i * 128);
+          b2_tma_reduce_add_2d(&tmDQ, sDQ + 16384, it.head * 64 + 32, it.q_begin + i * 128);
+          b2_bulk_commit();
+          b2_bulk_wait_read0();
+          mbar_arrive(dq_slab_free);
+        }
+      }
+      b2_bulk_wait0();                              // all dQ reductions have been performed before the CTA retires
     }
   } else if (warp >= 4) {
     // ===================================================== softmax / gradient warps (thread <-> key row x 32 queries)
@@ -257,16 +286,15 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int swz_row = (row >> 3) * 1024 + (row & 7) * 128;
     uint32_t g = 0;
 
-    // dQ of step g_done: TMEM -> smem -> TMA reduce-add into global (lanes = query rows here; this warp moves 16 of the 64 columns).
-    // (One 2 KB slab + one TMA reduce per warp, without the two CTA barriers, measured SLOWER: 295 vs 273 us - sixteen small reduce operations per step.)
-    const bool elected = (warp == 4 && lane == 0);
+    // dQ of step g_done: TMEM -> the shared staging tile; warp 2 (otherwise idle) issues the TMA reduce-add once all 16 warps have staged their columns.
+    // Hand-offs are mbarriers (dq_slab_free / dq_staged): the 8-warp version's two CTA-wide named barriers per step were 20 % of its stall cycles, and
+    // one small reduce per warp (no hand-off at all) was slower than two 16 KB reduces (295 vs 273 us).
     auto dq_readout = [&](uint32_t g_done, int qrow0, int hd) {
       mbar_wait(dq_full, g_done & 1);
       tc_fence_after();
-      if (elected) b2_bulk_wait_read0();             // the previous reduce has finished reading sDQ
-      asm volatile("bar.sync 1, 512;" ::: "memory");
       uint32_t r[16];
       tmem_ld_32x32b_x16(tDQ + lane_addr + qc * 16, r);
+      if (g_done > 0) mbar_wait(dq_slab_free, (g_done - 1) & 1);      // the previous reduce has finished reading the staging tile
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -276,12 +304,9 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int ch = 0; ch < 4; ++ch)
         *reinterpret_cast<uint4*>(dst + ((((qc & 1) * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (elected) {
-        b2_tma_reduce_add_2d(&tmDQ, sDQ, hd * 64, qrow0);
-        b2_tma_reduce_add_2d(&tmDQ, sDQ + 16384, hd * 64 + 32, qrow0);
-        b2_bulk_commit();
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_staged);
+      (void)qrow0; (void)hd;
     };
 
     // per-query statistics of a step: fetched into registers of threads 0..127 (one query each) one step ahead, published in shared memory through
@@ -340,7 +365,10 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             tmem_ld_wait();
             if (c == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(s_free); }      // S^T is in registers: S^T of the next step may be issued
             // the visibility mask is only needed on diagonal / span-boundary tiles: two specialised code paths (see attention_fwd_sm100.cu)
-            if (all_visible) b2_exp_chunk<false>(rs, mb + col0, mbi + 256 + col0, key, A0, A1, A2, A3, A4, ee, wp);
+            if (B2_VARIANT & 4) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { wp[j] = rs[2 * j] ^ rs[2 * j + 1]; ee[j] = make_float2(__uint_as_float(rs[2 * j]), __uint_as_float(rs[2 * j + 1])); }
+            } else if (all_visible) b2_exp_chunk<false>(rs, mb + col0, mbi + 256 + col0, key, A0, A1, A2, A3, A4, ee, wp);
             else b2_exp_chunk<true>(rs, mb + col0, mbi + 256 + col0, key, A0, A1, A2, A3, A4, ee, wp);
           }
           if (c == 0 && g > 0) { mbar_wait(grad_done, (g - 1) & 1); tc_fence_after(); }    // dV / dK / dQ of the previous step have consumed P^T, dS^T (TMEM and smem)
@@ -355,6 +383,10 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           uint32_t rp[16];
           tmem_ld_32x32b_x16(tDP + lane_addr + col0, rp);
           tmem_ld_wait();
+          if (B2_VARIANT & 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wd[c * 8 + j] = rp[2 * j] ^ rp[2 * j + 1] ^ wp[j] ^ __float_as_uint(ee[j].x);
+          } else
 #pragma unroll
           for (int e2 = 0; e2 < 16; e2 += 2) {
             const int j = e2 >> 1;
@@ -379,7 +411,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
-        if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
+        if (pending && !(B2_VARIANT & 1)) dq_readout(g - 1, prev_qrow0, prev_head);
         prev_qrow0 = it.q_begin + i * 128; prev_head = it.head; pending = true;
         stage_meta((g + 1) & 1);                             // statistics of the next step (fetched above); the buffer was last read in step g - 1
       }
@@ -410,8 +442,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       it = nx; has = has_n;
     }
-    if (pending) dq_readout(g - 1, prev_qrow0, prev_head);
-    if (elected) b2_bulk_wait0();                    // all dQ reductions have been performed before the CTA retires
+    if (pending && !(B2_VARIANT & 1)) dq_readout(g - 1, prev_qrow0, prev_head);
   }
 
   tc_fence_before();

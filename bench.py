@@ -149,7 +149,7 @@ def run_reference_arm(args):
                 cpu_baseline = dict(value = tps, unit = 'tokens/s', cores = cores, kind = 'port',
                                     sample = f'{b} sequences x {SEQ} tokens per step, fwd+bwd+Adam, fp32, median of {steps} timed steps after {warm} warm-up; {numa_note()}'),
                 e2e = dict(value = tps, unit = 'tokens/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0))
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
@@ -190,6 +190,7 @@ def family_model(name, args_, eng, rb):
     elif name == 'adaln_bwd': by = M * (4 * D + 4 * D + 8 * D + 8)
     elif name == 'resid_bwd': by = M * (4 * D + 2 * D + 2 * D) if a[1] is not None else M * (4 * D + 2 * D)
     elif name == 'attn_residual_fwd': by = M * (a[1] * 4 * D + 4 * D + 2 * D)
+    elif name == 'attn_residual_bwd2': by = M * (a[1] * 2 * D * a[2] + a[7] * 4 * D + (8 * D if a[2] else 0) + 4 * D)
     elif name == 'attn_residual_fwd_h16': by = M * (a[1] * 2 * D + 4 * D + 2 * D)
     elif name == 'attn_residual_bwd_h16': by = M * (a[2] * 2 * D + a[2] * (4 * D if a[-1] else 8 * D) + 8 * D)
     elif name == 'attn_residual_bwd': by = M * (a[2] * 4 * D + a[2] * (4 * D if a[-1] else 8 * D) + 8 * D)
@@ -363,14 +364,14 @@ def run_b200_arm(args):
                 ms = e0.elapsed_time(e1)
                 d = fam.setdefault(f, dict(ms = 0., flops = 0., bytes = 0., launches = 0))
                 d['ms'] += ms; d['flops'] += fl; d['bytes'] += by; d['launches'] += 1
-                label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else f'[K={a[9]}]' if name == 'gemm_resid' else '')      # per kernel instance (entry point + problem shape)
+                label = name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else f'[K={a[9]}]' if name == 'gemm_resid' else '[assemble]' if (name == 'attn_residual_bwd2' and not a[2]) else '')      # per kernel instance (entry point + problem shape)
                 k = inst.setdefault(label, dict(ms = 0., flops = 0., bytes = 0., launches = 0, family = f))
                 k['ms'] += ms; k['flops'] += fl; k['bytes'] += by; k['launches'] += 1
         if args.dump_launches:      # entry points of the profiled step in launch order, with the labels of the roofline table (tools/ncu_traffic.py aligns an ncu capture with it)
             seen, labels = {}, []
             for name in eng.ops.order:
                 a = eng.ops.timing[name][seen.get(name, 0)][2]; seen[name] = seen.get(name, 0) + 1
-                labels.append(name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else f'[K={a[9]}]' if name == 'gemm_resid' else ''))
+                labels.append(name + (f'[M={a[6]},N={a[7]},K={a[8]}]' if name == 'gemm_store' else f'[K={a[9]}]' if name == 'gemm_resid' else '[assemble]' if (name == 'attn_residual_bwd2' and not a[2]) else ''))
             json.dump(dict(key = f'{args.workload}:b{B}', launches = labels), open(args.dump_launches, 'w'))
         eng.ops.timing = None
         eng.ops.order = None
@@ -433,7 +434,7 @@ def run_b200_arm(args):
                                host_ms_per_step = round(sum(host_e2e[-e2e_steps:]) / e2e_steps, 3)),
                     gpu_launches = int(launches), host_enqueue_ms_per_step = round(host_enqueue_ms, 3), clocks = clocks, roofline = roof, cpu_baseline = cpu,
                     replica_checksum_spread = spread)
-        print(json.dumps(line))
+        emit(line)
         sys.stdout.flush()
     if world > 1:
         # captured graphs hold NCCL work: drop them and drain the device before the process group goes away.  The destructor has been
@@ -537,7 +538,7 @@ def run_sample_many(args):
                 roofline = dict(bound = 'hbm', kernel = 'attn_decode (text loop, kv read)', achieved = None, peak = pk['hbm'], unit = 'GB/s', frac = None,
                                 traffic = None, kv_bytes_text_loop = int(kv_bytes), note = 'the text loop is launch / latency bound at 32 samples: see text_loop_ms'),
                 clocks = sampler.summary(), cpu_baseline = cpu)
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_sample_many(args, prompts, noise):
@@ -564,7 +565,27 @@ def cpu_sample_many(args, prompts, noise):
                 sample = f'4 prompts, forced 256x384 modality with 4 midpoint steps (6 evaluations x cond/uncond), 24 greedy text tokens: {n_gen} generated positions in {dt:.1f} s')
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line of the contract goes to the process's ORIGINAL stdout; everything else that libraries print on file descriptor 1 (the NCCL version
+    banner is written there whatever NCCL_DEBUG_FILE says) has been routed to stderr by `claim_stdout`"""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
+def claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type = int, default = 1)
     ap.add_argument('--steps', type = int, default = 10)

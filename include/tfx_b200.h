@@ -107,6 +107,16 @@ int tfx_qk_bwd_pack(const float* dq, const float* dk, const void* q_bf16, const 
                     const int* rope_pos, const float* rope_cs, const float* gates, const float* dsum_mh, void* dqkvg_bf16, long long out_ld,
                     float* dq_gamma, float* dk_gamma, int M, int H, void* stream);
 
+/* AttentionResidual backward with DEFERRED assembly (exact; rowops.cu): instead of read-modify-writing the gradient of every earlier hidden at every layer, layer i
+ * stores three scalars per (token, hidden) and the complete gradient of ONE hidden is assembled when the backward pass needs it:
+ *   G_k = sum_{i' >= k-1} [a_{i',k} dx_{i'} + c1_{i',k} w_{i'}] - (sum c2_{i',k}) h_k.
+ * own = 1: layer with hiddens h_0..h_{n-1}; writes the scalars of h_0..h_{n-2} to scalars_out[token][k][3] (row stride scalar_stride floats), the parameter gradients,
+ * and grad_hidden = G_{n-1} from its own term plus the n_later later layers (dx_later[j], scalars_later[j] -> element [token 0][k = n-1][0], gammas / pseudo_queries[1 + j]).
+ * own = 0: assembly only (gammas[0] / pseudo_queries[0] unused): the gradient of h_0 after the first layer. */
+int tfx_attn_residual_bwd2(const void* const* hiddens_bf16, int n_hiddens, int own, const float* const* gammas, const float* const* pseudo_queries,
+                           const float* const* dx_later, const float* const* scalars_later, int n_later, const float* dx_out, const float* x_out, const float* lse,
+                           float* grad_hidden, float* scalars_out, int scalar_stride, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, void* stream);
+
 /* ---------------------------------------------------------------- optional attention variants (attn_variants.cu), HBM-bound row kernels
  * LASER (T.py:981-983, 1021-1022): v' = exp(c tanh(v / c)) before the attention, att = log(o') * sigmoid(gate) after it; `rows` (optional) maps token m to its
  * kv-cache row (raw values stay in the cache, T.py:976-977; the transformed copy is a second slab).  Backward: tfx_laser_bwd_prep replaces tfx_attn_bwd_prep

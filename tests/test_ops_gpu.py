@@ -626,3 +626,47 @@ def test_ode_kernels_follow_the_midpoint_rule(ops):
         w = w + dt * f(t0.item() + 0.5 * dt, w + 0.5 * dt * k1)
     torch.cuda.synchronize()
     assert torch.allclose(y, w, atol = 1e-5, rtol = 1e-5)
+
+def test_attn_residual_deferred_backward_chain_vs_autograd(ops):
+    """tfx_attn_residual_bwd2: a stack of 4 AttentionResiduals over 5 hiddens (layer i mixes h_0..h_{i+1}), loss = sum_i <x_i, R_i>.  The deferred kernels
+    assemble the COMPLETE gradient of each hidden once (own layer + stored scalars of the later layers) and must equal autograd's sum over layers."""
+    import ctypes
+    M, D, depth = 700, 512, 4
+    g = torch.Generator(device = 'cuda').manual_seed(11)
+    hid = [torch.randn(M, D, device = 'cuda', generator = g).to(BF16).float().requires_grad_(True) for _ in range(depth + 1)]
+    gams = [(torch.randn(D, device = 'cuda', generator = g) * 0.3).requires_grad_(True) for _ in range(depth)]
+    pqs = [(torch.randn(D, device = 'cuda', generator = g) * 0.5).requires_grad_(True) for _ in range(depth)]
+    R = [torch.randn(M, D, device = 'cuda', generator = g) for _ in range(depth)]
+    loss = 0.
+    for i in range(depth):
+        vals = torch.stack(hid[:i + 2])
+        keys = torch.nn.functional.normalize(vals, dim = -1) * D ** 0.5 * (gams[i] + 1)
+        sim = torch.einsum('lnd,d->nl', keys, pqs[i]) * D ** -0.5
+        loss = loss + (torch.einsum('nl,lnd->nd', sim.softmax(-1), vals) * R[i]).sum()
+    loss.backward()
+    hb = [h.detach().to(BF16) for h in hid]
+    keep = []
+    def parr(ts):
+        a = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts]); keep.append(a)
+        return ctypes.cast(a, ctypes.c_void_p)
+    xo = [torch.zeros(M, D, device = 'cuda') for _ in range(depth)]; lse = [torch.zeros(M, device = 'cuda') for _ in range(depth)]
+    for i in range(depth):
+        ops.attn_residual_fwd_h16(parr(hb[:i + 2]), i + 2, gams[i].detach(), pqs[i].detach(), xo[i], None, lse[i], M, D)
+    stride = (depth + 2) * 3
+    sc = torch.zeros(depth, M, depth + 2, 3, device = 'cuda')
+    G = [torch.full((M, D), 7., device = 'cuda') for _ in range(depth + 1)]
+    dgam = [torch.zeros(D, device = 'cuda') for _ in range(depth)]; dpq = [torch.zeros(D, device = 'cuda') for _ in range(depth)]
+    ws = torch.zeros(int(ops.lib.tfx_attn_residual_bwd_workspace_floats(M, D)), device = 'cuda')
+    gd, pd = [t.detach() for t in gams], [t.detach() for t in pqs]
+    for i in reversed(range(depth)):
+        later = list(range(i + 1, depth))
+        ops.attn_residual_bwd2(parr(hb[:i + 2]), i + 2, 1, parr([gd[j] for j in [i] + later]), parr([pd[j] for j in [i] + later]), parr([R[j] for j in later] or [R[i]]),
+                               parr([sc[j][0, i + 1] for j in later] or [R[i]]), len(later), R[i], xo[i], lse[i], G[i + 1], sc[i], stride, dgam[i], dpq[i], ws, M, D)
+    allj = list(range(depth))
+    ops.attn_residual_bwd2(parr(hb[:1]), 1, 0, parr([gd[0]] + gd), parr([pd[0]] + pd), parr(R), parr([sc[j][0, 0] for j in allj]), depth, None, None, None, G[0], None, stride, None, None, None, M, D)
+    torch.cuda.synchronize()
+    for k in range(depth + 1):
+        err = (G[k] - hid[k].grad).abs().max().item() / hid[k].grad.abs().max().item()
+        assert err < 2e-3, (k, err)
+    for i in range(depth):
+        assert torch.allclose(dgam[i], gams[i].grad, atol = 5e-3, rtol = 1e-2) and torch.allclose(dpq[i], pqs[i].grad, atol = 5e-3, rtol = 1e-2), i

@@ -9,7 +9,7 @@ The last step of the capture (the launches between the last two fused-Adam kerne
 launches exactly one `tfx::` kernel, except the ones listed in EXTRA."""
 import collections, csv, json, re, sys
 
-EXTRA = {'attn_residual_bwd': 2, 'attn_residual_bwd_h16': 2}          # main kernel + the parameter-gradient finish kernel
+EXTRA = {'attn_residual_bwd': 2, 'attn_residual_bwd_h16': 2, 'attn_residual_bwd2': 2}          # (the assembly-only call of bwd2 launches one kernel: handled below)          # main kernel + the parameter-gradient finish kernel
 
 def main(csv_path, order_path, out_path):
     rows = list(csv.reader(open(csv_path, errors = 'replace')))
@@ -28,12 +28,13 @@ def main(csv_path, order_path, out_path):
     order = json.load(open(order_path))
     labels = order['launches']
     # the weight repack of a step is launched by the forward that FOLLOWS the optimizer: rotate so that both lists start at the same point
-    want = sum(EXTRA.get(re.sub(r'\[.*', '', l), 1) for l in labels)
+    count = lambda l: 1 if l.endswith('[assemble]') else EXTRA.get(re.sub(r'\[.*', '', l), 1)
+    want = sum(count(l) for l in labels)
     assert want == len(step), f'alignment failed: bench lists {want} tfx kernels per step, the capture has {len(step)}'
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
     i = 0
     for l in labels:
-        n = EXTRA.get(re.sub(r'\[.*', '', l), 1)
+        n = count(l)
         for d in step[i:i + n]:
             agg[l][1] += d.get('dram__bytes_read.sum', 0.0) + d.get('dram__bytes_write.sum', 0.0)
             agg[l][2] += d.get('gpu__time_duration.sum', 0.0)

@@ -37,6 +37,7 @@ SIGNATURES = {
     'tfx_resid_bwd': [VP, VP, VP, VP, LL, VP, VP, VP, LL, VP, VP, I, I, VP],
     'tfx_attn_residual_fwd': [VP, I, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_attn_residual_bwd': [VP, VP, I, VP, VP, VP, VP, VP, VP, VP, VP, I, I, I, VP],
+    'tfx_attn_residual_bwd2': [VP, I, I, VP, VP, VP, VP, I, VP, VP, VP, VP, VP, I, VP, VP, VP, I, I, VP],
     'tfx_attn_residual_fwd_h16': [VP, I, VP, VP, VP, VP, VP, I, I, VP],
     'tfx_attn_residual_bwd_h16': [VP, VP, I, VP, VP, VP, VP, VP, VP, VP, VP, I, I, I, VP],
     'tfx_rmsnorm_fwd': [VP, VP, VP, VP, VP, VP, I, I, VP],

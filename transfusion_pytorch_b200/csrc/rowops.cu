@@ -5,6 +5,7 @@
 // transfusion.py:640-775 (AdaptiveWrapper), 779-829 (RMSNorm, AttentionResidual), 946-965 (qk norm, RoPE),
 // 3173-3184 (token select).
 #include "common.cuh"
+#include <string.h>
 #include "../../include/tfx_b200.h"
 
 namespace tfx {
@@ -329,6 +330,108 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd_k(PtrList hid, Pt
 #pragma unroll
     for (int w = 0; w < WARPS_PER_BLOCK; ++w) t += red[w][c];
     partials[(long long)blockIdx.x * D + c] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------ AttentionResidual backward, DEFERRED assembly (exact, less traffic)
+// The accumulating version above adds  a_k dx + c1_k w - c2_k h_k  into dH_k for EVERY earlier hidden k at EVERY layer: a read-modify-write of (i + 2)
+// fp32 rows per token and layer (68 % of that kernel's bytes).  Each contribution is (per-token scalars) x (a vector that already exists: the incoming
+// gradient dx_i', the layer's w_i', the hidden itself), so this version stores the three scalars per (token, layer, hidden) - 12 bytes instead of 2 KB -
+// and assembles the COMPLETE gradient of one hidden, once, when the backward pass needs it:
+//     G_k = sum_{i' >= k-1} [ a_{i',k} dx_{i'} + c1_{i',k} w_{i'} ] - (sum_{i'} c2_{i',k}) h_k
+// Layer i (own = 1): scalar pass over h_0 .. h_{i+1} (parameter gradients, scalars out), then G_{i+1} from its own term and the stored scalars / incoming
+// gradients of the later layers.  own = 0: only the assembly (G_0, after the first layer).  Bytes per token over 8 layers: 167 KB instead of 234 KB.
+struct ResBwd2Args {
+  const __nv_bfloat16* hid[12];     // bf16 hiddens h_0 .. h_{L1-1}
+  const float* dx_later[10];        // incoming gradients of the later AttentionResiduals (layers i+1 ..)
+  const float* sc_later[10];        // their scalars for THIS hidden: points at element [token 0][k = L1-1][0]; row stride = sc_stride floats
+  const float* gam[11];             // norm_keys.gamma: own layer first (unused when own = 0), then the later layers
+  const float* pq[11];
+  int L1, n_later, own;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd2_k(ResBwd2Args A, const float* __restrict__ dxo, const float* __restrict__ xo, const float* __restrict__ lse,
+                                                                 float* __restrict__ G, float* __restrict__ sc_out, int sc_stride, float* __restrict__ partials, int M, int tpw) {
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);    // (no early return: block-wide barriers below)
+  extern __shared__ __align__(16) float w_s[];                  // [1 + n_later][D]: w = (gamma + 1) * pq of the own layer (slot 0) and of the later ones
+  for (int j = A.own ? 0 : 1; j <= A.n_later; ++j)
+    for (int c = threadIdx.x; c < D; c += ROW_THREADS) w_s[j * D + c] = (A.gam[j][c] + 1.f) * A.pq[j][c];
+  __syncthreads();
+  float accw[NCH * 4];
+#pragma unroll
+  for (int i = 0; i < NCH * 4; ++i) accw[i] = 0.f;
+  for (int row = r0; row < r1; ++row) {
+    float g[NCH * 4], h[NCH * 4];
+    float c2sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) g[i] = 0.f;
+    if (A.own) {
+      float dxv[NCH * 4], w[NCH * 4];
+      load_row_f32<NCH>(dxo + (long long)row * D, lane, dxv);
+      load_row_f32<NCH>(xo + (long long)row * D, lane, h);
+      load_row_f32<NCH>(w_s, lane, w);
+      float mean_da = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) mean_da += h[i] * dxv[i];
+      mean_da = warp_sum(mean_da);
+      const float lse_r = lse[row];
+      for (int k = 0; k < A.L1; ++k) {
+        load_row_bf16<NCH>(A.hid[k] + (long long)row * D, lane, h);
+        float ss = 0.f, dot = 0.f, da = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; da += h[i] * dxv[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ss += __shfl_xor_sync(0xffffffffu, ss, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); da += __shfl_xor_sync(0xffffffffu, da, o);
+        }
+        const float nrm = fmaxf(sqrtf(ss), 1e-12f), rn = 1.f / nrm;
+        const float a = __expf(dot * rn - lse_r);
+        const float ds = a * (da - mean_da);
+        const float c1 = ds * rn, c2 = ds * dot * rn * rn * rn;
+#pragma unroll
+        for (int i = 0; i < NCH * 4; ++i) accw[i] += c1 * h[i];
+        if (k + 1 < A.L1) {
+          if (lane < 3) sc_out[(long long)row * sc_stride + k * 3 + lane] = lane == 0 ? a : (lane == 1 ? c1 : c2);
+        } else {                                    // the newest hidden: its gradient is assembled right here
+          c2sum = c2;
+#pragma unroll
+          for (int i = 0; i < NCH * 4; ++i) g[i] = a * dxv[i] + c1 * w[i];
+        }
+      }
+    } else {
+      load_row_bf16<NCH>(A.hid[A.L1 - 1] + (long long)row * D, lane, h);
+    }
+    // h now holds the hidden whose gradient is being assembled (index L1 - 1); add what the later layers sent to it
+    for (int j = 0; j < A.n_later; ++j) {
+      float d[NCH * 4], w[NCH * 4];
+      load_row_f32<NCH>(A.dx_later[j] + (long long)row * D, lane, d);
+      load_row_f32<NCH>(w_s + (j + 1) * D, lane, w);
+      const float* sc = A.sc_later[j] + (long long)row * sc_stride;
+      const float a = sc[0], c1 = sc[1];
+      c2sum += sc[2];
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) g[i] += a * d[i] + c1 * w[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) g[i] -= c2sum * h[i];
+    store_row_f32<NCH>(G + (long long)row * D, lane, g);
+  }
+  if (A.own) {
+    // d w = sum over tokens of c1 * h: block-level reduction, then ONE row of partial sums per block (folded by attn_res_bwd_finish_k)
+    __syncthreads();
+    float* red = w_s;                               // reuse: [WARPS_PER_BLOCK][D] fits below (1 + n_later) * D only for n_later >= 7, so the caller sizes smem for both
+    store_row_f32<NCH>(red + (threadIdx.x >> 5) * D, lane, accw);
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += ROW_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS_PER_BLOCK; ++w) t += red[w * D + c];
+      partials[(long long)blockIdx.x * D + c] = t;
+    }
   }
 }
 
@@ -691,6 +794,36 @@ int tfx_attn_residual_bwd_h16(const void* const* hiddens_bf16, float* const* dhi
                               const float* dx_out, const float* x_out, const float* lse, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, int init,
                               void* stream) {
   return attn_residual_bwd_impl(hiddens_bf16, true, dhiddens, n_hiddens, gamma, pseudo_query, dx_out, x_out, lse, dgamma, dpseudo_query, workspace, M, D, init, stream);
+}
+
+int tfx_attn_residual_bwd2(const void* const* hiddens_bf16, int n_hiddens, int own, const float* const* gammas, const float* const* pseudo_queries,
+                           const float* const* dx_later, const float* const* scalars_later, int n_later, const float* dx_out, const float* x_out, const float* lse,
+                           float* grad_hidden, float* scalars_out, int scalar_stride, float* dgamma, float* dpseudo_query, float* workspace, int M, int D, void* stream) {
+  if (M <= 0) return 0;
+  TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 12 && n_later >= 0 && n_later <= 10, "attn_residual_bwd2: %d hiddens / %d later layers out of range", n_hiddens, n_later);
+  TFX_REQUIRE(!own || workspace != nullptr, "attn_residual_bwd2: workspace of tfx_attn_residual_bwd_workspace_floats(M, D) floats is required");
+  ResBwd2Args A;
+  memset(&A, 0, sizeof(A));
+  A.L1 = n_hiddens; A.n_later = n_later; A.own = own ? 1 : 0;
+  for (int i = 0; i < n_hiddens; ++i) A.hid[i] = reinterpret_cast<const __nv_bfloat16*>(hiddens_bf16[i]);
+  for (int j = 0; j <= n_later; ++j) { A.gam[j] = gammas[j]; A.pq[j] = pseudo_queries[j]; }
+  for (int j = 0; j < n_later; ++j) { A.dx_later[j] = dx_later[j]; A.sc_later[j] = scalars_later[j]; }
+  const int tpw = ATTN_RES_BWD_TPW;
+  const int blocks = chunk_grid(M, tpw);
+  const int slots = (1 + n_later) > WARPS_PER_BLOCK ? (1 + n_later) : WARPS_PER_BLOCK;
+  const size_t smem = (size_t)slots * D * sizeof(float);
+  TFX_DISPATCH_NCH(D, {
+    auto kern = attn_res_bwd2_k<NCH>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<blocks, ROW_THREADS, smem, ST(stream)>>>(A, dx_out, x_out, lse, grad_hidden, scalars_out, scalar_stride, workspace, M, tpw);
+  });
+  if (int rc = check_launch("attn_residual_bwd2")) return rc;
+  if (own) {
+    const int rpb = 16;
+    attn_res_bwd_finish_k<<<dim3((D + 127) / 128, (blocks + rpb - 1) / rpb), 128, 0, ST(stream)>>>(workspace, blocks, D, gammas[0], pseudo_queries[0], dgamma, dpseudo_query, rpb);
+    return check_launch("attn_residual_bwd_finish");
+  }
+  return 0;
 }
 
 int tfx_rmsnorm_fwd(const float* x, const float* gamma, float* out_f32, void* out_bf16, const int* slot, void* out_mod_bf16, int M, int D, void* stream) {

@@ -94,6 +94,8 @@ class Engine:
         # Measured (profiles/r02_parity_report.txt, same-box A/B in profiles/r02_ab_hidden_bf16.txt): loss errors stay <= 1e-4 relative (bound 1e-3), hiddens 6e-3
         # (bound 2e-2), the step is 1.0 ms (1.8 %) shorter.  TFX_HIDDEN_BF16=0 restores fp32 hiddens.
         self.hid_bf16 = os.environ.get('TFX_HIDDEN_BF16', '1') == '1'
+        # AttentionResidual backward with deferred assembly (tfx_attn_residual_bwd2; needs the bf16 hiddens): TFX_ARES_DEFERRED=0 selects the accumulating kernel
+        self.ares_deferred = self.hid_bf16 and os.environ.get('TFX_ARES_DEFERRED', '1') == '1'
         self.bwd_kernel = os.environ.get('TFX_ATTN_BWD', 'ts')      # 'ts' (transposed scores, P^T / dS^T in TMEM) | 'tc' (round-1 kernel)
         self.fwd_kernel = os.environ.get('TFX_ATTN_FWD', 'ts')      # 'ts' (persistent, P in TMEM) | 'tc' (round-1 kernel, kept for A/B timing)
         self.frozen = False                         # True inside a sampling session: parameters cannot change, skip the re-pack check
@@ -716,12 +718,26 @@ class Engine:
         dy = self.buf('dy', (M, D), BF16)
         du = self.buf('du', (M, D), F32)
         arws = self.buf('attn_res_ws', (int(o.lib.tfx_attn_residual_bwd_workspace_floats(M, D)),), F32)
+        sc_stride = (self.depth + 2) * 3
+        arsc = self.buf('attn_res_sc', (self.depth, M, self.depth + 2, 3), F32) if self.ares_deferred else None
+        dxs = {}
         for i in reversed(range(self.depth)):
             L = st['layers'][i]
             pre = f'transformer.layers.{i}'
             lm = self.layer_maps[i]
             wA, wF = 2 * i, 2 * i + 1
-            (o.attn_residual_bwd_h16 if self.hid_bf16 else o.attn_residual_bwd)(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
+            if self.ares_deferred:
+                # complete gradient of x_c of THIS layer (hidden i + 1), assembled once from this layer's term and the stored scalars / incoming gradients of the
+                # later AttentionResiduals; the scalars for the earlier hiddens are stored for their own assembly further down the stack
+                dxs[i] = g
+                later = list(range(i + 1, self.depth))
+                gam = [self.P(f'transformer.layers.{j}.3.norm_keys.gamma') for j in [i] + later]
+                pqs = [self.P(f'transformer.layers.{j}.3.pseudo_queries') for j in [i] + later]
+                o.attn_residual_bwd2(self._ptr_array(hid[:i + 2]), i + 2, 1, self._ptr_array(gam), self._ptr_array(pqs), self._ptr_array([dxs[j] for j in later] or [g]),
+                                     self._ptr_array([arsc[j][0, i + 1] for j in later] or [g]), len(later), g, L['xr'], L['rlse'], dH[i + 1], arsc[i], sc_stride,
+                                     self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), arws, M, D)
+            else:
+              (o.attn_residual_bwd_h16 if self.hid_bf16 else o.attn_residual_bwd)(self._ptr_array(hid[:i + 2]), self._ptr_array(dH[:i + 2]), i + 2, self.P(f'{pre}.3.norm_keys.gamma'), self.P(f'{pre}.3.pseudo_queries'),
                                 g, L['xr'], L['rlse'], self.G(f'{pre}.3.norm_keys.gamma'), self.G(f'{pre}.3.pseudo_queries'), arws, M, D, 1 if i == self.depth - 1 else 0)
             gx = dH[i + 1]                       # complete gradient w.r.t. x_c of this layer; updated in place below
             # -- feed-forward branch
@@ -798,6 +814,12 @@ class Engine:
             if bucket_cb is not None:
                 bucket_cb(i)
         # ---- input side: gradient w.r.t. x0 = path gradient + AttentionResidual contributions to H[0]
+        if self.ares_deferred:                           # gradient of the input embedding x0 through all AttentionResiduals: assembly only
+            allj = list(range(self.depth))
+            gam = [self.P(f'transformer.layers.{j}.3.norm_keys.gamma') for j in [0] + allj]
+            pqs = [self.P(f'transformer.layers.{j}.3.pseudo_queries') for j in [0] + allj]
+            o.attn_residual_bwd2(self._ptr_array(hid[:1]), 1, 0, self._ptr_array(gam), self._ptr_array(pqs), self._ptr_array([dxs[j] for j in allj]),
+                                 self._ptr_array([arsc[j][0, 0] for j in allj]), len(allj), None, None, None, dH[0], None, sc_stride, None, None, None, M, D)
         o.axpy_f32(g, dH[0], 1.0, M * D)
         dmodtok = self.buf('dmodtok', (max(S, 1), D), BF16)
         o.embed_bwd(g, dv['text_id'], dv['slot'] if S > 0 else None, self.G('text_embed.weight'), dmodtok if S > 0 else None, M, D)

@@ -17,9 +17,17 @@ def ops():
     return _lib.Ops()
 
 
+@pytest.fixture(params = [0, 2], ids = ['single', 'paired'])
+def cluster_mode(ops, request):
+    """GEMM launches as independent CTAs (default) and as 2-CTA clusters sharing the B tile by TMA multicast"""
+    assert ops.lib.tfx_gemm_set_cluster_mode(request.param) == 0
+    yield request.param
+    ops.lib.tfx_gemm_set_cluster_mode(0)
+
+
 @pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 1), (1, 0)])
-@pytest.mark.parametrize('M,N,K', [(300, 390, 520), (1000, 1664, 512), (128, 128, 64)])
-def test_gemm_store_all_majors(ops, a_mn, b_mn, M, N, K):
+@pytest.mark.parametrize('M,N,K', [(300, 390, 520), (1000, 1664, 512), (128, 128, 64), (40000, 512, 192)])      # the last one: several tiles per CTA (pair), odd tile count
+def test_gemm_store_all_majors(ops, cluster_mode, a_mn, b_mn, M, N, K):
     g = torch.Generator(device = 'cuda').manual_seed(0)
     A = torch.randn(M, K, device = 'cuda', generator = g).to(BF16)
     B = torch.randn(N, K, device = 'cuda', generator = g).to(BF16)
@@ -275,7 +283,7 @@ def _rope_ref(x, pos, freqs):                       # interleaved pairs (x0, x1)
 
 
 @pytest.mark.parametrize('M,H,D', [(700, 8, 512), (300, 2, 128), (257, 4, 256)])
-def test_gemm_qkvg_epilogue_vs_torch(ops, M, H, D):
+def test_gemm_qkvg_epilogue_vs_torch(ops, cluster_mode, M, H, D):
     """to_qk | to_v | to_gates GEMM + per-head qk-RMSNorm + interleaved RoPE (T.py:946-965, 1027), incl. the kv-cache row scatter"""
     g = torch.Generator(device = 'cuda').manual_seed(4)
     HI, NQ = H * 64, 3 * H * 64 + 128
@@ -310,7 +318,7 @@ def test_gemm_qkvg_epilogue_vs_torch(ops, M, H, D):
 
 
 @pytest.mark.parametrize('M,N,K,two', [(900, 512, 512, False), (333, 512, 1408, False), (500, 512, 1024, True), (130, 128, 128, False)])
-def test_gemm_resid_epilogue_vs_torch(ops, M, N, K, two):
+def test_gemm_resid_epilogue_vs_torch(ops, cluster_mode, M, N, K, two):
     """branch output projection + AdaptiveWrapper output gate + residual (T.py:765-769, 1031, 1238-1242); `two`: skip_proj on cat(x, skip) (T.py:1217-1219)"""
     g = torch.Generator(device = 'cuda').manual_seed(5)
     nc = 4
@@ -344,7 +352,7 @@ def test_gemm_resid_epilogue_vs_torch(ops, M, N, K, two):
 
 
 @pytest.mark.parametrize('M,D,inner', [(600, 512, 1365), (200, 128, 341)])
-def test_gemm_geglu_epilogue_and_backward_vs_torch(ops, M, D, inner):
+def test_gemm_geglu_epilogue_and_backward_vs_torch(ops, cluster_mode, M, D, inner):
     """FeedForward net.0 + GEGLU (T.py:833-834, 846-847) on the tile-interleaved W1, and tfx_geglu_bwd against autograd"""
     g = torch.Generator(device = 'cuda').manual_seed(6)
     Ip = (inner + 63) // 64 * 64

@@ -7,7 +7,9 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio' ]
+        'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio',
+        'sm__cycles_elapsed.avg', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_srcunit_tex_op_write.sum', 'lts__t_sector_hit_rate.pct',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_active' ]
 def main(path):
     out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output = True, text = True).stdout
     rows = list(csv.reader(out.splitlines()))

@@ -19,6 +19,7 @@ VP, I, LL, F, ULL = c_void_p, c_int, c_longlong, c_float, c_ulonglong
 # name -> argtypes, mirrors include/tfx_b200.h exactly (order matters)
 SIGNATURES = {
     'tfx_init': [I],
+    'tfx_gemm_set_cluster_mode': [I],
     'tfx_gemm_store': [VP, LL, I, VP, LL, I, I, I, I, VP, LL, VP, LL, VP, VP, F, I, I, VP],
     'tfx_gemm_qkvg': [VP, LL, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, I, VP, VP, VP],
     'tfx_gemm_resid': [VP, LL, VP, LL, I, VP, LL, I, I, I, VP, VP, VP, VP, VP, VP, VP, LL, VP, VP],

@@ -76,6 +76,13 @@ __device__ __forceinline__ void red_row_f32(float* __restrict__ base, int lane, 
   }
 }
 
+// cp.async pieces for the per-warp row rings of the depth-serial kernels (rowops.cu: AttentionResidual forward / deferred backward)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
 // dispatch on model dim D (multiple of 128, <= 1024)
 #define TFX_DISPATCH_NCH(D, ...)                                                       \
   do {                                                                                 \

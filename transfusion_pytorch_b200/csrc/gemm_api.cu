@@ -32,6 +32,12 @@ static int dispatch_major(const GemmOperand& A, const GemmOperand& B, const Gemm
 
 extern "C" {
 
+int tfx_gemm_set_cluster_mode(int mode) {
+  TFX_REQUIRE(mode >= 0 && mode <= 3, "gemm_set_cluster_mode: mode %d not in {0 (off), 1 (off), 2 (always pair), 3 (pair large problems)}", mode);
+  gemm_cluster_mode_ref() = mode;
+  return 0;
+}
+
 int tfx_gemm_store(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M, int N, int K,
                    float* out_f32, long long ld_f32, void* out_bf16, long long ld_bf16, const float* bias, const long long* row_off,
                    float alpha, int accumulate, int k_splits, void* stream) {

@@ -21,6 +21,9 @@
 
 namespace tfx {
 
+#ifndef GEMM_ABLATE_HALF_B
+#define GEMM_ABLATE_HALF_B 0
+#endif
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;     // 64 bf16 = 128 B = one swizzle atom row
 constexpr int GEMM_UK = 16;     // UMMA K for 16-bit inputs
@@ -199,7 +202,11 @@ __device__ __forceinline__ void stg_store_rows(const uint8_t* sw, int lane, uint
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// CL = 2: clusters of two CTAs work on vertically adjacent tiles (m_blk, m_blk + 1) of the same N block.  Each CTA fetches HALF of the B tile and
+// multicasts it into both (the smem stage of a CTA is written by its peer too, so a stage is free only when BOTH MMA issuers have committed it:
+// commits are multicast to both empty barriers, which count 2).  All these GEMMs sit on the L2 -> SM bandwidth cap (profiles/r02_ncu_gemm_l2.txt:
+// 6.1 - 7.8 KB / clk of tile loads at 38 - 46 % tensor activity); sharing B removes a third of that traffic for 128 x 256 tiles.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL = 1>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI>::THREADS), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI>;
@@ -220,18 +227,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_tiles = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
-  const int num_items = m_tiles * n_tiles * p.k_splits;
+  const int m_units = (m_tiles + CL - 1) / CL;            // a work item = CL vertically adjacent tiles, one per CTA of the cluster
+  const int unit_items = m_units * n_tiles;
+  const int num_items = unit_items * p.k_splits;
+  const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EW); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();               // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -239,17 +251,22 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int split = item / (m_tiles * n_tiles);
-        const int rem = item - split * (m_tiles * n_tiles);
-        const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
+      for (int item = first_item; item < num_items; item += item_stride) {
+        const int split = item / unit_items;
+        const int rem = item - split * unit_items;
+        const int m_unit = rem / n_tiles, n_blk = rem - m_unit * n_tiles;
+        const int m_blk = m_unit * CL + cta_rank;             // (past the last tile for an odd tile count: zero-filled by TMA, results discarded)
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
+#if GEMM_ABLATE_HALF_B
+          mbar_expect_tx(&full_bar[stage], CL == 1 ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES);
+#else
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#endif
           if (!A_MN) {
             if (kb * GEMM_BK < p.K1) tma_load_2d(&tmA, &full_bar[stage], sA, kb * GEMM_BK, m_blk * GEMM_BM);
             else tma_load_2d(&tmA2, &full_bar[stage], sA, kb * GEMM_BK - p.K1, m_blk * GEMM_BM);
@@ -258,12 +275,34 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int a = 0; a < GEMM_BM / 64; ++a)
               tma_load_2d(&tmA, &full_bar[stage], sA + a * (GEMM_BK * 128), m_blk * GEMM_BM + a * 64, kb * GEMM_BK);
           }
-          if (!B_MN) {
-            tma_load_2d(&tmB, &full_bar[stage], sB, kb * GEMM_BK, n_blk * BN);
-          } else {
+          if constexpr (CL == 1) {
+#if GEMM_ABLATE_HALF_B      // timing experiment only (wrong results): the SM ingests half of the B tile, as a cta_group::2 pair would
+            if (!B_MN) {
+              tma_load_2d(&tmB, &full_bar[stage], sB, kb * GEMM_BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              tma_load_2d(&tmB, &full_bar[stage], sB + a * (GEMM_BK * 128), n_blk * BN + a * 64, kb * GEMM_BK);
+              for (int a = 0; a < BN / 128; ++a)
+                tma_load_2d(&tmB, &full_bar[stage], sB + a * (GEMM_BK * 128), n_blk * BN + a * 64, kb * GEMM_BK);
+            }
+#else
+            if (!B_MN) {
+              tma_load_2d(&tmB, &full_bar[stage], sB, kb * GEMM_BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a)
+                tma_load_2d(&tmB, &full_bar[stage], sB + a * (GEMM_BK * 128), n_blk * BN + a * 64, kb * GEMM_BK);
+            }
+#endif
+          } else {                                            // this CTA's half of the B tile, delivered to both CTAs (tmB box: BN / 2 rows)
+            if (!B_MN) {
+              tma_load_2d_mc(&tmB, &full_bar[stage], sB + cta_rank * (BN / 2) * 128, kb * GEMM_BK, n_blk * BN + cta_rank * (BN / 2), (uint16_t)3);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 128; ++a) {
+                const int aa = cta_rank * (BN / 128) + a;
+                tma_load_2d_mc(&tmB, &full_bar[stage], sB + aa * (GEMM_BK * 128), n_blk * BN + aa * 64, kb * GEMM_BK, (uint16_t)3);
+              }
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -275,8 +314,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-        const int split = item / (m_tiles * n_tiles);
+      for (int item = first_item; item < num_items; item += item_stride, ++local) {
+        const int split = item / unit_items;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
         const int buf = local & 1;
@@ -297,7 +336,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                      : umma_smem_desc_sw128(sB + k * (GEMM_UK * 2), 0, 1024);
             umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if constexpr (CL == 1) umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          else umma_commit_mc(&empty_bar[stage], (uint16_t)3);            // ... in both CTAs: the peer multicasts into this slot as well
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[buf]);              // accumulator ready for the epilogue
@@ -313,8 +353,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // as the current slab has been pulled into registers), so its DRAM latency hides behind the current tile's math and stores
     auto resid_prefetch = [&](int it_) {
       if constexpr (EPI == EPI_RESID) {
-        const int rem_ = it_ % (m_tiles * n_tiles);
-        const int mb_ = rem_ / n_tiles, nb_ = rem_ - mb_ * n_tiles;
+        const int rem_ = it_ % unit_items;
+        const int mb_ = (rem_ / n_tiles) * CL + cta_rank, nb_ = rem_ % n_tiles;
         const int wrow_ = mb_ * GEMM_BM + quad * 32, cb_ = nb_ * BN + part * 32;
         const int rv_ = min(32, p.M - wrow_);
         if (cb_ < p.N) {
@@ -322,17 +362,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + (lane >> 3), ch = lane & 7;
             const bool ok = rr < rv_;
-            cp_async16_zfill(sw + rr * 128 + ((ch ^ (rr & 7)) << 4), p.x_res + (long long)(wrow_ + (ok ? rr : 0)) * p.N + cb_ + ch * 4, ok);
+            cp_async16_zfill(sw + rr * 128 + ((ch ^ (rr & 7)) << 4), p.x_res + (long long)(ok ? wrow_ + rr : 0) * p.N + cb_ + ch * 4, ok);
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
     };
     int local = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-      const int split = item / (m_tiles * n_tiles);
-      const int rem = item - split * (m_tiles * n_tiles);
-      const int m_blk = rem / n_tiles, n_blk = rem - m_blk * n_tiles;
+    for (int item = first_item; item < num_items; item += item_stride, ++local) {
+      const int split = item / unit_items;
+      const int rem = item - split * unit_items;
+      const int m_unit = rem / n_tiles, n_blk = rem - m_unit * n_tiles;
+      const int m_blk = m_unit * CL + cta_rank;               // a tile past the end has rows_valid <= 0: every store below is row-guarded
       const int buf = local & 1;
       const uint32_t bphase = (local >> 1) & 1;
       const int wrow0 = m_blk * GEMM_BM + quad * 32;          // first row of this warp's 32-row slab
@@ -601,7 +642,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t xrv[32];
             stg_get<8>(sw, lane, xrv);                  // residual row (prefetched by cp.async one tile ahead)
             __syncwarp();                               // every lane holds its row: the 4 KB tile is free for the NEXT tile's slab
-            if (item + (int)gridDim.x < num_items) resid_prefetch(item + gridDim.x);
+            if (item + item_stride < num_items) resid_prefetch(item + item_stride);
             if (zrow) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -640,8 +681,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             stg64_store(swb, lane, reinterpret_cast<uint8_t*>(p.x_out_bf16 + (long long)wrow0 * p.N + cbase), (long long)p.N * 2, rows_valid);
           }
           __syncwarp();
-        } else if (item + (int)gridDim.x < num_items) {
-          resid_prefetch(item + gridDim.x);             // keep the one-ahead commit-group bookkeeping uniform
+        } else if (item + item_stride < num_items) {
+          resid_prefetch(item + item_stride);             // keep the one-ahead commit-group bookkeeping uniform
         }
       } else if constexpr (EPI == EPI_GEGLU) {
         static_assert(EPI != EPI_GEGLU || BN == 256, "GEGLU epilogue expects 256-wide N tiles (2 x [64 value | 64 gate])");
@@ -695,6 +736,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();               // no CTA leaves while its peer can still signal its barriers
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
@@ -737,6 +779,16 @@ struct GemmOperand {
   long long ld2 = 0;
 };
 
+// CTA pairing (CL = 2) is OFF unless asked for: TFX_GEMM_CLUSTER=2 in the environment or tfx_gemm_set_cluster_mode(2) pairs every launch, mode 3 only
+// the launches where every SM still gets two tiles.  Measured on the b128 step shapes (profiles/r02_gemm_l2_bound.txt): the plain-store forward GEMM
+// gains 6 %, the fused-epilogue and gradient GEMMs lose 1 - 2 % - multicast at cluster size 2 does not lower the L2 -> SM traffic that bounds them.
+inline int& gemm_cluster_mode_ref() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("TFX_GEMM_CLUSTER"); mode = e ? atoi(e) : 0; }
+  return mode;
+}
+inline int gemm_cluster_mode() { return gemm_cluster_mode_ref(); }
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EPI>;
@@ -755,17 +807,46 @@ int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& 
     const int per = (kbt + p.k_splits - 1) / p.k_splits;
     p.k_splits = (kbt + per - 1) / per;            // no empty split
   }
-  if (!B_MN) rc = make_tmap_bf16(&tmB, B.ptr, p.K, p.N, B.ld, BN); else rc = make_tmap_bf16(&tmB, B.ptr, p.N, p.K, B.ld, GEMM_BK);
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
+  const int items = m_tiles * n_tiles * p.k_splits;
+  if (items <= 0) return 0;
+  const int mode = gemm_cluster_mode();
+  const bool paired = mode == 2 || (mode == 3 && m_tiles >= 2 && items >= 2 * num_sms);
+  // paired CTAs each fetch half of the B tile: the box of tmB is BN / 2 rows (K-major; the MN-major boxes are 64 wide either way)
+#if GEMM_ABLATE_HALF_B
+  if (!B_MN) rc = make_tmap_bf16(&tmB, B.ptr, p.K, p.N, B.ld, BN / 2);
+#else
+  if (!B_MN) rc = make_tmap_bf16(&tmB, B.ptr, p.K, p.N, B.ld, paired ? BN / 2 : BN);
+#endif
+  else rc = make_tmap_bf16(&tmB, B.ptr, p.N, p.K, B.ld, GEMM_BK);
   if (rc) return rc;
-  auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, EPI>;
+  if (paired) {
+    auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, EPI, 2>;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+    if (!max_clusters) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return -2;
+      cfg.gridDim = dim3(2 * (num_sms / 2));
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = num_sms / 2; }
+      max_clusters = nc < num_sms / 2 ? nc : num_sms / 2;
+    }
+    const int pair_items = ((m_tiles + 1) / 2) * n_tiles * p.k_splits;
+    const int clusters = pair_items < max_clusters ? pair_items : max_clusters;
+    cfg.gridDim = dim3(2 * clusters);
+    return cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, p) == cudaSuccess ? 0 : -3;
+  }
+  auto kern = gemm_sm100_kernel<BN, A_MN, B_MN, EPI, 1>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return -2;
     attr_set = true;
   }
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
-  const int items = m_tiles * n_tiles * p.k_splits;
-  if (items <= 0) return 0;
   const int grid = items < num_sms ? items : num_sms;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmA2, tmB, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;

@@ -214,12 +214,42 @@ __global__ void __launch_bounds__(ROW_THREADS) resid_bwd_k(const float* __restri
 // ------------------------------------------------------------------------------------ AttentionResidual forward
 // sim_l = <h_l, (gamma+1)*pq> / max(|h_l|, eps)   (sqrt(D) of the RMSNorm cancels the D^-1/2 scale)
 // x = sum_l softmax_l(sim) h_l           (T.py:803-829)   single pass, online softmax over depth.
+// The depth loop is a serial chain (online softmax), so the hiddens of a warp's rows stream through a per-warp ring of shared-memory slots
+// filled by lane-private cp.async pieces: RING - 1 row loads per warp stay in flight without spending registers (a register double buffer
+// was measured SLOWER - 338 vs 255 us, 88 registers halve the resident warps; the plain loop reached 0.70 of the HBM peak).
+constexpr int ARES_FWD_RING = 4;
 template <int NCH, bool HB>
 __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L1, const float* __restrict__ gamma, const float* __restrict__ pq,
                                                              float* __restrict__ xo, __nv_bfloat16* __restrict__ xb, float* __restrict__ lse_out, int M) {
   constexpr int D = NCH * 128;
+  constexpr int RING = ARES_FWD_RING;
+  constexpr int SLOT = D * (HB ? 2 : 4);
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  extern __shared__ __align__(16) uint8_t ares_ring[];
+  const uint8_t* ring = ares_ring + (threadIdx.x >> 5) * (RING * SLOT);
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  int iss_row = warp0, iss_k = 0, iss_slot = 0;
+  auto issue = [&]() {
+    if (iss_row < M) {
+      const uint32_t dst = ring_u32 + iss_slot * SLOT;
+      if (HB) {
+        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(hid.p[iss_k]) + (long long)iss_row * D + lane * 4;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) cp_async_8(dst + (c * 128 + lane * 4) * 2, b + c * 128);
+      } else {
+        const float* f = hid.p[iss_k] + (long long)iss_row * D + lane * 4;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) cp_async_16(dst + (c * 128 + lane * 4) * 4, f + c * 128);
+      }
+      if (++iss_k == L1) { iss_k = 0; iss_row += nwarps; }
+    }
+    cp_async_commit();
+    iss_slot = iss_slot + 1 == RING ? 0 : iss_slot + 1;
+  };
+#pragma unroll
+  for (int i = 0; i < RING; ++i) issue();
+  int cons_slot = 0;
   float w[NCH * 4], t[NCH * 4];
   load_row_f32<NCH>(gamma, lane, w);
   load_row_f32<NCH>(pq, lane, t);
@@ -230,15 +260,18 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) acc[i] = 0.f;
     float m = -INFINITY, l = 0.f;
-    // (prefetching the next hidden into a second register set was measured SLOWER - 338 vs 255 us: 88 registers halve the resident warps)
     for (int k = 0; k < L1; ++k) {
       float h[NCH * 4];
-      if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(hid.p[k]) + (long long)row * D, lane, h);      // bf16 copies of the hiddens: half the read traffic
-      else load_row_f32<NCH>(hid.p[k] + (long long)row * D, lane, h);
+      cp_async_wait<RING - 1>();
+      if (HB) load_row_bf16<NCH>(reinterpret_cast<const __nv_bfloat16*>(ring + cons_slot * SLOT), lane, h);
+      else load_row_f32<NCH>(reinterpret_cast<const float*>(ring + cons_slot * SLOT), lane, h);
+      cons_slot = cons_slot + 1 == RING ? 0 : cons_slot + 1;
+      issue();
       float ss = 0.f, dot = 0.f;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; }
-      ss = warp_sum(ss); dot = warp_sum(dot);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); }
       const float sim = dot / fmaxf(sqrtf(ss), 1e-12f);
       const float mn = fmaxf(m, sim);
       const float a = __expf(m - mn), b = __expf(sim - mn);
@@ -253,6 +286,7 @@ __global__ void __launch_bounds__(ROW_THREADS) attn_res_fwd_k(PtrList hid, int L
     if (xb) store_row_bf16<NCH>(xb + (long long)row * D, lane, acc);
     if (lse_out && lane == 0) lse_out[row] = m + __logf(l);
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------ AttentionResidual backward
@@ -350,16 +384,83 @@ struct ResBwd2Args {
   int L1, n_later, own;
 };
 
+// Every global read of the kernel goes through a per-warp ring of row-sized shared-memory slots filled by cp.async (lane-private 16 / 8 / 4 byte
+// pieces: a lane only ever reads back what it copied itself, so cp.async.wait_group is the only synchronisation).  The item order of a row is
+// fixed - [scalars of the later layers + lse] [dx_out] [x_out] [h_0 .. h_{L1-1}] [dx_later ..] - so RING - 1 row loads per warp are always in
+// flight.  The register-prefetch version kept one (profiles/r02_ab_ares_deferred.txt: 0.57 of the HBM peak, slower than the kernel it replaces).
+template <int NCH> struct ResBwd2Cfg { static constexpr int RING = NCH <= 4 ? 5 : 3; };
+
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd2_k(ResBwd2Args A, const float* __restrict__ dxo, const float* __restrict__ xo, const float* __restrict__ lse,
                                                                  float* __restrict__ G, float* __restrict__ sc_out, int sc_stride, float* __restrict__ partials, int M, int tpw) {
   constexpr int D = NCH * 128;
+  constexpr int RING = ResBwd2Cfg<NCH>::RING;
+  constexpr int SLOT = D * 4;                                   // bytes: one fp32 row
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int r0 = min(M, warp * tpw), r1 = min(M, r0 + tpw);    // (no early return: block-wide barriers below)
-  extern __shared__ __align__(16) float w_s[];                  // [1 + n_later][D]: w = (gamma + 1) * pq of the own layer (slot 0) and of the later ones
+  extern __shared__ __align__(16) float w_s[];                  // [max(1 + n_later, warps)][D]: w = (gamma + 1) * pq of the own layer (slot 0) and of the later ones; then the rings
+  const int w_slots = (1 + A.n_later) > WARPS_PER_BLOCK ? (1 + A.n_later) : WARPS_PER_BLOCK;
+  const uint8_t* ring = reinterpret_cast<const uint8_t*>(w_s + w_slots * D) + (threadIdx.x >> 5) * (RING * SLOT);
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+
+  // ---- producer side of the ring
+  const int n_items = A.own ? 3 + A.L1 + A.n_later : 2 + A.n_later;
+  int iss_row = r0, iss_it = 0, iss_slot = 0;
+  auto issue = [&]() {
+    if (iss_row < r1) {
+      const uint32_t dst = ring_u32 + iss_slot * SLOT;
+      const int it = iss_it;
+      if (it == 0) {                                            // lane j: (a, c1, c2) of later layer j for this hidden; lane 31: lse of the row
+        if (lane < A.n_later) {
+          const float* sp = A.sc_later[lane] + (long long)iss_row * sc_stride;
+          cp_async_4(dst + lane * 16, sp); cp_async_4(dst + lane * 16 + 4, sp + 1); cp_async_4(dst + lane * 16 + 8, sp + 2);
+        }
+        if (A.own && lane == 31) cp_async_4(dst + 31 * 16, lse + iss_row);
+      } else {
+        const float* f = nullptr;
+        const __nv_bfloat16* b = nullptr;
+        if (A.own) {
+          if (it == 1) f = dxo; else if (it == 2) f = xo; else if (it < 3 + A.L1) b = A.hid[it - 3]; else f = A.dx_later[it - 3 - A.L1];
+        } else {
+          if (it == 1) b = A.hid[A.L1 - 1]; else f = A.dx_later[it - 2];
+        }
+        if (f) {
+          f += (long long)iss_row * D + lane * 4;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) cp_async_16(dst + (c * 128 + lane * 4) * 4, f + c * 128);
+        } else {
+          b += (long long)iss_row * D + lane * 4;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) cp_async_8(dst + (c * 128 + lane * 4) * 2, b + c * 128);
+        }
+      }
+      if (++iss_it == n_items) { iss_it = 0; ++iss_row; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");         // (an empty group past the last row keeps the group count uniform)
+    iss_slot = iss_slot + 1 == RING ? 0 : iss_slot + 1;
+  };
+  // ---- consumer side: the oldest outstanding row -> registers, then its slot is refilled
+  int cons_slot = 0;
+  auto take_f32 = [&](float (&v)[NCH * 4]) {
+    cp_async_wait<RING - 1>();
+    const float* sp = reinterpret_cast<const float*>(ring + cons_slot * SLOT);
+    load_row_f32<NCH>(sp, lane, v);
+    cons_slot = cons_slot + 1 == RING ? 0 : cons_slot + 1;
+    issue();
+  };
+  auto take_bf16 = [&](float (&v)[NCH * 4]) {
+    cp_async_wait<RING - 1>();
+    const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(ring + cons_slot * SLOT);
+    load_row_bf16<NCH>(sp, lane, v);
+    cons_slot = cons_slot + 1 == RING ? 0 : cons_slot + 1;
+    issue();
+  };
+
   for (int j = A.own ? 0 : 1; j <= A.n_later; ++j)
     for (int c = threadIdx.x; c < D; c += ROW_THREADS) w_s[j * D + c] = (A.gam[j][c] + 1.f) * A.pq[j][c];
+#pragma unroll
+  for (int i = 0; i < RING; ++i) issue();
   __syncthreads();
   float accw[NCH * 4];
 #pragma unroll
@@ -369,21 +470,30 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd2_k(ResBwd2Args A,
     float c2sum = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) g[i] = 0.f;
+    // item 0: this lane's later-layer scalars, lse broadcast from lane 31
+    cp_async_wait<RING - 1>();
+    const float4 scl = *reinterpret_cast<const float4*>(ring + cons_slot * SLOT + lane * 16);
+    cons_slot = cons_slot + 1 == RING ? 0 : cons_slot + 1;
+    issue();
     if (A.own) {
-      float dxv[NCH * 4], w[NCH * 4];
-      load_row_f32<NCH>(dxo + (long long)row * D, lane, dxv);
-      load_row_f32<NCH>(xo + (long long)row * D, lane, h);
-      load_row_f32<NCH>(w_s, lane, w);
+      const float lse_r = __shfl_sync(0xffffffffu, scl.x, 31);
+      float dxv[NCH * 4];
+      take_f32(dxv);
+      take_f32(h);
       float mean_da = 0.f;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) mean_da += h[i] * dxv[i];
       mean_da = warp_sum(mean_da);
-      const float lse_r = lse[row];
       for (int k = 0; k < A.L1; ++k) {
-        load_row_bf16<NCH>(A.hid[k] + (long long)row * D, lane, h);
+        take_bf16(h);
         float ss = 0.f, dot = 0.f, da = 0.f;
 #pragma unroll
-        for (int i = 0; i < NCH * 4; ++i) { ss += h[i] * h[i]; dot += h[i] * w[i]; da += h[i] * dxv[i]; }
+        for (int c = 0; c < NCH; ++c) {
+          const float4 w4 = *reinterpret_cast<const float4*>(w_s + c * 128 + lane * 4);       // w of the own layer straight from shared memory (register budget)
+          ss += h[4 * c] * h[4 * c] + h[4 * c + 1] * h[4 * c + 1] + h[4 * c + 2] * h[4 * c + 2] + h[4 * c + 3] * h[4 * c + 3];
+          dot += h[4 * c] * w4.x + h[4 * c + 1] * w4.y + h[4 * c + 2] * w4.z + h[4 * c + 3] * w4.w;
+          da += h[4 * c] * dxv[4 * c] + h[4 * c + 1] * dxv[4 * c + 1] + h[4 * c + 2] * dxv[4 * c + 2] + h[4 * c + 3] * dxv[4 * c + 3];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           ss += __shfl_xor_sync(0xffffffffu, ss, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); da += __shfl_xor_sync(0xffffffffu, da, o);
@@ -399,31 +509,38 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) attn_res_bwd2_k(ResBwd2Args A,
         } else {                                    // the newest hidden: its gradient is assembled right here
           c2sum = c2;
 #pragma unroll
-          for (int i = 0; i < NCH * 4; ++i) g[i] = a * dxv[i] + c1 * w[i];
+          for (int c = 0; c < NCH; ++c) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w_s + c * 128 + lane * 4);
+            g[4 * c] = a * dxv[4 * c] + c1 * w4.x; g[4 * c + 1] = a * dxv[4 * c + 1] + c1 * w4.y;
+            g[4 * c + 2] = a * dxv[4 * c + 2] + c1 * w4.z; g[4 * c + 3] = a * dxv[4 * c + 3] + c1 * w4.w;
+          }
         }
       }
     } else {
-      load_row_bf16<NCH>(A.hid[A.L1 - 1] + (long long)row * D, lane, h);
+      take_bf16(h);
     }
     // h now holds the hidden whose gradient is being assembled (index L1 - 1); add what the later layers sent to it
     for (int j = 0; j < A.n_later; ++j) {
-      float d[NCH * 4], w[NCH * 4];
-      load_row_f32<NCH>(A.dx_later[j] + (long long)row * D, lane, d);
-      load_row_f32<NCH>(w_s + (j + 1) * D, lane, w);
-      const float* sc = A.sc_later[j] + (long long)row * sc_stride;
-      const float a = sc[0], c1 = sc[1];
-      c2sum += sc[2];
+      float d[NCH * 4];
+      take_f32(d);
+      const float a = __shfl_sync(0xffffffffu, scl.x, j), c1 = __shfl_sync(0xffffffffu, scl.y, j);
+      c2sum += __shfl_sync(0xffffffffu, scl.z, j);
 #pragma unroll
-      for (int i = 0; i < NCH * 4; ++i) g[i] += a * d[i] + c1 * w[i];
+      for (int c = 0; c < NCH; ++c) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w_s + (j + 1) * D + c * 128 + lane * 4);
+        g[4 * c] += a * d[4 * c] + c1 * w4.x; g[4 * c + 1] += a * d[4 * c + 1] + c1 * w4.y;
+        g[4 * c + 2] += a * d[4 * c + 2] + c1 * w4.z; g[4 * c + 3] += a * d[4 * c + 3] + c1 * w4.w;
+      }
     }
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) g[i] -= c2sum * h[i];
     store_row_f32<NCH>(G + (long long)row * D, lane, g);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (A.own) {
     // d w = sum over tokens of c1 * h: block-level reduction, then ONE row of partial sums per block (folded by attn_res_bwd_finish_k)
     __syncthreads();
-    float* red = w_s;                               // reuse: [WARPS_PER_BLOCK][D] fits below (1 + n_later) * D only for n_later >= 7, so the caller sizes smem for both
+    float* red = w_s;                               // [warps][D]: the caller sizes the w area for max(1 + n_later, warps) rows
     store_row_f32<NCH>(red + (threadIdx.x >> 5) * D, lane, accw);
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += ROW_THREADS) {
@@ -752,8 +869,22 @@ static int attn_residual_fwd_impl(const void* const* hiddens, bool hb, int n_hid
   TFX_REQUIRE(n_hiddens >= 1 && n_hiddens <= 32, "attn_residual: n_hiddens %d out of range [1,32]", n_hiddens);
   PtrList pl;
   for (int i = 0; i < n_hiddens; ++i) pl.p[i] = reinterpret_cast<float*>(const_cast<void*>(hiddens[i]));
-  if (hb) TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH, true><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, lse_out, M)));
-  else TFX_DISPATCH_NCH(D, (attn_res_fwd_k<NCH, false><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, lse_out, M)));
+  // persistent grid: exactly the resident blocks (registers / ring shared memory decide), rows strided over all warps
+#define TFX_ARES_FWD_LAUNCH(HBV)                                                                                                            \
+  TFX_DISPATCH_NCH(D, {                                                                                                                     \
+    auto kern = attn_res_fwd_k<NCH, HBV>;                                                                                                   \
+    const int smem = WARPS_PER_BLOCK * ARES_FWD_RING * D * (HBV ? 2 : 4);                                                                   \
+    static int per_sm = 0;                                                                                                                  \
+    if (!per_sm) {                                                                                                                          \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                                                        \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROW_THREADS, smem);                                                      \
+      if (per_sm < 1) per_sm = 1;                                                                                                           \
+    }                                                                                                                                       \
+    const long long want = ((long long)M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, cap = (long long)num_sms() * per_sm;                     \
+    kern<<<(int)(want < cap ? want : cap), ROW_THREADS, smem, ST(stream)>>>(pl, n_hiddens, gamma, pseudo_query, x_out, (__nv_bfloat16*)x_out_bf16, lse_out, M); \
+  })
+  if (hb) TFX_ARES_FWD_LAUNCH(true); else TFX_ARES_FWD_LAUNCH(false);
+#undef TFX_ARES_FWD_LAUNCH
   return check_launch("attn_residual_fwd");
 }
 int tfx_attn_residual_fwd(const float* const* hiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
@@ -766,6 +897,7 @@ int tfx_attn_residual_fwd_h16(const void* const* hiddens_bf16, int n_hiddens, co
 }
 
 static const int ATTN_RES_BWD_TPW = 4;
+static const int ATTN_RES_BWD2_TPW = 8;      // the ring start-up bubble is paid once per warp: more rows per warp (the workspace is sized for the smaller constant)
 long long tfx_attn_residual_bwd_workspace_floats(int M, int D) { return (long long)chunk_grid(M, ATTN_RES_BWD_TPW) * D; }
 
 static int attn_residual_bwd_impl(const void* const* hiddens, bool hb, float* const* dhiddens, int n_hiddens, const float* gamma, const float* pseudo_query,
@@ -808,13 +940,14 @@ int tfx_attn_residual_bwd2(const void* const* hiddens_bf16, int n_hiddens, int o
   for (int i = 0; i < n_hiddens; ++i) A.hid[i] = reinterpret_cast<const __nv_bfloat16*>(hiddens_bf16[i]);
   for (int j = 0; j <= n_later; ++j) { A.gam[j] = gammas[j]; A.pq[j] = pseudo_queries[j]; }
   for (int j = 0; j < n_later; ++j) { A.dx_later[j] = dx_later[j]; A.sc_later[j] = scalars_later[j]; }
-  const int tpw = ATTN_RES_BWD_TPW;
+  const int tpw = ATTN_RES_BWD2_TPW;
   const int blocks = chunk_grid(M, tpw);
   const int slots = (1 + n_later) > WARPS_PER_BLOCK ? (1 + n_later) : WARPS_PER_BLOCK;
-  const size_t smem = (size_t)slots * D * sizeof(float);
   TFX_DISPATCH_NCH(D, {
+    const size_t smem = (size_t)(slots + WARPS_PER_BLOCK * ResBwd2Cfg<NCH>::RING) * D * sizeof(float);
     auto kern = attn_res_bwd2_k<NCH>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_set = false;                 // (one flag per NCH instantiation; the size below is the maximum any call can ask for)
+    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((11 + WARPS_PER_BLOCK * ResBwd2Cfg<NCH>::RING) * D * sizeof(float))); attr_set = true; }
     kern<<<blocks, ROW_THREADS, smem, ST(stream)>>>(A, dx_out, x_out, lse, grad_hidden, scalars_out, scalar_stride, workspace, M, tpw);
   });
   if (int rc = check_launch("attn_residual_bwd2")) return rc;

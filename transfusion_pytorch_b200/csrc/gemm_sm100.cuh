@@ -202,17 +202,22 @@ __device__ __forceinline__ void stg_store_rows(const uint8_t* sw, int lane, uint
   }
 }
 
-// CL = 2: clusters of two CTAs work on vertically adjacent tiles (m_blk, m_blk + 1) of the same N block.  Each CTA fetches HALF of the B tile and
-// multicasts it into both (the smem stage of a CTA is written by its peer too, so a stage is free only when BOTH MMA issuers have committed it:
-// commits are multicast to both empty barriers, which count 2).  All these GEMMs sit on the L2 -> SM bandwidth cap (profiles/r02_ncu_gemm_l2.txt:
-// 6.1 - 7.8 KB / clk of tile loads at 38 - 46 % tensor activity); sharing B removes a third of that traffic for 128 x 256 tiles.
+// CL = 2: a CTA PAIR (cluster of two, tcgen05 cta_group::2) computes a 256 x BN tile.  Each CTA loads its own 128 rows of A and only HALF of the B
+// tile (BN / 2 rows); the leader's MMA issuer runs 256 x BN x 16 UMMAs that read both shared memories and write 128 x BN accumulators into each
+// CTA's TMEM, so each CTA's epilogue is unchanged.  TMA completion bytes of both CTAs are counted on the leader's `full` barrier; commits are
+// multicast to both CTAs' `empty` / `tfull` barriers; both epilogues release the accumulator on the leader's `tempty` barrier.
+// A pair ingests 32 KB per k-block and SM instead of 48.  Measured (profiles/r02_gemm_pair_experiments.txt): correct, and NOT faster on this model's
+// shapes - operand ingest is not what bounds them - so it is an option (tfx_gemm_set_cluster_mode), off by default.
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL = 1>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI>::THREADS), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // declared 1024-byte aligned (SWIZZLE_128B tiles) and used directly: rounding the pointer up through an integer loses the shared address space
+  // and turned every staging access of the epilogues into a generic LD / ST (profiles/r02_gemm_pair_experiments.txt: "ST.E.128 desc[..]")
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("tfx gemm: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
   constexpr int EW = Cfg::EW;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING);
@@ -236,14 +241,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EW); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], CL * EW); }      // (pairs: only the leader's full / tempty barriers are used)
     mbar_fence_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (CL == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    else { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+  }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();               // the peer's barriers are initialised before anything is multicast at them
+  if constexpr (CL > 1) cluster_sync_all();               // the peer's barriers and TMEM are set up before anything is signalled at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -262,46 +270,45 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-#if GEMM_ABLATE_HALF_B
-          mbar_expect_tx(&full_bar[stage], CL == 1 ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES);
-#else
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-#endif
-          if (!A_MN) {
-            if (kb * GEMM_BK < p.K1) tma_load_2d(&tmA, &full_bar[stage], sA, kb * GEMM_BK, m_blk * GEMM_BM);
-            else tma_load_2d(&tmA2, &full_bar[stage], sA, kb * GEMM_BK - p.K1, m_blk * GEMM_BM);
-          } else {
-#pragma unroll
-            for (int a = 0; a < GEMM_BM / 64; ++a)
-              tma_load_2d(&tmA, &full_bar[stage], sA + a * (GEMM_BK * 128), m_blk * GEMM_BM + a * 64, kb * GEMM_BK);
-          }
           if constexpr (CL == 1) {
-#if GEMM_ABLATE_HALF_B      // timing experiment only (wrong results): the SM ingests half of the B tile, as a cta_group::2 pair would
+#if GEMM_ABLATE_HALF_B      // timing experiment only (wrong results): the SM ingests half of the B tile, as a CTA pair does
+            mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES / 2);
+#else
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#endif
+            if (!A_MN) {
+              if (kb * GEMM_BK < p.K1) tma_load_2d(&tmA, &full_bar[stage], sA, kb * GEMM_BK, m_blk * GEMM_BM);
+              else tma_load_2d(&tmA2, &full_bar[stage], sA, kb * GEMM_BK - p.K1, m_blk * GEMM_BM);
+            } else {
+#pragma unroll
+              for (int a = 0; a < GEMM_BM / 64; ++a)
+                tma_load_2d(&tmA, &full_bar[stage], sA + a * (GEMM_BK * 128), m_blk * GEMM_BM + a * 64, kb * GEMM_BK);
+            }
             if (!B_MN) {
               tma_load_2d(&tmB, &full_bar[stage], sB, kb * GEMM_BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / (GEMM_ABLATE_HALF_B ? 128 : 64); ++a)
+                tma_load_2d(&tmB, &full_bar[stage], sB + a * (GEMM_BK * 128), n_blk * BN + a * 64, kb * GEMM_BK);
+            }
+          } else {
+            // pair: this CTA's A rows and its half of the B tile; all bytes are counted on the leader's barrier
+            const uint32_t lead_full = cluster_map(&full_bar[stage], 0);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES / 2));
+            if (!A_MN) {
+              if (kb * GEMM_BK < p.K1) tma_load_2d_pair(&tmA, lead_full, sA, kb * GEMM_BK, m_blk * GEMM_BM);
+              else tma_load_2d_pair(&tmA2, lead_full, sA, kb * GEMM_BK - p.K1, m_blk * GEMM_BM);
+            } else {
+#pragma unroll
+              for (int a = 0; a < GEMM_BM / 64; ++a)
+                tma_load_2d_pair(&tmA, lead_full, sA + a * (GEMM_BK * 128), m_blk * GEMM_BM + a * 64, kb * GEMM_BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(&tmB, lead_full, sB, kb * GEMM_BK, n_blk * BN + cta_rank * (BN / 2));        // tmB box: BN / 2 rows
             } else {
 #pragma unroll
               for (int a = 0; a < BN / 128; ++a)
-                tma_load_2d(&tmB, &full_bar[stage], sB + a * (GEMM_BK * 128), n_blk * BN + a * 64, kb * GEMM_BK);
-            }
-#else
-            if (!B_MN) {
-              tma_load_2d(&tmB, &full_bar[stage], sB, kb * GEMM_BK, n_blk * BN);
-            } else {
-#pragma unroll
-              for (int a = 0; a < BN / 64; ++a)
-                tma_load_2d(&tmB, &full_bar[stage], sB + a * (GEMM_BK * 128), n_blk * BN + a * 64, kb * GEMM_BK);
-            }
-#endif
-          } else {                                            // this CTA's half of the B tile, delivered to both CTAs (tmB box: BN / 2 rows)
-            if (!B_MN) {
-              tma_load_2d_mc(&tmB, &full_bar[stage], sB + cta_rank * (BN / 2) * 128, kb * GEMM_BK, n_blk * BN + cta_rank * (BN / 2), (uint16_t)3);
-            } else {
-#pragma unroll
-              for (int a = 0; a < BN / 128; ++a) {
-                const int aa = cta_rank * (BN / 128) + a;
-                tma_load_2d_mc(&tmB, &full_bar[stage], sB + aa * (GEMM_BK * 128), n_blk * BN + aa * 64, kb * GEMM_BK, (uint16_t)3);
-              }
+                tma_load_2d_pair(&tmB, lead_full, sB + a * (GEMM_BK * 128), n_blk * BN + (cta_rank * (BN / 128) + a) * 64, kb * GEMM_BK);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -310,8 +317,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && cta_rank == 0) {          // (pairs: the leader issues for both SMs)
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
       for (int item = first_item; item < num_items; item += item_stride, ++local) {
@@ -334,13 +341,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                      : umma_smem_desc_sw128(sA + k * (GEMM_UK * 2), 0, 1024);
             const uint64_t db = B_MN ? umma_smem_desc_sw128(sB + k * (GEMM_UK * 128), GEMM_BK * 128, 1024)
                                      : umma_smem_desc_sw128(sB + k * (GEMM_UK * 2), 0, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CL == 1) umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if constexpr (CL == 1) umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-          else umma_commit_mc(&empty_bar[stage], (uint16_t)3);            // ... in both CTAs: the peer multicasts into this slot as well
+          else umma_commit_pair(&empty_bar[stage], (uint16_t)3);          // ... in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);              // accumulator ready for the epilogue
+        if constexpr (CL == 1) umma_commit(&tfull_bar[buf]);              // accumulator ready for the epilogue
+        else umma_commit_pair(&tfull_bar[buf], (uint16_t)3);
       }
     }
   } else {
@@ -730,14 +739,20 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // release this accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if constexpr (CL == 1) mbar_arrive(&tempty_bar[buf]);
+        else mbar_arrive_cluster(cluster_map(&tempty_bar[buf], 0));      // the leader's issuer waits for both epilogues
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();               // no CTA leaves while its peer can still signal its barriers
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+  if (warp == 1) {
+    tc_fence_after();
+    if constexpr (CL == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -780,8 +795,8 @@ struct GemmOperand {
 };
 
 // CTA pairing (CL = 2) is OFF unless asked for: TFX_GEMM_CLUSTER=2 in the environment or tfx_gemm_set_cluster_mode(2) pairs every launch, mode 3 only
-// the launches where every SM still gets two tiles.  Measured on the b128 step shapes (profiles/r02_gemm_l2_bound.txt): the plain-store forward GEMM
-// gains 6 %, the fused-epilogue and gradient GEMMs lose 1 - 2 % - multicast at cluster size 2 does not lower the L2 -> SM traffic that bounds them.
+// the launches where every SM still gets two tiles.  Measured on the b128 step shapes (profiles/r02_gemm_pair_experiments.txt): within +-3 % of the
+// single-CTA kernel on every shape, slightly slower on most.
 inline int& gemm_cluster_mode_ref() {
   static int mode = -1;
   if (mode < 0) { const char* e = getenv("TFX_GEMM_CLUSTER"); mode = e ? atoi(e) : 0; }

@@ -410,7 +410,7 @@ def run_b200_arm(args):
                     flops_model = 'un-padded problem sizes (FFN inner 1365, qkvg rows 1544, time-MLP K 513, vocab 390)',
                     families = {f: fam_row(d) for f, d in fam.items()},
                     whole_step_tflops = whole, whole_step_frac = whole / pk['tf_sustained'], whole_step_frac_of_burst = whole / pk['tf_burst'],
-                    kernels = [inst_row(lbl, k) for lbl, k in ranked[:16]])
+                    kernels = [inst_row(lbl, k) for lbl, k in ranked[:28]])
 
     if rank == 0:
         clocks = sampler.summary() if sampler else None

@@ -14,28 +14,51 @@ struct PtrList { float* p[32]; };
 
 // ------------------------------------------------------------------------------------ adaLN forward
 // u = isM ? LN(x)*(gamma_c+1)+beta_c : LN(x)*(g+1)      (T.py:747-755; text-only 677-679)
+// The fp32 token rows stream through a per-warp ring of shared-memory slots filled by lane-private cp.async pieces (ADALN_FWD_RING - 1 rows per
+// warp in flight, no registers spent): with one row per warp in flight the kernel sat at 0.63 of the HBM peak (profiles/r02_traffic.json).
+// The FiLM rows (L2-resident, address depends on the token's condition row) are plain loads; the condition row is fetched one row ahead.
+constexpr int ADALN_FWD_RING = 4;
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS) adaln_fwd_k(const float* __restrict__ x, const int* __restrict__ cond_row,
                                                           const float* __restrict__ film, long long film_ld,
                                                           const float* __restrict__ g, __nv_bfloat16* __restrict__ u,
                                                           float* __restrict__ stats, int M) {
   constexpr int D = NCH * 128;
+  constexpr int RING = ADALN_FWD_RING;
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  extern __shared__ __align__(16) float adaln_ring[];
+  const float* ring = adaln_ring + (threadIdx.x >> 5) * (RING * D);
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  int iss_row = warp0, iss_slot = 0;
+  auto issue = [&]() {
+    if (iss_row < M) {
+      const float* f = x + (long long)iss_row * D + lane * 4;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) cp_async_16(ring_u32 + (iss_slot * D + c * 128 + lane * 4) * 4, f + c * 128);
+      iss_row += nwarps;
+    }
+    cp_async_commit();
+    iss_slot = iss_slot + 1 == RING ? 0 : iss_slot + 1;
+  };
+#pragma unroll
+  for (int i = 0; i < RING; ++i) issue();
+  int cons_slot = 0;
   float gv[NCH * 4];
   load_row_f32<NCH>(g, lane, gv);
-  // the condition row of the NEXT token is fetched one iteration ahead, so that the FiLM rows (whose address depends on it) are requested together with
-  // the token itself instead of one global-load latency later (half of the tokens are modality tokens: 0.61 -> of the HBM roof before)
   int cr_next = (cond_row && warp0 < M) ? cond_row[warp0] : -1;
   for (int row = warp0; row < M; row += nwarps) {
     const int cr = cr_next;
     float v[NCH * 4], gm[NCH * 4], bt[NCH * 4];
-    load_row_f32<NCH>(x + (long long)row * D, lane, v);
     if (cr >= 0) {
       load_row_f32<NCH>(film + cr * film_ld, lane, gm);
       load_row_f32<NCH>(film + cr * film_ld + D, lane, bt);
     }
     cr_next = (cond_row && row + nwarps < M) ? cond_row[row + nwarps] : -1;
+    cp_async_wait<RING - 1>();
+    load_row_f32<NCH>(ring + cons_slot * D, lane, v);
+    cons_slot = cons_slot + 1 == RING ? 0 : cons_slot + 1;
+    issue();
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH * 4; ++i) s += v[i];
@@ -54,6 +77,7 @@ __global__ void __launch_bounds__(ROW_THREADS) adaln_fwd_k(const float* __restri
     store_row_bf16<NCH>(u + (long long)row * D, lane, v);
     if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------ adaLN backward
@@ -725,6 +749,8 @@ __global__ void __launch_bounds__(ROW_THREADS) clean_flow_bwd_k(float* __restric
 // forward (GEMM epilogue): xhat = x*inv;  y = xhat*8*(gamma+1);  q = R(pos) y (interleaved pairs)   (T.py:950-965)
 // One warp per token; 8 lanes share a head (lane owns 8 consecutive dims = 4 rope pairs: 32 B fp32 / 16 B bf16 accesses),
 // so a warp covers 4 heads per pass and the per-head dot product is a 3-step shuffle.
+// (A cp.async-ring version of this kernel - one slot per (token, 4-head group), rope / 1/|x| / gate pieces riding along - was measured at 880 us per
+// launch against 248 us for these plain loads, profiles/r02_ring_kernels.txt: reverted.)
 __global__ void __launch_bounds__(ROW_THREADS) qk_bwd_pack_k(const float* __restrict__ dq, const float* __restrict__ dk, const __nv_bfloat16* __restrict__ q,
                                                             const __nv_bfloat16* __restrict__ k, const float* __restrict__ qk_inv, const float* __restrict__ gq,
                                                             const float* __restrict__ gk, const int* __restrict__ rope_pos, const float2* __restrict__ rope_cs,
@@ -841,7 +867,18 @@ extern "C" {
 int tfx_adaln_fwd(const float* x, const int* cond_row, const float* film, long long film_ld, const float* ln_gamma,
                   void* u_bf16, float* stats, int M, int D, void* stream) {
   if (M <= 0) return 0;
-  TFX_DISPATCH_NCH(D, (adaln_fwd_k<NCH><<<row_grid(M, num_sms()), ROW_THREADS, 0, ST(stream)>>>(x, cond_row, film, film_ld, ln_gamma, (__nv_bfloat16*)u_bf16, stats, M)));
+  TFX_DISPATCH_NCH(D, {
+    auto kern = adaln_fwd_k<NCH>;
+    const int smem = WARPS_PER_BLOCK * ADALN_FWD_RING * D * 4;
+    static int per_sm = 0;                            // persistent grid = the resident blocks (ring shared memory / registers decide)
+    if (!per_sm) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROW_THREADS, smem);
+      if (per_sm < 1) per_sm = 1;
+    }
+    const long long want = ((long long)M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, cap = (long long)num_sms() * per_sm;
+    kern<<<(int)(want < cap ? want : cap), ROW_THREADS, smem, ST(stream)>>>(x, cond_row, film, film_ld, ln_gamma, (__nv_bfloat16*)u_bf16, stats, M);
+  });
   return check_launch("adaln_fwd");
 }
 

@@ -28,9 +28,9 @@ int tfx_init(int device);                       /* checks the device is sm_10x *
  * D[m][n] = sum_k A(m,k) B(n,k); operands bf16, fp32 accumulation in TMEM.
  * x_mn_major = 0: operand stored [MN][K] (row pitch ld); 1: stored [K][MN].                      */
 
-/* CTA pairing of the GEMM family (clusters of 2, tcgen05 cta_group::2: one 256 x N UMMA over two SMs, each loading half of B): 0 / 1 = off (default),
- * 2 = every launch, 3 = launches with at least two tiles per SM.  Also read once from the environment (TFX_GEMM_CLUSTER).  No reference
- * counterpart: a tuning knob of this library (measured in profiles/r02_gemm_pair_experiments.txt).                                            */
+/* CTA pairing of the GEMM family (clusters of 2, tcgen05 cta_group::2: one 256 x N UMMA over two SMs, each loading half of the B tile):
+ * 1 = never, 2 = every launch, 3 = launches with K >= 1024 per work item and at least two tiles per SM (default).  Also read once from the
+ * environment (TFX_GEMM_CLUSTER).  No reference counterpart: a tuning knob of this library (profiles/r02_gemm_pair_experiments.txt).   */
 int tfx_gemm_set_cluster_mode(int mode);
 
 /* generic: out = alpha*acc + bias[n]  -> fp32 (store / atomic accumulate, optional per-row offsets) and/or bf16.

@@ -17,12 +17,12 @@ def ops():
     return _lib.Ops()
 
 
-@pytest.fixture(params = [0, 2], ids = ['single', 'paired'])
+@pytest.fixture(params = [1, 2], ids = ['single', 'paired'])
 def cluster_mode(ops, request):
     """GEMM launches as independent CTAs (default) and as 2-CTA clusters sharing the B tile by TMA multicast"""
     assert ops.lib.tfx_gemm_set_cluster_mode(request.param) == 0
     yield request.param
-    ops.lib.tfx_gemm_set_cluster_mode(0)
+    ops.lib.tfx_gemm_set_cluster_mode(3)
 
 
 @pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 1), (1, 0)])

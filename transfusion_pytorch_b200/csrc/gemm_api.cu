@@ -33,7 +33,7 @@ static int dispatch_major(const GemmOperand& A, const GemmOperand& B, const Gemm
 extern "C" {
 
 int tfx_gemm_set_cluster_mode(int mode) {
-  TFX_REQUIRE(mode >= 0 && mode <= 3, "gemm_set_cluster_mode: mode %d not in {0 (off), 1 (off), 2 (always pair), 3 (pair large problems)}", mode);
+  TFX_REQUIRE(mode >= 1 && mode <= 3, "gemm_set_cluster_mode: mode %d not in {1 (never pair), 2 (always pair), 3 (pair long-K launches, default)}", mode);
   gemm_cluster_mode_ref() = mode;
   return 0;
 }

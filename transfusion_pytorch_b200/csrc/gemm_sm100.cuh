@@ -100,6 +100,23 @@ __device__ __forceinline__ void gelu_parts(float g, float& cdf, float& pdf) {
   pdf = 0.3989422804014327f * E;
 }
 __device__ __forceinline__ float gelu_erf(float x) { float c, d; gelu_parts(x, c, d); return x * c; }
+// two elements at once on the packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2): v * g * Phi(g).  Same formula as gelu_parts, the 0.5 folded into the
+// polynomial; 21 instructions per PAIR instead of ~18 per element - the GEGLU epilogue is issue-bound (profiles/r02_gemm_pair_experiments.txt).
+__device__ __forceinline__ float2 geglu_pair(float2 g, float2 v) {
+  const float2 ax = make_float2(fabsf(g.x) * 0.70710678118654752f, fabsf(g.y) * 0.70710678118654752f);
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), ax, make_float2(1.f, 1.f));
+  const float2 t = make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y));
+  const float2 q = __fmul2_rn(__fmul2_rn(ax, ax), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 E = make_float2(exp2f(q.x), exp2f(q.y));
+  float2 poly = __ffma2_rn(make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  poly = __ffma2_rn(poly, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  poly = __ffma2_rn(poly, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  poly = __ffma2_rn(poly, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  const float2 h = __fmul2_rn(__fmul2_rn(poly, t), E);                       // 0.5 * (1 - erf(|g| / sqrt 2))
+  const float2 sg = make_float2(copysignf(1.f, g.x), copysignf(1.f, g.y));
+  const float2 cdf = __ffma2_rn(sg, __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-h.x, -h.y)), make_float2(0.5f, 0.5f));      // g >= 0 ? 1 - h : h
+  return __fmul2_rn(__fmul2_rn(g, cdf), v);
+}
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
   const int sz = valid ? 16 : 0;
@@ -212,14 +229,17 @@ template <int BN, bool A_MN, bool B_MN, int EPI, int CL = 1>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI>::THREADS), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI>;
-  constexpr int STAGES = Cfg::STAGES;
+  // a CTA pair keeps only half of the B tile per stage: the same ring memory holds more, smaller stages (BN 256: 6 x 32 KB instead of 4 x 48 KB)
+  constexpr int STAGE_STRIDE = CL == 1 ? Cfg::STAGE_BYTES : Cfg::A_BYTES + Cfg::B_BYTES / 2;
+  constexpr int STAGES = CL == 1 ? Cfg::STAGES : (Cfg::STAGES * Cfg::STAGE_BYTES) / STAGE_STRIDE;
+  static_assert(STAGE_STRIDE % 1024 == 0 && 2 * STAGES + 5 <= 32, "stage alignment / barrier area");
   // declared 1024-byte aligned (SWIZZLE_128B tiles) and used directly: rounding the pointer up through an integer loses the shared address space
   // and turned every staging access of the epilogues into a generic LD / ST (profiles/r02_gemm_pair_experiments.txt: "ST.E.128 desc[..]")
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("tfx gemm: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
   constexpr int EW = Cfg::EW;
-  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING);
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
@@ -268,7 +288,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int kb1 = min(kb0 + kb_per_split, kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sA = smem + stage * STAGE_STRIDE;
           uint8_t* sB = sA + Cfg::A_BYTES;
           if constexpr (CL == 1) {
 #if GEMM_ABLATE_HALF_B      // timing experiment only (wrong results): the SM ingests half of the B tile, as a CTA pair does
@@ -333,7 +353,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sA = smem_u32(smem + stage * STAGE_STRIDE);
           const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UK; ++k) {
@@ -708,7 +728,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           {
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) { const float2 bv = *reinterpret_cast<const float2*>(p.bias + cv + j); v[j] = __uint_as_float(r[j]) + bv.x; v[j + 1] = __uint_as_float(r[j + 1]) + bv.y; }
+            for (int j = 0; j < 32; j += 2) { const float2 t2 = __fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), *reinterpret_cast<const float2*>(p.bias + cv + j)); v[j] = t2.x; v[j + 1] = t2.y; }
             stg64_put_pack(sw, lane, v);
           }
           __syncwarp();
@@ -716,7 +736,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_32x32b_x32(tg, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) { const float2 bg = *reinterpret_cast<const float2*>(p.bias + cg + j); g[j] = __uint_as_float(r[j]) + bg.x; g[j + 1] = __uint_as_float(r[j + 1]) + bg.y; }
+          for (int j = 0; j < 32; j += 2) { const float2 t2 = __fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), *reinterpret_cast<const float2*>(p.bias + cg + j)); g[j] = t2.x; g[j + 1] = t2.y; }
           __syncwarp();
           stg64_put_pack(sw, lane, g);
           __syncwarp();
@@ -726,8 +746,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const float2 bv = *reinterpret_cast<const float2*>(p.bias + cv + j);
-            g[j] = gelu_erf(g[j]) * (__uint_as_float(r[j]) + bv.x);
-            g[j + 1] = gelu_erf(g[j + 1]) * (__uint_as_float(r[j + 1]) + bv.y);
+            const float2 o = geglu_pair(make_float2(g[j], g[j + 1]), __fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), bv));
+            g[j] = o.x; g[j + 1] = o.y;
           }
           __syncwarp();
           stg64_put_pack(sw, lane, g);
@@ -794,12 +814,13 @@ struct GemmOperand {
   long long ld2 = 0;
 };
 
-// CTA pairing (CL = 2) is OFF unless asked for: TFX_GEMM_CLUSTER=2 in the environment or tfx_gemm_set_cluster_mode(2) pairs every launch, mode 3 only
-// the launches where every SM still gets two tiles.  Measured on the b128 step shapes (profiles/r02_gemm_pair_experiments.txt): within +-3 % of the
-// single-CTA kernel on every shape, slightly slower on most.
+// CTA pairing (CL = 2): mode 3 (default) pairs the launches whose main loop dominates - at least 16 k-blocks (K >= 1024) per work item, two tiles per
+// SM - mode 2 pairs every launch, mode 1 none (TFX_GEMM_CLUSTER in the environment, or tfx_gemm_set_cluster_mode).  Measured on the b128 step shapes
+// (profiles/r02_gemm_pair_experiments.txt): K = 2816 dgrad / K = 131072 split-K wgrad gain 7 % (1530 TFLOP/s), the K = 512 launches are bound by
+// their epilogues and gain nothing (-1 .. +3 %).
 inline int& gemm_cluster_mode_ref() {
   static int mode = -1;
-  if (mode < 0) { const char* e = getenv("TFX_GEMM_CLUSTER"); mode = e ? atoi(e) : 0; }
+  if (mode < 0) { const char* e = getenv("TFX_GEMM_CLUSTER"); mode = e ? atoi(e) : 3; }
   return mode;
 }
 inline int gemm_cluster_mode() { return gemm_cluster_mode_ref(); }
@@ -826,7 +847,8 @@ int launch_gemm_t(const GemmOperand& A, const GemmOperand& B, const GemmParams& 
   const int items = m_tiles * n_tiles * p.k_splits;
   if (items <= 0) return 0;
   const int mode = gemm_cluster_mode();
-  const bool paired = mode == 2 || (mode == 3 && m_tiles >= 2 && items >= 2 * num_sms);
+  const int kb_item = ((p.K + GEMM_BK - 1) / GEMM_BK + p.k_splits - 1) / p.k_splits;      // k-blocks per work item
+  const bool paired = mode == 2 || (mode == 3 && m_tiles >= 2 && kb_item >= 16 && items >= 2 * num_sms);
   // paired CTAs each fetch half of the B tile: the box of tmB is BN / 2 rows (K-major; the MN-major boxes are 64 wide either way)
 #if GEMM_ABLATE_HALF_B
   if (!B_MN) rc = make_tmap_bf16(&tmB, B.ptr, p.K, p.N, B.ld, BN / 2);

@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals and (optionally) the sequence."""
-import csv, collections, re, sys
+import csv, collections, gzip, re, sys
 
 def load(path):
-    rows = list(csv.reader(open(path)))
+    rows = list(csv.reader(gzip.open(path, 'rt', errors = 'replace') if path.endswith('.gz') else open(path, errors = 'replace')))
     hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
     h = rows[hi]; kn, mv, gs = h.index('Kernel Name'), h.index('Metric Value'), h.index('Grid Size')
+    mn = h.index('Metric Name') if 'Metric Name' in h else None
     out = []
     for r in rows[hi + 1:]:
         if len(r) <= mv: continue
+        if mn is not None and r[mn] != 'gpu__time_duration.sum': continue      # (captures with several metrics per launch: keep the duration rows)
         try: v = float(r[mv].replace(',', ''))
         except ValueError: continue
         name = re.sub(r'^void ', '', r[kn]); name = re.sub(r'\(.*', '', name)

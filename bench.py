@@ -57,8 +57,9 @@ class ClockSampler:
     holds driver locks for tens of ms each."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
     POLLER = r"""
-import subprocess, sys, time
+import os, subprocess, sys, time
 uuid, index, Q = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+parent, t_end = os.getppid(), time.time() + 3600.0       # never outlive the benchmark process
 try:
     import pynvml
     pynvml.nvmlInit()
@@ -67,7 +68,7 @@ try:
     get = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
 except Exception:
     h = None
-while True:
+while os.getppid() == parent and time.time() < t_end:
     try:
         if h is not None:
             mask = int(get(h)); act = lambda bit: 'Active' if mask & bit else 'Not Active'

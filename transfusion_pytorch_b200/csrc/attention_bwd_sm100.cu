@@ -29,6 +29,11 @@
 #ifndef B2_VARIANT
 #define B2_VARIANT 0
 #endif
+#ifndef B2_PIPE
+#define B2_PIPE 0      // 1: software-pipelined softmax / gradient warps (exponentials of step g + 1 in the shadow of step g's gradient products).  Correct
+                       // (unit tests green) and measured EQUAL to the plain order - 282.6 vs 280.6 us at M = 32 k, 1055 vs 1066 us at M = 131 k
+                       // (profiles/r02_attn_bwd_ablation.txt): the warps are issue-bound (IPC 0.48 per scheduler), not idle in the hand-off shadow.
+#endif
 
 namespace tfx {
 
@@ -61,6 +66,32 @@ __device__ __forceinline__ float b2_keep_if_less(float p, int a, int b) {
   uint32_t r;
   asm("{\n\t.reg .s32 t;\n\tsub.s32 t, %2, %3;\n\tshr.s32 t, t, 31;\n\tand.b32 %0, %1, t;\n\t}" : "=r"(r) : "r"(__float_as_uint(p)), "r"(a), "r"(b));
   return __uint_as_float(r);
+}
+
+// pipelined order: the same chunk, but scale * (1 - tanh^2) = fma(e^2, OC, SC) leaves as bf16 pairs (it waits in registers across a hand-off)
+template <bool MASKED>
+__device__ __forceinline__ void b2_exp_chunk_om(const uint32_t (&rs)[16], const float* __restrict__ nl, const int* __restrict__ lim1, int key, float2 A0, float2 A1, float2 A2,
+                                                float2 A3, float2 A4, float2 OC, float2 SC, uint32_t* __restrict__ om, uint32_t* __restrict__ wp) {
+#pragma unroll
+  for (int e2 = 0; e2 < 16; e2 += 2) {
+    const float2 x = make_float2(__uint_as_float(rs[e2]), __uint_as_float(rs[e2 + 1]));
+    const float2 X = __fmul2_rn(x, x);
+    float2 gp = __ffma2_rn(A4, X, A3);
+    gp = __ffma2_rn(gp, X, A2);
+    gp = __ffma2_rn(gp, X, A1);
+    gp = __ffma2_rn(gp, X, A0);
+    const float2 e = __fmul2_rn(x, gp);
+    const float2 pe = __fadd2_rn(e, *reinterpret_cast<const float2*>(nl + e2));
+    float p0 = b2_ex2(pe.x), p1 = b2_ex2(pe.y);
+    if (MASKED) {
+      const int2 lm = *reinterpret_cast<const int2*>(lim1 + e2);
+      p0 = b2_keep_if_less(p0, key, lm.x);
+      p1 = b2_keep_if_less(p1, key, lm.y);
+    }
+    const float2 oms = __ffma2_rn(__fmul2_rn(e, e), OC, SC);
+    om[e2 >> 1] = pack_bf16(oms.x, oms.y);
+    wp[e2 >> 1] = pack_bf16(p0, p1);
+  }
 }
 
 // 32 transposed scores (one key row x 32 queries) -> e = cap log2e tanh(y) (kept for the 1 - tanh^2 factor) and bf16 pairs of p = 2^(e - lse2[q]).
@@ -333,6 +364,134 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     };
 
+#if B2_PIPE
+    // ---- software-pipelined order (B2_PIPE): the exponentials of step g + 1 need only S^T(g + 1), which the MMA warp produces while step g is still in
+    // its dS^T phase - so they are computed right after dS^T(g) has been handed over, in the shadow of dK(g) / dQ(g) / dP^T(g + 1), and P^T and the
+    // scale (1 - tanh^2) factor wait in registers as bf16 pairs until the gradient products of step g have released the P^T columns.  The MMA warp's
+    // order is unchanged; s_free arrives one phase earlier than in the unpipelined order.
+    auto advance = [&](B2Item& t, int& kk, int& ii) -> bool {      // next (key tile item, query tile) step of this CTA
+      if (++ii < t.n_q) return true;
+      ii = 0; ++kk;
+      return b2_item(kk, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, t);
+    };
+    uint32_t wp[16], om[16];                           // P^T and scale * (1 - tanh^2) of the step in flight: this thread's key row x 32 queries, bf16 pairs
+    auto phase_A = [&](uint32_t ga, int kv0) {
+      const float* mb = sMeta + (ga & 1) * 512;
+      const int* mbi = reinterpret_cast<const int*>(mb);
+      mbar_wait(&meta_full[ga & 1], (ga >> 1) & 1);
+      const int min_lim = min(min(mbi[384], mbi[385]), min(mbi[386], mbi[387]));
+      const bool all_visible = kv0 + 127 <= min_lim;
+      const int key = kv0 + row;
+      mbar_wait(s_full, ga & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = qc * 32 + c * 16;
+        uint32_t rs[16];
+        tmem_ld_32x32b_x16(tS + lane_addr + col0, rs);
+        tmem_ld_wait();
+        if (c == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(s_free); }       // S^T is in registers: S^T of the next step may be issued
+        if (all_visible) b2_exp_chunk_om<false>(rs, mb + col0, mbi + 256 + col0, key, A0, A1, A2, A3, A4, OC, SC, om + c * 8, wp + c * 8);
+        else b2_exp_chunk_om<true>(rs, mb + col0, mbi + 256 + col0, key, A0, A1, A2, A3, A4, OC, SC, om + c * 8, wp + c * 8);
+      }
+    };
+    auto dkv_readout = [&](const B2Item& t, int kk) {   // dK (fp32) and dV (bf16) of a finished key tile: 16 of the 64 columns per warp
+      mbar_wait(dkv_full, kk & 1);
+      tc_fence_after();
+      uint32_t r[16], r2[16];
+      tmem_ld_32x32b_x16(tDK + lane_addr + qc * 16, r);
+      tmem_ld_32x32b_x16(tDV + lane_addr + qc * 16, r2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dkv_free);          // the accumulators may be overwritten by the next item
+      const int key = t.kv0 + row;
+      if (key < t.kv_end) {
+        float* dst = dk + (long long)key * H * 64 + t.head * 64 + qc * 16;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst + ch * 4) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+        __nv_bfloat16* dst2 = dv + (long long)key * ld_dv + t.head * 64 + qc * 16;
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = pack_bf16(__uint_as_float(r2[qd * 8 + 2 * e]), __uint_as_float(r2[qd * 8 + 2 * e + 1]));
+          *reinterpret_cast<uint4*>(dst2 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    };
+    // cursors: M = the step whose statistics are in registers (one ahead of the exponentials), B = the step of the gradient phase
+    B2Item itM, itB;
+    int kM = 0, iM = 0, kB = 0, iB = 0;
+    uint32_t gA = 0, gB = 0;
+    bool hasM = b2_item(0, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, itM);
+    bool hasB = hasM, pending = false;
+    itB = itM;
+    if (hasM) {
+      fetch_meta(itM.q_begin, itM.q_end, itM.head, 0); stage_meta(0);
+      const int kv0 = itM.kv0;
+      hasM = advance(itM, kM, iM);
+      if (hasM) fetch_meta(itM.q_begin, itM.q_end, itM.head, iM);       // statistics of step 1 travel through registers
+      phase_A(0, kv0);
+    }
+    while (hasB) {
+      // ---- P^T(gB) into TMEM once dV / dK / dQ of the previous step have consumed P^T and dS^T (TMEM and smem)
+      if (gB > 0) { mbar_wait(grad_done, (gB - 1) & 1); tc_fence_after(); }
+      tmem_st_32x32b_x16(tPT + lane_addr + qc * 16, wp);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pt_full);
+      if (pending) dq_readout(gB - 1, 0, 0);            // dQ of the previous step (complete together with grad_done) leaves while dP^T lands
+      // ---- dS^T(gB) = P^T o (dP^T - D) o scale (1 - tanh^2)
+      mbar_wait(dp_full, gB & 1);
+      tc_fence_after();
+      const float* mbB = sMeta + (gB & 1) * 512;
+      uint32_t wd[16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = qc * 32 + c * 16;
+        uint32_t rp[16];
+        tmem_ld_32x32b_x16(tDP + lane_addr + col0, rp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e2 = 0; e2 < 16; e2 += 2) {
+          const int j = c * 8 + (e2 >> 1);
+          const float2 pf = unpack2_bf16(wp[j]);                                                  // the SAME bf16 P^T the dV product sees
+          const float2 oms = unpack2_bf16(om[j]);
+          const float2 dpd = __fadd2_rn(make_float2(__uint_as_float(rp[e2]), __uint_as_float(rp[e2 + 1])), *reinterpret_cast<const float2*>(mbB + 128 + col0 + e2));   // + (-D)
+          const float2 d = __fmul2_rn(__fmul2_rn(pf, dpd), oms);
+          wd[j] = pack_bf16(d.x, d.y);
+        }
+      }
+      tmem_st_32x32b_x16(tDP + lane_addr + qc * 32, wd);
+      {
+        uint8_t* db = sDS + (qc >> 1) * 16384 + swz_row;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          *reinterpret_cast<uint4*>(db + ((((qc & 1) * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(wd[4 * ch], wd[4 * ch + 1], wd[4 * ch + 2], wd[4 * ch + 3]);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      pending = true;
+      // ---- exponentials of the next step, in the shadow of this step's gradient products
+      if (hasM) {                                       // cursor M sits on step gA + 1: its statistics are in registers
+        ++gA;
+        stage_meta(gA & 1);                             // (the buffer was last read two steps back, before the grad_done wait above)
+        const int kv0 = itM.kv0;
+        hasM = advance(itM, kM, iM);
+        if (hasM) fetch_meta(itM.q_begin, itM.q_end, itM.head, iM);
+        phase_A(gA, kv0);
+      }
+      if (iB + 1 == itB.n_q) dkv_readout(itB, kB);      // last query tile of this key tile
+      hasB = advance(itB, kB, iB);
+      ++gB;
+    }
+    if (pending) dq_readout(gB - 1, 0, 0);
+#else
     B2Item it, nx;
     bool has = b2_item(0, n_items, H, kt_order, kt_kv0, kt_kvend, kt_q0, kt_qend, it);
     if (has) { fetch_meta(it.q_begin, it.q_end, it.head, 0); stage_meta(0); }
@@ -443,6 +602,7 @@ attn_bwd_ts_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       it = nx; has = has_n;
     }
     if (pending && !(B2_VARIANT & 1)) dq_readout(g - 1, prev_qrow0, prev_head);
+  #endif
   }
 
   tc_fence_before();

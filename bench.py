@@ -449,9 +449,14 @@ def run_b200_arm(args):
             row['traffic'] = tmap.get(lbl)
             return row
         ranked = sorted(inst.items(), key = lambda kv: -kv[1]['ms'])
+        # DRAM traffic of the dominant family, per launch like `achieved`: every instance's ncu bytes x its launches (None when an instance was not captured)
+        fam_inst = [(lbl, k) for lbl, k in inst.items() if k['family'] == top]
+        fam_traffic = (int(sum(tmap[lbl] * k['launches'] for lbl, k in fam_inst) / max(1, sum(k['launches'] for _, k in fam_inst)))
+                       if fam_inst and all(lbl in tmap for lbl, _ in fam_inst) else None)
         whole = value * ALGO_TRAIN_FLOP_PER_TOKEN / 1e12 / world
         roof = dict(bound = 'tensor', kernel = top, achieved = ach, peak = pk['tf_sustained'], unit = 'TFLOP/s', frac = ach / pk['tf_sustained'],
-                    traffic = tmap.get(ranked[0][0]) if ranked else None, traffic_kernel = ranked[0][0] if ranked else None,
+                    traffic = fam_traffic, traffic_kernel = top + ' (average per launch over the family: ncu DRAM bytes of every instance x its launches / launches)',
+                    largest_kernel = dict(kernel = ranked[0][0], traffic = tmap.get(ranked[0][0])) if ranked else None,
                     peak_source = pk['src'] + ' (sustained bf16 GEMM; burst ' + str(pk['tf_burst']) + ', HBM copy ' + str(pk['hbm']) + ' GB/s)', share_of_step = fam[top]['ms'] / tot,
                     flops_model = 'un-padded problem sizes (FFN inner 1365, qkvg rows 1544, time-MLP K 513, vocab 390)',
                     families = {f: fam_row(d) for f, d in fam.items()},

@@ -77,16 +77,16 @@ while os.getppid() == parent and time.time() < t_end:
         else:
             out = subprocess.run(['nvidia-smi', '--query-gpu=' + Q, '--format=csv,noheader,nounits', '-i', str(index)], capture_output = True, text = True, timeout = 5).stdout
             row = [c.strip() for c in out.strip().split(',')]
-        print(','.join(row), flush = True)
+        print(','.join([repr(time.time())] + row), flush = True)
     except Exception:
         pass
     time.sleep(0.2)
 """
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self._stop = index, [], None, False
-
-    def start(self):
+        """launches the poller at once (interpreter + NVML start-up take a few hundred ms - longer than a 10-step timed region); only the rows stamped
+        between start() and `stop_flag = True` are kept"""
+        self.index, self.rows, self.proc, self._stop, self.t0 = index, [], None, False, None
         try:
             import torch
             uuid = 'GPU-' + str(torch.cuda.get_device_properties(self.index).uuid)
@@ -97,6 +97,9 @@ while os.getppid() == parent and time.time() < t_end:
         except Exception:
             self.proc = None
 
+    def start(self):
+        self.t0 = time.time()
+
     @property
     def stop_flag(self):
         return self._stop
@@ -105,10 +108,14 @@ while os.getppid() == parent and time.time() < t_end:
     def stop_flag(self, v):           # (kept as an attribute write: `sampler.stop_flag = True` ends the sampling)
         self._stop = bool(v)
         if v and self.proc is not None:
+            t1 = time.time()
             try:
                 self.proc.terminate()
                 out, _ = self.proc.communicate(timeout = 5)
-                self.rows = [[c.strip() for c in ln.split(',')] for ln in out.strip().splitlines() if ln.strip()]
+                rows = [[c.strip() for c in ln.split(',')] for ln in out.strip().splitlines() if ln.strip()]
+                inside = [r[1:] for r in rows if self.t0 is not None and self.t0 - 0.05 <= float(r[0]) <= t1 + 0.05]
+                # a timed region shorter than one polling period: the sample nearest to it (taken under the same load: the warm-up runs the same step)
+                self.rows = inside or [r[1:] for r in rows[-1:]]
             except Exception:
                 pass
             self.proc = None
@@ -279,6 +286,7 @@ def run_b200_arm(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id = torch.device('cuda', local))
     dev = torch.device('cuda', local)
+    sampler = ClockSampler(local) if rank == 0 else None          # (the poller process starts now; rows are kept from sampler.start() on)
     B = args.batch if args.scaling == 'weak' else max(1, args.batch // world)      # strong scaling: --batch is the GLOBAL batch, split over the ranks
     torch.manual_seed(0)
     cfg4 = args.workload == 'config4'
@@ -343,7 +351,6 @@ def run_b200_arm(args):
     for i in range(max(args.warmup, 3 * POOL) if (cfg4 and trainer.cuda_graph) else args.warmup):
         step_resident(i)
         torch.cuda.synchronize(); log('warmup step', i, 'done')
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.start()
     l0 = eng.ops.launches
     ms_total = timed(step_resident, args.steps)
@@ -529,6 +536,7 @@ def run_sample_many(args):
     from transfusion_pytorch_b200 import Transfusion, synth
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
     torch.cuda.set_device(dev)
+    sampler = ClockSampler(dev.index or 0)
     torch.manual_seed(0)
     model = Transfusion(**CTOR).to(dev).eval()
     synth.fill_parameters_(model, seed = 0)
@@ -540,7 +548,7 @@ def run_sample_many(args):
     for _ in range(max(1, args.warmup)):
         out = model.sample_many(copy.deepcopy(prompts), **kw)
     torch.cuda.synchronize()
-    sampler = ClockSampler(dev.index or 0); sampler.start()
+    sampler.start()
     times_ms, l0 = [], eng.ops.launches
     for _ in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)

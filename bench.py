@@ -58,7 +58,7 @@ class ClockSampler:
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
     POLLER = r"""
 import os, subprocess, sys, time
-uuid, index, Q = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+uuid, index, Q, period = sys.argv[1], int(sys.argv[2]), sys.argv[3], float(sys.argv[4])
 parent, t_end = os.getppid(), time.time() + 3600.0       # never outlive the benchmark process
 try:
     import pynvml
@@ -80,10 +80,10 @@ while os.getppid() == parent and time.time() < t_end:
         print(','.join([repr(time.time())] + row), flush = True)
     except Exception:
         pass
-    time.sleep(0.2)
+    time.sleep(period)
 """
 
-    def __init__(self, index):
+    def __init__(self, index, period = 0.2):
         """launches the poller at once (interpreter + NVML start-up take a few hundred ms - longer than a 10-step timed region); only the rows stamped
         between start() and `stop_flag = True` are kept"""
         self.index, self.rows, self.proc, self._stop, self.t0 = index, [], None, False, None
@@ -93,7 +93,8 @@ while os.getppid() == parent and time.time() < t_end:
         except Exception:
             uuid = 'none'
         try:
-            self.proc = subprocess.Popen([sys.executable, '-c', self.POLLER, uuid, str(self.index), self.Q], stdout = subprocess.PIPE, stderr = subprocess.DEVNULL, text = True)
+            if os.environ.get('TFX_BENCH_NO_CLOCKS'): raise RuntimeError('clock sampling disabled (diagnosis only: the line is then not a valid bench line)')
+            self.proc = subprocess.Popen([sys.executable, '-c', self.POLLER, uuid, str(self.index), self.Q, str(period)], stdout = subprocess.PIPE, stderr = subprocess.DEVNULL, text = True)
         except Exception:
             self.proc = None
 
@@ -536,7 +537,7 @@ def run_sample_many(args):
     from transfusion_pytorch_b200 import Transfusion, synth
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
     torch.cuda.set_device(dev)
-    sampler = ClockSampler(dev.index or 0)
+    sampler = ClockSampler(dev.index or 0, period = 1.0)      # the loop is host-latency-bound: NVML queries take driver locks, one per second is enough here
     torch.manual_seed(0)
     model = Transfusion(**CTOR).to(dev).eval()
     synth.fill_parameters_(model, seed = 0)

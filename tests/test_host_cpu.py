@@ -256,3 +256,24 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert want == list(argtypes), f'{name}: parameter classes differ: {[w.__name__ for w in want]} vs {[a.__name__ for a in argtypes]}'
         checked += 1
     assert checked >= 35
+
+
+def test_bench_clock_sampler_keeps_the_rows_of_the_timed_region(monkeypatch):
+    """bench.py samples clocks from a separate process that starts long before the timed region: only rows stamped inside [start(), stop] are kept, and a
+    region shorter than a polling period falls back to the nearest sample.  (The real poller talks to NVML; a fake one prints the same row format.)"""
+    import importlib, sys, time
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module('bench')
+    fake = ("import sys, time\nperiod = float(sys.argv[4])\nn = 0\nwhile True:\n"
+            "    print(','.join([repr(time.time()), str(1500 + n), '1965', '700.0', 'Not Active', 'Not Active', 'Not Active', 'Active']), flush = True)\n"
+            "    n += 1; time.sleep(period)\n")
+    monkeypatch.setattr(bench.ClockSampler, 'POLLER', fake)
+    s = bench.ClockSampler(0, period = 0.1)
+    time.sleep(0.6)                      # "warm-up": rows before start() must not count
+    s.start(); time.sleep(0.45); s.stop_flag = True
+    out = s.summary()
+    assert 3 <= out['samples'] <= 6 and out['sm_mhz'] >= 1504 and out['sm_max_mhz'] == 1965 and out['reasons'] == ['sw_power_cap']
+    s = bench.ClockSampler(0, period = 0.2)
+    time.sleep(0.5)
+    s.start(); s.stop_flag = True        # empty region: the nearest sample stands in
+    assert s.summary()['samples'] == 1

@@ -307,6 +307,14 @@ def main():
         ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (4,), model_output_clean = True, transformer = dict(dim = 128, depth = 2, heads = 2))
         times = (torch.rand(3, count_modalities(batch), generator = torch.Generator().manual_seed(7)) * 1.2).clamp(max = 0.999)
         run_interleaved(ref, 'small_clean', ctor, batch, times, seed = 1)
+    if only in ('', 'posemb'):
+        # axial positional embedding (T.py:1383-1403, 2792-2796; MP.py:1003-1046): 2-D latents of different (h, w) per instance, so that the factorised
+        # per-axis tables are evaluated at the batch maximum and sliced per instance.  Upstream package unpinned: the shim's restatement is the oracle.
+        ctor = dict(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (2, 2), add_pos_emb = True, modality_num_dim = 2,
+                    transformer = dict(dim = 128, depth = 2, heads = 2))
+        batch = synth.posemb_batch()
+        times = torch.rand(3, count_modalities(batch), generator = torch.Generator().manual_seed(5))
+        run_interleaved(ref, 'small_posemb', ctor, batch, times, seed = 1)
     if only:
         return
 

@@ -221,6 +221,8 @@ class OracleEngine:
     `model._engine = OracleEngine(model)`).  The product never constructs it."""
 
     def __init__(self, model):
+        if any(getattr(model, 'add_pos_emb', ())):
+            raise NotImplementedError('the CPU checker does not restate the axial positional embedding: that feature is pinned by tests/golden/small_posemb.pt (reference + shim)')
         self.ref = TorchReference(model)
         self.model = model
         self.state = None

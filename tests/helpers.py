@@ -16,6 +16,8 @@ def golden_inputs(name):
     """(batch, times) exactly as oracle/make_golden.py built them."""
     if name in ('small_one_modality', 'small_laser_vres', 'small_velocity', 'small_clean'):
         return synth.small_batch(3, seed = 1, dim_latent = 32, text_vocab = 64)
+    if name == 'small_posemb':
+        return synth.posemb_batch()
     if name == 'small_two_modalities':
         return synth.config4_batch(2, seed = 2, total_len = 300, dims = (32, 16), text_vocab = 64)
     if name == 'config2_b2':

@@ -277,3 +277,45 @@ def test_bench_clock_sampler_keeps_the_rows_of_the_timed_region(monkeypatch):
     time.sleep(0.5)
     s.start(); s.stop_flag = True        # empty region: the nearest sample stands in
     assert s.summary()['samples'] == 1
+
+
+def test_axial_pos_emb_tables_and_pack_coordinates_match_the_reference_module():
+    """`add_pos_emb` (T.py:1383-1403, 2792-2796; MP.py:1003-1046): the engine's factorised tables + coordinate gather reproduce
+    `ContinuousAxialPositionalEmbedding(axial_dims, flatten = True)` per instance (shim restatement of the un-vendored package: parity unpinned upstream),
+    its parameter gradients match autograd, and pack_batch emits the row-major coordinates of every latent row."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'shims'))
+    from axial_positional_embedding import ContinuousAxialPositionalEmbedding
+    from transfusion_pytorch_b200.engine import posemb_tables, posemb_add, posemb_backward
+    torch.manual_seed(0)
+    D = 16
+    ref = ContinuousAxialPositionalEmbedding(D, 2)
+    params = [tuple(p.detach().clone() for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)) for m in ref.mlps]
+    shapes = [(2, 3), (3, 2), (4, 2), (1, 5)]
+    lens = (8, 8)                                         # batch maximum (4, 5) rounded up to a multiple of 8
+    coords = [torch.cat([torch.from_numpy(np.unravel_index(np.arange(h * w), (h, w))[a]) for h, w in shapes]).int() for a in range(2)]
+    rows = torch.zeros(sum(h * w for h, w in shapes), D)
+    tabs = posemb_tables(params, lens, 'cpu')
+    posemb_add(rows, tabs, coords)
+    want = torch.cat([ref(torch.tensor(sh), flatten = True) for sh in shapes])
+    assert torch.allclose(rows, want.detach(), atol = 1e-5)
+    d = torch.randn_like(rows)
+    (want * d).sum().backward()
+    grads = [tuple(torch.zeros_like(p) for p in ps) for ps in params]
+    posemb_backward(d, tabs, coords, params, grads)
+    for m, gs in zip(ref.mlps, grads):
+        for p, g in zip((m[0].weight, m[0].bias, m[2].weight, m[2].bias), gs):
+            assert torch.allclose(g, p.grad, atol = 1e-4, rtol = 1e-4)
+    # pack: coordinates of the compact rows, table lengths
+    model = Transfusion(num_text_tokens = 64, dim_latent = 32, modality_default_shape = (2, 2), add_pos_emb = True, modality_num_dim = 2,
+                        transformer = dict(dim = 128, depth = 2, heads = 2))
+    assert 'pos_emb_mlp.0.mlps.1.2.weight' in model.state_dict() and model.state_dict()['pos_emb_mlp.0.mlps.0.0.weight'].shape == (256, 1)
+    batch = synth.posemb_batch()
+    rb, _ = model.pack(batch, times = torch.rand(3, 2))
+    assert rb.pos_max == ((8, 8),)
+    off = 0
+    for inst in rb.instances:                             # one type: compact rows are the instances in scan order
+        c0, c1 = np.unravel_index(np.arange(inst.length), inst.axial_shape)
+        assert (rb.pos_c0[off:off + inst.length] == c0).all() and (rb.pos_c1[off:off + inst.length] == c1).all()
+        off += inst.length
+    assert off == rb.S and (rb.pos_c2 == -1).all()

@@ -88,7 +88,7 @@ class DataParallelTrainer:
     @staticmethod
     def _signature(rb, eng):
         return (rb.M, rb.B, rb.n_cond, rb.S, tuple(rb.type_rows), tuple(getattr(rb, n).shape[0] if getattr(rb, n) is not None else 0 for n in eng.META_NAMES), rb.total_tokens,
-                tuple(rb.n_type_tokens), (rb.max_rope_pos + 1 + 1023) // 1024, rb.has_labels)
+                tuple(rb.n_type_tokens), (rb.max_rope_pos + 1 + 1023) // 1024, rb.has_labels, rb.pos_max)
 
     def _graph_step(self, rb, device_lat = None, noise = None):
         """Returns the loss of a replayed (or freshly captured) step, or None when this batch must run eagerly.

@@ -41,6 +41,38 @@ def _round_up(x: int, m: int) -> int:
 _EMPTY_I32 = np.zeros(0, dtype = np.int32)
 
 
+# ------------------------------------------------------------------ axial positional embedding (optional: `add_pos_emb`; T.py:1383-1403, 2792-2796; MP.py:1003-1046)
+# One MLP Linear(1, h) -> SiLU -> Linear(h, D) per axis, evaluated on the integer coordinates 0 .. L-1 (L = batch maximum of that axis) and summed over
+# the axes per latent row.  The tables have at most a few hundred rows: plain tensor algebra on the device (not kernels), off every benchmarked path.
+def posemb_tables(params, lens, device):
+    """params: per axis (w0 [h, 1], b0 [h], w2 [D, h], b2 [D]); returns per axis (seq [L, 1], pre [L, h], act [L, h], table [L, D])"""
+    out = []
+    for (w0, b0, w2, b2), L in zip(params, lens):
+        seq = torch.arange(int(L), device = device, dtype = F32)[:, None]
+        pre = seq * w0.reshape(1, -1) + b0
+        act = pre * torch.sigmoid(pre)
+        out.append((seq, pre, act, act @ w2.t() + b2))
+    return out
+
+
+def posemb_add(rows: Tensor, tables, coords):
+    """rows[s] += sum over axes of table_axis[coord_axis[s]]"""
+    for (_, _, _, e), c in zip(tables, coords):
+        rows += e.index_select(0, c)
+
+
+def posemb_backward(d_rows: Tensor, tables, coords, params, grads):
+    """accumulates the parameter gradients (grads: per axis views (gw0, gb0, gw2, gb2)) of the rows' gradient d_rows [n, D] fp32"""
+    for (seq, pre, act, e), c, (w0, b0, w2, b2), (gw0, gb0, gw2, gb2) in zip(tables, coords, params, grads):
+        d_e = torch.zeros_like(e).index_add_(0, c, d_rows)
+        gw2 += d_e.t() @ act
+        gb2 += d_e.sum(0)
+        sig = torch.sigmoid(pre)
+        d_pre = (d_e @ w2) * (sig * (1. + pre * (1. - sig)))
+        gw0 += (d_pre * seq).sum(0)[:, None]
+        gb0 += d_pre.sum(0)
+
+
 class KVCache:
     """Slab kv cache (decode path; reference layout `(layers, 2, batch, heads, seq, dim_head)`, T.py:976-977, 1264, 2260, re-padded and
     concatenated per step there).  Here: per layer one K (post-RoPE) and one V matrix, bf16 `[n_slabs * cap, heads * 64]`, token-major like
@@ -78,6 +110,7 @@ class Engine:
         self.softcap = tr.softcap_value
         self.laser, self.laser_clamp, self.vres = tr.attn_laser, tr.laser_softclamp_value, tr.use_value_residual
         self.clean, self.clean_eps = bool(getattr(model, 'model_output_clean', False)), float(getattr(model, 'eps', 1e-2))
+        self.posemb = tuple(bool(a) for a in getattr(model, 'add_pos_emb', ()))      # per modality type: axial positional embedding on the latent tokens
         self.scale = 64 ** -0.5
         self.dls = list(model.dim_latents)
         self.dlp = [_round_up(d, 8) for d in self.dls]
@@ -158,6 +191,10 @@ class Engine:
 
     def P(self, name):            # parameter tensor by state-dict name
         return self.named[name]
+
+    def _posemb_params(self, t, nax, grads = False):
+        get = self.G if grads else self.P
+        return [tuple(get(f'pos_emb_mlp.{t}.mlps.{a}.{k}') for k in ('0.weight', '0.bias', '2.weight', '2.bias')) for a in range(nax)]
 
     def G(self, name):            # gradient view inside the flat buffer
         o, p = self.offs[name], self.named[name]
@@ -304,7 +341,7 @@ class Engine:
 
     # ------------------------------------------------------------------ descriptor upload
     META_NAMES = ['text_id', 'label', 'kv_limit', 'rope_pos', 'cond_row', 'slot', 'tile_q0', 'tile_qend', 'tile_kv0', 'tile_kvend',
-                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order', 'kv_row', 'p2']
+                  'kt_kv0', 'kt_kvend', 'kt_q0', 'kt_qend', 'row_token', 't2_q0', 't2_qend', 't2_kv0', 't2_kvend', 'k2_kv0', 'k2_kvend', 'k2_q0', 'k2_qend', 'k2_order', 'kv_row', 'p2', 'pos_c0', 'pos_c1', 'pos_c2']
 
     def stage_meta(self, rb: RaggedBatch):
         """All per-token / per-tile int32 metadata and the float metadata of a batch in ONE pooled pinned buffer.
@@ -431,6 +468,12 @@ class Engine:
                         modtok[s0:s1].copy_(x)
                 if has_proj:
                     o.gemm_store(noised, dlp, 0, pk[f'wl2m{t}'], dlp, 0, n, D, dl, modtok[s0:s1], D, None, 0, self.P(f'latent_to_model_projs.{t}.bias'), None, 1.0, 0, 1)
+                if self.posemb and self.posemb[t]:          # + axial positional embedding (T.py:2792-2796)
+                    nax = int(self.model.modality_num_dim[t])
+                    coords = [dv[f'pos_c{a}'][s0:s1] for a in range(nax)]
+                    tabs = posemb_tables(self._posemb_params(t, nax), rb.pos_max[t][:nax], self.device)
+                    posemb_add(modtok[s0:s1], tabs, coords)
+                    st.setdefault('posemb', {})[t] = (tabs, coords)
                 st['noised'].append(noised); st['flow'].append(flow)
         x0 = self.buf(f'{tag}x0', (M, D), F32)
         x0b = self.buf(f'{tag}x0b', (M, D), BF16)
@@ -826,6 +869,10 @@ class Engine:
         if S > 0:
             if self.clean and dneg is not None:           # the clean-prediction flow also depends on the (projected) noised tokens
                 o.add_f32_into_bf16(dmodtok, D, dneg, D, S, D)
+            for t, (tabs, coords) in st.get('posemb', {}).items():      # axial positional embedding: the rows' gradient is the table gradient, scattered by coordinate
+                s0, s1 = rb.type_rows[t]
+                nax = len(tabs)
+                posemb_backward(dmodtok[s0:s1].float(), tabs, coords, self._posemb_params(t, nax), self._posemb_params(t, nax, grads = True))
             for t, (s0, s1) in enumerate(rb.type_rows):
                 n = s1 - s0
                 if n == 0 or f'latent_to_model_projs.{t}.weight' not in self.named:

@@ -92,6 +92,10 @@ class RaggedBatch:
     k2_qend: np.ndarray = None
     p2: np.ndarray = None                   # persistent tcgen05 forward: (first tile of a pair of adjacent 128-row query tiles) * 2 + has_second, heaviest pair first
     k2_order: np.ndarray = None             # 128-key tiles sorted by the number of query tiles that see them (persistent attention backward)
+    pos_c0: np.ndarray = None               # axial positional embedding (add_pos_emb): coordinate of every compact row along axis 0 / 1 / 2 of its instance (-1: none)
+    pos_c1: np.ndarray = None
+    pos_c2: np.ndarray = None
+    pos_max: tuple = None                   # per type: per-axis table lengths (batch maximum, rounded up to a multiple of 8) or None
     kv_row: np.ndarray = None               # kv-cache forward only: cache row each (new) token's key / value is appended at
     single_row_tiles: bool = False          # every attention tile holds exactly one query row (text decode): use the decode kernel
     max_rope_pos: int = 0
@@ -184,7 +188,6 @@ def pack_batch(
     return_embed: bool,
     need_axial_pos_emb: bool = False,
 ) -> RaggedBatch:
-    assert not need_axial_pos_emb, 'axial positional embeddings are outside the B200 hot path (SURVEY.md section 2, row 16)'
     B = len(modalities)
     n_types = model.num_modalities
     times_np = None
@@ -330,6 +333,24 @@ def pack_batch(
         latents = latents, instances = instances, modality_positions = modality_positions,
         total_tokens = int(full_lens.sum()), n_type_tokens = n_type_tokens, max_rope_pos = max_rope, has_labels = return_loss)
     rb.n_valid = int((label >= 0).sum())
+    add_pos = getattr(model, 'add_pos_emb', None)
+    if add_pos is not None and any(add_pos) and instances:
+        # axial positional embedding (T.py:2792-2796; MP.py:1003-1046): row-major coordinates of every latent row inside its instance; the engine
+        # evaluates one factorised table per (type, axis) at the batch maximum and gathers with these
+        coords = [np.full(S, -1, dtype = np.int32) for _ in range(3)]
+        pmax = [None] * n_types
+        for inst in instances:
+            t = inst.modality_type
+            if not add_pos[t]:
+                continue
+            ax = tuple(int(a) for a in inst.axial_shape)
+            assert len(ax) <= 3, 'axial positional embeddings are implemented for up to 3 axes'
+            r0 = int(type_base[t]) + inst.row0
+            for a, c in enumerate(np.unravel_index(np.arange(inst.length), ax)):
+                coords[a][r0:r0 + inst.length] = c
+            pmax[t] = ax if pmax[t] is None else tuple(max(x, y) for x, y in zip(pmax[t], ax))
+        rb.pos_c0, rb.pos_c1, rb.pos_c2 = coords
+        rb.pos_max = tuple(None if m is None else tuple((x + 7) // 8 * 8 for x in m) for m in pmax)
     build_tiles(rb, qfirst)
     return rb
 

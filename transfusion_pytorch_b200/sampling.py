@@ -262,7 +262,8 @@ class SamplingMixin:
                     ys.append(noise.float())
                 slabs = [states.index(st) for st in group]
                 base, ropes = [st.cache_len for st in group], [st.tokens_seen for st in group]
-                placeholder = lambda st: torch.empty(st.dim_latent, st.modality_length) if self.channel_first_latent[st.curr_modality_id] else torch.empty(st.modality_length, st.dim_latent)
+                # (the true axial shape, not the flattened length: the axial positional embedding reads the coordinates off it)
+                placeholder = lambda st: torch.empty(st.dim_latent, *st.modality_shape) if self.channel_first_latent[st.curr_modality_id] else torch.empty(*st.modality_shape, st.dim_latent)
                 samples = [[(st.curr_modality_id, placeholder(st))] for st in group]      # shapes only: the latents live on the device (ODE state)
                 if use_cfg:
                     # unconditional branch: every text token replaced by the null id, earlier modalities at t = 1 - rebuilt per modality round

@@ -49,6 +49,14 @@ def fill_parameters_(module: torch.nn.Module, seed: int = 0, scale: float = 1.0)
     module.load_state_dict(sd)
 
 
+def posemb_batch(seed: int = 77, dim_latent: int = 32, text_vocab: int = 64):
+    """three ragged samples with 2-D latents of different (h, w) per instance: the axial positional embedding fixture (tests/golden/small_posemb.pt)"""
+    g = _gen(seed)
+    txt = lambda n: torch.randint(0, text_vocab, (n,), generator = g)
+    lat = lambda h, w: torch.randn(h, w, dim_latent, generator = g)
+    return [[txt(5), lat(2, 3), txt(4), lat(3, 2), txt(3)], [txt(7), lat(4, 2), txt(2)], [lat(1, 5), txt(6)]]
+
+
 def config2_sample(seed: int, dim_latent: int = 384, text_vocab: int = 256,
                    text_lens = (200, 200, 99), span_len: int = 256):
     """One sample of the graded shape: [text200, latent 256xdl, text200, latent 256xdl, text99]

@@ -175,6 +175,17 @@ class _AttnResidualParams(Module):
         nn.init.normal_(self.pseudo_queries, std = 0.02)
 
 
+class _AxialPosEmb(Module):
+    """parameters of `axial_positional_embedding.ContinuousAxialPositionalEmbedding(dim, num_axial_dims)` (T.py:1398-1401): one MLP
+    `Linear(1, 2 dim) -> SiLU -> Linear(2 dim, dim)` per axis, evaluated on the integer coordinate and summed over the axes.  Holds the
+    parameters only (state-dict layout `mlps.{axis}.{0,2}.{weight,bias}`); the engine evaluates the factorised tables."""
+    def __init__(self, dim, num_axial_dims, mlp_expansion = 2.):
+        super().__init__()
+        self.num_axial_dims = num_axial_dims
+        hidden = int(dim * mlp_expansion)
+        self.mlps = ModuleList([nn.Sequential(nn.Linear(1, hidden), nn.SiLU(), nn.Linear(hidden, dim)) for _ in range(num_axial_dims)])
+
+
 class _Rotary(Module):
     def __init__(self, dim, theta = 10000):
         super().__init__()
@@ -299,8 +310,15 @@ class Transfusion(SamplingMixin, Module):
         assert all(not exists(nd) or not exists(s) or len(s) == nd for nd, s in zip(self.modality_num_dim, self.modality_default_shape))
 
         self.add_pos_emb = cast_tuple(add_pos_emb, self.num_modalities)
-        if any(self.add_pos_emb): raise NotImplementedError('add_pos_emb (axial positional embedding) is outside the B200 hot path')
-        self.pos_emb_mlp = ModuleList([None] * self.num_modalities)
+        assert len(self.add_pos_emb) == self.num_modalities
+        self.pos_emb_mlp = ModuleList([])                # T.py:1383-1403
+        for add, nd in zip(self.add_pos_emb, self.modality_num_dim):
+            if not add:
+                self.pos_emb_mlp.append(None)
+                continue
+            assert exists(nd), '`modality_num_dim` must be set if you wish to automatically inject axial positional embeddings'
+            assert nd <= 3, 'axial positional embeddings are implemented for up to 3 axes'
+            self.pos_emb_mlp.append(_AxialPosEmb(dim, nd))
 
         modality_encoder = cast_tuple(modality_encoder, 1 if exists(modality_encoder) else self.num_modalities)
         modality_decoder = cast_tuple(modality_decoder, 1 if exists(modality_decoder) else self.num_modalities)
@@ -351,7 +369,7 @@ class Transfusion(SamplingMixin, Module):
     def get_modality_info(self, modality_type = None):
         t = default(modality_type, 0)
         return dict(encoder = self.modality_encoder[t], decoder = self.modality_decoder[t], latent_to_model = self.latent_to_model_projs[t],
-                    model_to_latent = self.model_to_latent_projs[t], add_pos_emb = False, pos_emb_mlp = None, num_dim = self.modality_num_dim[t],
+                    model_to_latent = self.model_to_latent_projs[t], add_pos_emb = self.add_pos_emb[t], pos_emb_mlp = self.pos_emb_mlp[t], num_dim = self.modality_num_dim[t],
                     dim_latent = self.dim_latents[t], default_shape = self.modality_default_shape[t], som_id = self.som_ids[t], eom_id = self.eom_ids[t],
                     to_shape_fn = self.to_modality_shape_fn[t], channel_first_latent = self.channel_first_latent[t], modality_type = t)
 
@@ -627,7 +645,7 @@ class Transfusion(SamplingMixin, Module):
             fn = default(num_modalities_to_times_fn, default_modality_length_to_time_fn)
             times = fn(tensor(n_mods))
         process = get_processing_strategy(self.modality_processing)
-        rb = process(samples, times, self, need_axial_pos_emb = False, return_loss = return_loss, return_embed = return_embed)
+        rb = process(samples, times, self, need_axial_pos_emb = any(self.add_pos_emb), return_loss = return_loss, return_embed = return_embed)
         return rb, times
 
     # ------------------------------------------------------------------ main forward (transfusion.py:2925-3450)

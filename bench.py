@@ -85,8 +85,8 @@ while os.getppid() == parent and time.time() < t_end:
 
     def __init__(self, index, period = 0.2):
         """launches the poller at once (interpreter + NVML start-up take a few hundred ms - longer than a 10-step timed region); only the rows stamped
-        between start() and `stop_flag = True` are kept"""
-        self.index, self.rows, self.proc, self._stop, self.t0 = index, [], None, False, None
+        between start() and stop() are kept"""
+        self.index, self.rows, self.proc, self.t0 = index, [], None, None
         try:
             import torch
             uuid = 'GPU-' + str(torch.cuda.get_device_properties(self.index).uuid)
@@ -101,25 +101,21 @@ while os.getppid() == parent and time.time() < t_end:
     def start(self):
         self.t0 = time.time()
 
-    @property
-    def stop_flag(self):
-        return self._stop
-
-    @stop_flag.setter
-    def stop_flag(self, v):           # (kept as an attribute write: `sampler.stop_flag = True` ends the sampling)
-        self._stop = bool(v)
-        if v and self.proc is not None:
-            t1 = time.time()
-            try:
-                self.proc.terminate()
-                out, _ = self.proc.communicate(timeout = 5)
-                rows = [[c.strip() for c in ln.split(',')] for ln in out.strip().splitlines() if ln.strip()]
-                inside = [r[1:] for r in rows if self.t0 is not None and self.t0 - 0.05 <= float(r[0]) <= t1 + 0.05]
-                # a timed region shorter than one polling period: the sample nearest to it (taken under the same load: the warm-up runs the same step)
-                self.rows = inside or [r[1:] for r in rows[-1:]]
-            except Exception:
-                pass
-            self.proc = None
+    def stop(self):
+        """ends the sampling: terminates the poller and keeps the rows stamped inside [start(), now]"""
+        if self.proc is None:
+            return
+        t1 = time.time()
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout = 5)
+            rows = [[c.strip() for c in ln.split(',')] for ln in out.strip().splitlines() if ln.strip()]
+            inside = [r[1:] for r in rows if self.t0 is not None and self.t0 - 0.05 <= float(r[0]) <= t1 + 0.05]
+            # a timed region shorter than one polling period: the sample nearest to it (taken under the same load: the warm-up runs the same step)
+            self.rows = inside or [r[1:] for r in rows[-1:]]
+        except Exception:
+            pass
+        self.proc = None
 
     def summary(self):
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
@@ -358,7 +354,7 @@ def run_b200_arm(args):
     host_enqueue_ms = timed.host_ms
     launches = eng.ops.launches - l0
     if sampler:
-        sampler.stop_flag = True
+        sampler.stop()
     ms_step = ms_total / args.steps
     log('resident ms/step', ms_step)
     value = world * B * SEQ / (ms_step / 1e3)
@@ -559,7 +555,7 @@ def run_sample_many(args):
         out = model.sample_many(copy.deepcopy(prompts), **kw)          # host prompts in, host samples out: H2D / D2H inside the timed region
         e1.record(); torch.cuda.synchronize()
         times_ms.append((1e3 * (time.perf_counter() - t0), e0.elapsed_time(e1)))
-    sampler.stop_flag = True
+    sampler.stop()
     launches = (eng.ops.launches - l0) // args.steps
     # one more (untimed) call with CUDA events around every text loop / modality round: where the wall time goes
     model._sampling_timer = {}

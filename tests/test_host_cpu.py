@@ -270,12 +270,12 @@ def test_bench_clock_sampler_keeps_the_rows_of_the_timed_region(monkeypatch):
     monkeypatch.setattr(bench.ClockSampler, 'POLLER', fake)
     s = bench.ClockSampler(0, period = 0.1)
     time.sleep(0.6)                      # "warm-up": rows before start() must not count
-    s.start(); time.sleep(0.45); s.stop_flag = True
+    s.start(); time.sleep(0.45); s.stop()
     out = s.summary()
     assert 3 <= out['samples'] <= 6 and out['sm_mhz'] >= 1504 and out['sm_max_mhz'] == 1965 and out['reasons'] == ['sw_power_cap']
     s = bench.ClockSampler(0, period = 0.2)
     time.sleep(0.5)
-    s.start(); s.stop_flag = True        # empty region: the nearest sample stands in
+    s.start(); s.stop()                  # empty region: the nearest sample stands in
     assert s.summary()['samples'] == 1
 
 
